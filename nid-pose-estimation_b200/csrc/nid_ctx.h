@@ -1,0 +1,119 @@
+// Internal context layout shared by the kernels TU, the C-ABI TU and the LM driver.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nid_b200.h"
+
+namespace nid {
+
+// Everything the evaluation kernels need; passed by value (fits the 4 KB parameter space easily).
+struct EvalParams {
+  int rows, cols, cell, bins, rb, cb, N, ncell;  // ncell = cell*cell
+  int job0;        // first job handled by this launch
+  int S;           // strips per cell (CTAs per cell and job)
+  int strip_rows;  // rows of a cell handled by one strip
+  int hist_stride; // bins*bins + bins
+  // per pair [n_pairs][...]
+  const double* pwx;
+  const double* pwy;
+  const double* pwz;
+  const uint8_t* im0;
+  const uint8_t* im1;
+  const uint8_t* inb0;
+  const int* n_c;       // [n_pairs][ncell]
+  const double* href;   // [n_pairs][ncell]
+  const double* cam;    // [n_pairs][4]
+  // reference-intensity lookup (depends on bins only)
+  const double* lut_w;  // [256][4]
+  const int* lut_k;     // [256]
+  // per job
+  const double* poses;  // [jobs][16]
+  const int* job_pair;  // [jobs]
+  double* part;         // [jobs][ncell][S][hist_stride]
+  double* jpart;        // [jobs][ncell][S][6]
+  double* hist;         // [jobs][ncell][hist_stride] normalised P_j | P_t of the last eval
+  double* ht;           // [jobs][ncell]
+  double* hj;
+  double* err;
+  double* der;          // [jobs][ncell][6]
+  double* gn;           // [jobs][44] : chi2, H[36], b[6], n_active
+  double huber_delta;
+  double huber_dsqr;
+};
+
+}  // namespace nid
+
+struct nid_ctx {
+  int device = 0;
+  int rows = 0, cols = 0, cell = 0, bins = 0, degree = 3;
+  int N = 0, ncell = 0, rb = 0, cb = 0;
+  int n_pairs = 0, max_jobs = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+
+  // per pair
+  double *pwx = nullptr, *pwy = nullptr, *pwz = nullptr;
+  uint8_t *im0 = nullptr, *im1 = nullptr, *inb0 = nullptr;
+  int* n_c = nullptr;
+  double* href = nullptr;
+  double* cam = nullptr;
+  double* Twc0 = nullptr;      // [n_pairs][16]
+  unsigned int* cnt = nullptr; // [n_pairs][ncell][256] reference intensity counts (in-bounds at prepare)
+  std::vector<char> pair_set, pair_prepared;
+  // staging
+  double* d_depth = nullptr;   // [N] scratch
+  double* d_img64 = nullptr;   // [N] scratch for the f64 image entry point
+  int* d_flag = nullptr;
+  double* d_pix = nullptr;     // [8N] scratch for nid_warp_sample_f64
+  float* d_pix4 = nullptr;     // [4N] scratch for nid_warp_sample
+  double* d_bsv = nullptr;     // [4N] scratch for nid_get_ref_weights
+  int* d_bsi = nullptr;        // [N]
+  // luts
+  double* lut_w = nullptr;
+  int* lut_k = nullptr;
+  // per job
+  double* poses = nullptr;
+  int* job_pair = nullptr;
+  double *part = nullptr, *jpart = nullptr, *hist = nullptr;
+  double *ht = nullptr, *hj = nullptr, *err = nullptr, *der = nullptr, *gn = nullptr;
+  double* hard = nullptr;      // [jobs][ncell+1]
+  size_t part_slots = 0;       // capacity in (job,strip) units
+  // pinned host mirrors
+  double* h_poses = nullptr;
+  int* h_job_pair = nullptr;
+  double* h_out = nullptr;     // [max_jobs][ncell*8 + 44]
+  int opt_force_strips = 0;
+  double* lm_trace = nullptr;  // set by nid_solve for the duration of one call
+  int lm_trace_cap = 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int opt_time_kernels = 0;
+  cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double kernel_ms[4] = {0, 0, 0, 0};  // k_hist, k_jac, k_jac_final, k_entropy
+  long long kernel_calls[4] = {0, 0, 0, 0};
+};
+
+namespace nid {
+void set_error(const std::string& s);
+int check_cuda(cudaError_t e, const char* what);
+EvalParams make_params(nid_ctx* c, int n_jobs);
+
+// kernel launchers (nid_kernels.cu)
+int launch_build_lut(nid_ctx* c);
+int launch_points(nid_ctx* c, int pair);
+int launch_prepare(nid_ctx* c, int pair, const double* d_pose16);
+int launch_ref_weights(nid_ctx* c, int pair);
+int launch_points_aos(nid_ctx* c, int pair, double* d_out);
+int launch_eval(nid_ctx* c, int n_jobs, int want_jac);
+int launch_gn(nid_ctx* c, int n_jobs, double delta);
+int launch_hard(nid_ctx* c, int n_jobs);
+int launch_warp_sample(nid_ctx* c, int pair, const double* d_pose16, int f64);
+int launch_check_integral(nid_ctx* c, const double* d_src, uint8_t* d_dst, int is_ref);
+int launch_chi2(nid_ctx* c, int n_jobs, double delta);
+int launch_eval_mixed(nid_ctx* c, int nj, int nt, double delta);
+int launch_points_soa(nid_ctx* c, int pair, const double* d_in);
+int launch_import_flags(nid_ctx* c, int pair, const double* d_bsv);
+}  // namespace nid

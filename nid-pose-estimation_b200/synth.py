@@ -90,7 +90,7 @@ class _Scene:
         dc = np.stack([(c - cx) / fx, (r - cy) / fy, np.ones_like(c)], axis=-1)
         d = dc @ R.T
         s = np.full((rows, cols), (self.z0 - t[2]))
-        for _ in range(25):
+        for _ in range(8):
             X = t[0] + s * d[..., 0]
             Y = t[1] + s * d[..., 1]
             g = t[2] + s * d[..., 2] - self.height(X, Y)
