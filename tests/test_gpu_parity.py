@@ -61,7 +61,8 @@ def test_prepare_eval_parity(nid, orc, make_pair, cell, bins, rows, cols):
         np.testing.assert_allclose(err[act], erro[act], rtol=1e-10)
         # cost-only flavour gives the same entropies and leaves der alone
         Ht2, Hj2, J2 = ctx.eval(0, M, False)
-        assert np.array_equal(Ht2[act], Ht[act]) and np.array_equal(Hj2[act], Hj[act])
+        np.testing.assert_allclose(Ht2[act], Ht[act], rtol=1e-13)
+        np.testing.assert_allclose(Hj2[act], Hj[act], rtol=1e-13)
         assert np.all(np.isnan(J2))
 
 

@@ -20,10 +20,11 @@ def test_reference_cuda_vs_oracle_vs_ours(nid, orc, synth, cell, bins):
     bv, bi = P.ref_weights()
     R = ref_gpu.RefGpu(p, cell, bins)
     # a1: Calculate3Dpoint
-    assert np.array_equal(R.points3d(), P.points3d(), equal_nan=True)
+    # (nvcc fuses the reference's multiply-adds, the oracle and this library do not: last-bit agreement)
+    np.testing.assert_allclose(R.points3d(), P.points3d(), rtol=4e-16, atol=1e-15)
     ctx = nid.Context(p.rows, p.cols, cell, bins)
     ctx.set_pair(0, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
-    assert np.array_equal(ctx.points3d(0), R.points3d(), equal_nan=True)
+    assert np.array_equal(ctx.points3d(0), P.points3d(), equal_nan=True)
     nc2, href2 = ctx.prepare(0, orc.se3_to_mat16(pose0))
     assert np.array_equal(nc, nc2)
     R.set_prepare(nc, bv, bi, np.where(np.isnan(href), 0.0, href))
