@@ -148,7 +148,9 @@ void* nid_stream(nid_ctx* ctx);
  * device time between them (synchronises on the stop event). */
 int nid_event_record(nid_ctx* ctx, int slot);
 int nid_event_elapsed_ms(nid_ctx* ctx, float* ms);
-/* options: "force_strips" (CTAs per cell and job; 0 = automatic); "time_kernels" (1: bracket every kernel
+/* options: "path" (0 automatic, 1 natural-order kernels, 2 sorted kernels); "keep_hist" (1: keep the
+ * normalised histograms of every evaluation for nid_debug_hist);
+ * "force_strips" (natural path: CTAs per cell and job; 0 = automatic); "time_kernels" (1: bracket every kernel
  * of nid_eval_staged / nid_eval_jobs with CUDA events and accumulate per-kernel device time; resets) */
 int nid_set_option(nid_ctx* ctx, const char* key, int value);
 

@@ -56,15 +56,53 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.n_c = c->n_c; p.href = c->href; p.cam = c->cam;
   p.lut_w = c->lut_w; p.lut_k = c->lut_k;
   p.poses = c->poses; p.job_pair = c->job_pair;
-  p.part = c->part; p.jpart = c->jpart; p.hist = c->hist;
+  const bool sorted = use_sorted(c);
+  p.part = c->part; p.jpart = sorted ? c->jpart_s : c->jpart; p.hist = c->opt_keep_hist ? c->hist : nullptr;
   p.ht = c->ht; p.hj = c->hj; p.err = c->err; p.der = c->der; p.gn = c->gn;
+  p.sx = c->sx; p.sy = c->sy; p.sz = c->sz;
+  p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start;
+  p.max_tasks = c->max_tasks; p.g_stride = (int)c->g_stride;
+  p.G = c->G; p.wv = c->wv;
   return p;
+}
+
+// The sorted path pays a fixed cost per (cell, class) segment; below ~12 pixels per segment on average
+// (e.g. the reference's default 16x16 cells at 640x480) the natural-order kernels are used instead.
+bool use_sorted(const nid_ctx* c) {
+  if (c->opt_path == 1) return false;
+  if (c->opt_path == 2) return true;
+  return (double)c->N / ((double)c->ncell * NID_NCLS) >= 12.0;
 }
 
 template <typename T>
 static int dalloc(T** p, size_t n, const char* what) {
   cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (n ? n : 1));
   if (e != cudaSuccess) return check_cuda(e, what);
+  return NID_OK;
+}
+
+// per-job scratch of the active path, allocated on first use / grown when a pair with more tasks is prepared
+int ensure_job_buffers(nid_ctx* c) {
+  const size_t J = c->max_jobs, NC = c->ncell;
+  const size_t hs = (size_t)c->bins * c->bins + c->bins;
+  if (c->opt_keep_hist && !c->hist) OKR(dalloc(&c->hist, J * NC * hs, "hist"));
+  if (use_sorted(c)) {
+    const size_t need = (size_t)std::max(c->max_ntasks_prepared, 1);
+    if (c->g_stride < need) {
+      CU(cudaStreamSynchronize(c->stream), "sync before growing job buffers");
+      if (c->G) cudaFree(c->G);
+      if (c->jpart_s) cudaFree(c->jpart_s);
+      c->G = nullptr; c->jpart_s = nullptr;
+      OKR(dalloc(&c->G, J * need * c->bins, "G"));
+      OKR(dalloc(&c->jpart_s, J * need * 6, "jpart_s"));
+      c->g_stride = need;
+    }
+    if (!c->wv) OKR(dalloc(&c->wv, J * NC * hs, "wv"));
+  } else if (!c->part) {
+    c->part_slots = J + 2 * (size_t)c->sm_count + 64;
+    OKR(dalloc(&c->part, c->part_slots * NC * hs, "part"));
+    OKR(dalloc(&c->jpart, c->part_slots * NC * 6, "jpart"));
+  }
   return NID_OK;
 }
 
@@ -134,14 +172,19 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   OKR(dalloc(&c->im0, P * N, "im0")); OKR(dalloc(&c->im1, P * N, "im1")); OKR(dalloc(&c->inb0, P * N, "inb0"));
   OKR(dalloc(&c->n_c, P * NC, "n_c")); OKR(dalloc(&c->href, P * NC, "href"));
   OKR(dalloc(&c->cam, P * 4, "cam")); OKR(dalloc(&c->Twc0, P * 16, "Twc0"));
-  OKR(dalloc(&c->cnt, P * NC * 256, "cnt"));
+  OKR(dalloc(&c->cnt, P * NC * NID_NCLS, "cnt"));
+  c->max_tasks = (int)(N / NID_TASK_PX + NC * NID_NCLS + 1);
+  OKR(dalloc(&c->sx, P * N, "sx")); OKR(dalloc(&c->sy, P * N, "sy")); OKR(dalloc(&c->sz, P * N, "sz"));
+  OKR(dalloc(&c->tasks, P * (size_t)c->max_tasks, "tasks"));
+  OKR(dalloc(&c->ntasks, P, "ntasks"));
+  CU(cudaMemset(c->ntasks, 0, sizeof(int) * P), "memset ntasks");
+  OKR(dalloc(&c->cell_task_start, P * (NC + 1), "cell_task_start"));
+  OKR(dalloc(&c->seg_start, P * (NC * NID_NCLS + 1), "seg_start"));
+  c->h_ntasks.assign(P, 0);
   OKR(dalloc(&c->d_depth, N, "d_depth")); OKR(dalloc(&c->d_img64, N, "d_img64")); OKR(dalloc(&c->d_flag, 1, "d_flag"));
   OKR(dalloc(&c->lut_w, 256 * 4, "lut_w")); OKR(dalloc(&c->lut_k, 256, "lut_k"));
   OKR(dalloc(&c->poses, J * 16, "poses")); OKR(dalloc(&c->job_pair, J, "job_pair"));
-  c->part_slots = J + 2 * (size_t)c->sm_count + 64;
-  OKR(dalloc(&c->part, c->part_slots * NC * hs, "part"));
-  OKR(dalloc(&c->jpart, c->part_slots * NC * 6, "jpart"));
-  OKR(dalloc(&c->hist, J * NC * hs, "hist"));
+  (void)hs;
   OKR(dalloc(&c->ht, J * NC, "ht")); OKR(dalloc(&c->hj, J * NC, "hj")); OKR(dalloc(&c->err, J * NC, "err"));
   OKR(dalloc(&c->der, J * NC * 6, "der")); OKR(dalloc(&c->gn, J * 44, "gn"));
   OKR(dalloc(&c->hard, J * (NC + 1), "hard"));
@@ -151,6 +194,7 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   c->pair_set.assign(P, 0);
   c->pair_prepared.assign(P, 0);
   OKR(launch_build_lut(c));
+  OKR(sorted_init(c));
   CU(cudaStreamSynchronize(c->stream), "sync after lut");
   *out = c;
   return NID_OK;
@@ -162,7 +206,8 @@ int nid_destroy(nid_ctx* c) {
   cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->pwx, c->pwy, c->pwz, c->im0, c->im1, c->inb0, c->n_c, c->href, c->cam, c->Twc0, c->cnt, c->d_depth,
                   c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
-                  c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard};
+                  c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
+                  c->sx, c->sy, c->sz, c->tasks, c->ntasks, c->cell_task_start, c->seg_start, c->G, c->wv, c->jpart_s};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->h_poses) cudaFreeHost(c->h_poses);
   if (c->h_job_pair) cudaFreeHost(c->h_job_pair);
@@ -204,6 +249,7 @@ int nid_set_pair(nid_ctx* c, int pair, const double* depth, const uint8_t* im0, 
 }
 
 static int upload_images_f64(nid_ctx* c, int pair, const double* im0, const double* im1);
+static int build_sorted_layout(nid_ctx* c, int pair);
 
 int nid_set_pair_f64(nid_ctx* c, int pair, const double* depth, const double* im0, const double* im1,
                      const double T_wc0[16], const double intr[5]) {
@@ -260,6 +306,9 @@ int nid_import_prepare(nid_ctx* c, int pair, const double* bs_value, const int* 
   OKR(launch_import_flags(c, pair, c->d_bsv));
   CU(cudaMemcpyAsync(c->n_c + pair * c->ncell, bs_counter, sizeof(int) * c->ncell, cudaMemcpyDefault, c->stream), "H2D n_c");
   CU(cudaMemcpyAsync(c->href + pair * c->ncell, Href, sizeof(double) * c->ncell, cudaMemcpyDefault, c->stream), "H2D href");
+  CU(cudaMemsetAsync(c->cnt + (size_t)pair * c->ncell * NID_NCLS, 0, sizeof(unsigned int) * c->ncell * NID_NCLS, c->stream), "memset cnt");
+  OKR(launch_count_classes(c, pair));
+  OKR(build_sorted_layout(c, pair));
   CU(cudaStreamSynchronize(c->stream), "sync import");
   c->pair_prepared[pair] = 1;
   return NID_OK;
@@ -283,6 +332,51 @@ int nid_get_points3d(nid_ctx* c, int pair, double* points_3d) {
   return NID_OK;
 }
 
+// Regroup the pair's valid pixels by (cell, reference class) and cut the segments into warp tasks. The
+// class counts come from the device; offsets and the task table are integer bookkeeping done here.
+static int build_sorted_layout(nid_ctx* c, int pair) {
+  const int NC = c->ncell;
+  std::vector<unsigned int> cnt((size_t)NC * NID_NCLS);
+  CU(cudaMemcpyAsync(cnt.data(), c->cnt + (size_t)pair * NC * NID_NCLS, sizeof(unsigned int) * cnt.size(),
+                     cudaMemcpyDeviceToHost, c->stream), "D2H cnt");
+  CU(cudaStreamSynchronize(c->stream), "sync cnt");
+  std::vector<int> seg((size_t)NC * NID_NCLS + 1), cts(NC + 1);
+  std::vector<int2> tasks;
+  tasks.reserve(c->max_tasks);
+  int off = 0;
+  for (int cell = 0; cell < NC; cell++) {
+    cts[cell] = (int)tasks.size();
+    for (int v = 0; v < NID_NCLS; v++) {
+      const int len = (int)cnt[(size_t)cell * NID_NCLS + v];
+      seg[(size_t)cell * NID_NCLS + v] = off;
+      for (int o = 0; o < len; o += NID_TASK_PX) {
+        int2 t;
+        t.x = off + o;
+        t.y = std::min(NID_TASK_PX, len - o) | (v << 9) | (cell << 18);
+        tasks.push_back(t);
+      }
+      off += len;
+    }
+  }
+  seg[(size_t)NC * NID_NCLS] = off;
+  cts[NC] = (int)tasks.size();
+  const int nt = (int)tasks.size();
+  if (nt > c->max_tasks || NC > 0x3fff) { set_error("task table overflow"); return NID_ERR_STATE; }
+  CU(cudaMemcpyAsync(c->seg_start + (size_t)pair * (NC * NID_NCLS + 1), seg.data(), sizeof(int) * seg.size(),
+                     cudaMemcpyHostToDevice, c->stream), "H2D seg_start");
+  if (nt) CU(cudaMemcpyAsync(c->tasks + (size_t)pair * c->max_tasks, tasks.data(), sizeof(int2) * nt,
+                             cudaMemcpyHostToDevice, c->stream), "H2D tasks");
+  CU(cudaMemcpyAsync(c->cell_task_start + (size_t)pair * (NC + 1), cts.data(), sizeof(int) * (NC + 1),
+                     cudaMemcpyHostToDevice, c->stream), "H2D cell_task_start");
+  CU(cudaMemcpyAsync(c->ntasks + pair, &nt, sizeof(int), cudaMemcpyHostToDevice, c->stream), "H2D ntasks");
+  OKR(launch_scatter(c, pair));
+  CU(cudaStreamSynchronize(c->stream), "sync scatter");  // host vectors go out of scope
+  c->h_ntasks[pair] = nt;
+  c->max_ntasks_prepared = 0;
+  for (int v : c->h_ntasks) c->max_ntasks_prepared = std::max(c->max_ntasks_prepared, v);
+  return NID_OK;
+}
+
 int nid_prepare(nid_ctx* c, int pair, const double T_cw1[16], int* bs_counter, double* Href) {
   if (!c || pair < 0 || pair >= c->n_pairs || !T_cw1) { set_error("bad argument"); return NID_ERR_ARG; }
   if (!c->pair_set[pair]) { set_error("pair not set"); return NID_ERR_STATE; }
@@ -290,6 +384,8 @@ int nid_prepare(nid_ctx* c, int pair, const double T_cw1[16], int* bs_counter, d
   memcpy(c->h_poses, T_cw1, sizeof(double) * 16);
   CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream), "H2D pose");
   OKR(launch_prepare(c, pair, c->poses));
+  OKR(launch_href(c, pair));
+  OKR(build_sorted_layout(c, pair));
   int* h_nc = (int*)c->h_out;
   double* h_href = c->h_out + c->ncell;  // ncell ints fit in ncell doubles
   CU(cudaMemcpyAsync(h_nc, c->n_c + pair * c->ncell, sizeof(int) * c->ncell, cudaMemcpyDeviceToHost, c->stream), "D2H n_c");
@@ -551,6 +647,7 @@ int nid_warp_sample_f64(nid_ctx* c, int pair, const double T_cw1[16], double* ou
 int nid_debug_hist(nid_ctx* c, int job, int cell_index, double* P_t, double* P_j) {
   if (!c || job < 0 || job >= c->max_jobs || cell_index < 0 || cell_index >= c->ncell) { set_error("bad argument"); return NID_ERR_ARG; }
   const size_t hs = (size_t)c->bins * c->bins + c->bins;
+  if (!c->hist) { set_error("set option keep_hist=1 before the evaluation"); return NID_ERR_STATE; }
   const double* src = c->hist + ((size_t)job * c->ncell + cell_index) * hs;
   CU(cudaStreamSynchronize(c->stream), "sync");
   if (P_j) CU(cudaMemcpy(P_j, src, sizeof(double) * c->bins * c->bins, cudaMemcpyDeviceToHost), "D2H P_j");
@@ -585,6 +682,12 @@ int nid_event_elapsed_ms(nid_ctx* c, float* ms) {
 int nid_set_option(nid_ctx* c, const char* key, int value) {
   if (!c || !key) { set_error("bad argument"); return NID_ERR_ARG; }
   if (!strcmp(key, "force_strips")) { c->opt_force_strips = value; return NID_OK; }
+  if (!strcmp(key, "path")) {
+    if (value < 0 || value > 2) { set_error("path must be 0 (auto), 1 (natural) or 2 (sorted)"); return NID_ERR_ARG; }
+    c->opt_path = value;
+    return NID_OK;
+  }
+  if (!strcmp(key, "keep_hist")) { c->opt_keep_hist = value; return NID_OK; }
   if (!strcmp(key, "time_kernels")) {
     c->opt_time_kernels = value;
     for (int i = 0; i < 4; i++) { c->kernel_ms[i] = 0; c->kernel_calls[i] = 0; }

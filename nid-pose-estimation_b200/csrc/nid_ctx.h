@@ -7,6 +7,9 @@
 
 #include "../../include/nid_b200.h"
 
+#define NID_NCLS 257  /* reference-intensity classes 0..255 + 256 = valid point without reference sample */
+#define NID_TASK_PX 256 /* pixels per warp task of the sorted path */
+
 namespace nid {
 
 // Everything the evaluation kernels need; passed by value (fits the 4 KB parameter space easily).
@@ -42,6 +45,17 @@ struct EvalParams {
   double* gn;           // [jobs][44] : chi2, H[36], b[6], n_active
   double huber_delta;
   double huber_dsqr;
+  // sorted path
+  const double* sx;     // [n_pairs][N] world points regrouped by (cell, class)
+  const double* sy;
+  const double* sz;
+  const int2* tasks;    // [n_pairs][max_tasks] {start, count | cls<<9 | cell<<18}
+  const int* ntasks;    // [n_pairs]
+  const int* cell_task_start;  // [n_pairs][ncell+1]
+  int max_tasks;        // task-table stride per pair
+  int g_stride;         // partial-buffer stride per job (tasks)
+  double* G;            // [jobs][g_stride][bins]
+  double* wv;           // [jobs][ncell][bins*bins+bins]
 };
 
 }  // namespace nid
@@ -62,7 +76,21 @@ struct nid_ctx {
   double* href = nullptr;
   double* cam = nullptr;
   double* Twc0 = nullptr;      // [n_pairs][16]
-  unsigned int* cnt = nullptr; // [n_pairs][ncell][256] reference intensity counts (in-bounds at prepare)
+  unsigned int* cnt = nullptr; // [n_pairs][ncell][NID_NCLS] pixel counts per reference class at prepare
+  // sorted path, per pair
+  double *sx = nullptr, *sy = nullptr, *sz = nullptr;
+  int2* tasks = nullptr;
+  int* ntasks = nullptr;
+  int* cell_task_start = nullptr;
+  int* seg_start = nullptr;    // [n_pairs][ncell*NID_NCLS+1]
+  int max_tasks = 0;
+  std::vector<int> h_ntasks;
+  int max_ntasks_prepared = 0;
+  // sorted path, per job (grown on demand)
+  double *G = nullptr, *wv = nullptr, *jpart_s = nullptr;
+  size_t g_stride = 0;
+  int opt_path = 0;            // 0 auto, 1 natural-order atomics (v1), 2 sorted
+  int opt_keep_hist = 0;
   std::vector<char> pair_set, pair_prepared;
   // staging
   double* d_depth = nullptr;   // [N] scratch
@@ -91,7 +119,7 @@ struct nid_ctx {
   int lm_trace_cap = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int opt_time_kernels = 0;
-  cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t kev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   double kernel_ms[4] = {0, 0, 0, 0};  // k_hist, k_jac, k_jac_final, k_entropy
   long long kernel_calls[4] = {0, 0, 0, 0};
 };
@@ -101,6 +129,32 @@ void set_error(const std::string& s);
 int check_cuda(cudaError_t e, const char* what);
 EvalParams make_params(nid_ctx* c, int n_jobs);
 
+// optional per-kernel stopwatch (option "time_kernels"): events between the launches of one evaluation
+inline void ktime_mark(nid_ctx* c, int i) {
+  if (!c->opt_time_kernels) return;
+  if (!c->kev[i]) cudaEventCreate(&c->kev[i]);
+  cudaEventRecord(c->kev[i], c->stream);
+}
+inline void ktime_collect(nid_ctx* c, int n, const int* slot) {
+  if (!c->opt_time_kernels) return;
+  cudaEventSynchronize(c->kev[n]);
+  for (int i = 0; i < n; i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]);
+    c->kernel_ms[slot[i]] += ms;
+    c->kernel_calls[slot[i]]++;
+  }
+}
+bool use_sorted(const nid_ctx* c);
+int ensure_job_buffers(nid_ctx* c);
+
+// sorted path (nid_sorted.cu)
+int sorted_init(nid_ctx* c);
+int launch_count_classes(nid_ctx* c, int pair);
+int launch_scatter(nid_ctx* c, int pair);
+int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int want_jac);
+int launch_href(nid_ctx* c, int pair);
+
 // kernel launchers (nid_kernels.cu)
 int launch_build_lut(nid_ctx* c);
 int launch_points(nid_ctx* c, int pair);
@@ -108,6 +162,7 @@ int launch_prepare(nid_ctx* c, int pair, const double* d_pose16);
 int launch_ref_weights(nid_ctx* c, int pair);
 int launch_points_aos(nid_ctx* c, int pair, double* d_out);
 int launch_eval(nid_ctx* c, int n_jobs, int want_jac);
+int launch_eval_natural(nid_ctx* c, int n_jobs, int want_jac);
 int launch_gn(nid_ctx* c, int n_jobs, double delta);
 int launch_hard(nid_ctx* c, int n_jobs);
 int launch_warp_sample(nid_ctx* c, int pair, const double* d_pose16, int f64);

@@ -109,11 +109,13 @@ __global__ void k_prepare(EvalParams p, int pair, const double* __restrict__ pos
     if (!isnan(x0) && row < p.rb * p.cell && col < p.cb * p.cell) {
       double x1, y1, z1, u, v;
       warp_project(P, cam, x0, p.pwy[base + i], p.pwz[base + i], x1, y1, z1, u, v);
+      int key = 256;  // valid point, no reference sample
       if (inb_cost(u, v, p.rows, p.cols)) {
         flag = 1;
-        int c = (row / p.rb) * p.cell + (col / p.cb);
-        atomicAdd(&cnt[((size_t)pair * p.ncell + c) * 256 + p.im0[base + i]], 1u);
+        key = p.im0[base + i];
       }
+      int c = (row / p.rb) * p.cell + (col / p.cb);
+      atomicAdd(&cnt[((size_t)pair * p.ncell + c) * NID_NCLS + key], 1u);
     }
     inb0[base + i] = flag;
   }
@@ -128,7 +130,7 @@ __global__ void k_href(EvalParams p, int pair, const unsigned int* __restrict__ 
   __shared__ unsigned int s_cnt[256];
   __shared__ int s_n;
   const int c = blockIdx.x;
-  const unsigned int* cc = cnt + ((size_t)pair * p.ncell + c) * 256;
+  const unsigned int* cc = cnt + ((size_t)pair * p.ncell + c) * NID_NCLS;
   const int t = threadIdx.x;
   s_cnt[t] = cc[t];
   __syncthreads();
@@ -601,10 +603,15 @@ int launch_check_integral(nid_ctx* c, const double* d_src, uint8_t* d_dst, int i
 
 int launch_prepare(nid_ctx* c, int pair, const double* d_pose16) {
   EvalParams p = make_params(c, 1);
-  cudaError_t e = cudaMemsetAsync(c->cnt + (size_t)pair * c->ncell * 256, 0, sizeof(unsigned int) * c->ncell * 256, c->stream);
+  cudaError_t e = cudaMemsetAsync(c->cnt + (size_t)pair * c->ncell * NID_NCLS, 0, sizeof(unsigned int) * c->ncell * NID_NCLS, c->stream);
   if (e != cudaSuccess) return check_cuda(e, "memset cnt");
   k_prepare<<<grid_for(c->N, 256, c->sm_count * 8), 256, 0, c->stream>>>(p, pair, d_pose16, c->inb0, c->cnt);
   NID_LAUNCH_CHECK(c, "k_prepare");
+  return NID_OK;
+}
+
+int launch_href(nid_ctx* c, int pair) {
+  EvalParams p = make_params(c, 1);
   k_href<<<c->ncell, 256, sizeof(double) * c->bins, c->stream>>>(p, pair, c->cnt, c->n_c, c->href);
   NID_LAUNCH_CHECK(c, "k_href");
   return NID_OK;
@@ -617,24 +624,14 @@ int launch_ref_weights(nid_ctx* c, int pair) {
   return NID_OK;
 }
 
-// optional per-kernel stopwatch (option "time_kernels"): events between the launches of one evaluation
-static void ktime_mark(nid_ctx* c, int i) {
-  if (!c->opt_time_kernels) return;
-  if (!c->kev[i]) cudaEventCreate(&c->kev[i]);
-  cudaEventRecord(c->kev[i], c->stream);
-}
-static void ktime_collect(nid_ctx* c, int n, const int* slot) {
-  if (!c->opt_time_kernels) return;
-  cudaEventSynchronize(c->kev[n]);
-  for (int i = 0; i < n; i++) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]);
-    c->kernel_ms[slot[i]] += ms;
-    c->kernel_calls[slot[i]]++;
-  }
+int launch_eval(nid_ctx* c, int n_jobs, int want_jac) {
+  int r = ensure_job_buffers(c);
+  if (r != NID_OK) return r;
+  if (use_sorted(c)) return launch_eval_sorted(c, 0, n_jobs, n_jobs, want_jac);
+  return launch_eval_natural(c, n_jobs, want_jac);
 }
 
-int launch_eval(nid_ctx* c, int n_jobs, int want_jac) {
+int launch_eval_natural(nid_ctx* c, int n_jobs, int want_jac) {
   EvalParams p = make_params(c, n_jobs);
   const size_t smem = sizeof(double) * p.hist_stride;
   dim3 g1(p.S, p.ncell, n_jobs);
@@ -666,26 +663,37 @@ int launch_eval(nid_ctx* c, int n_jobs, int want_jac) {
 // LM lockstep round: jobs [0,nj) want cost+Jacobian+GN block, jobs [nj,nj+nt) want the robust cost only
 int launch_eval_mixed(nid_ctx* c, int nj, int nt, double delta) {
   const int na = nj + nt;
+  int r = ensure_job_buffers(c);
+  if (r != NID_OK) return r;
   EvalParams p = make_params(c, na);
   p.huber_delta = delta;
   p.huber_dsqr = (double)(float)(delta * delta);  // `float dsqr`, robust_kernel_impl.h:84
-  const size_t smem = sizeof(double) * p.hist_stride;
-  k_hist<<<dim3(p.S, p.ncell, na), 256, smem, c->stream>>>(p);
-  NID_LAUNCH_CHECK(c, "k_hist");
+  EvalParams q = p;
+  q.job0 = nj;
+  if (use_sorted(c)) {
+    if (nj > 0) { r = launch_eval_sorted(c, 0, nj, na, 1); if (r != NID_OK) return r; }
+    if (nt > 0) { r = launch_eval_sorted(c, nj, nt, na, 0); if (r != NID_OK) return r; }
+  } else {
+    const size_t smem = sizeof(double) * p.hist_stride;
+    k_hist<<<dim3(p.S, p.ncell, na), 256, smem, c->stream>>>(p);
+    NID_LAUNCH_CHECK(c, "k_hist");
+    if (nj > 0) {
+      k_jac<<<dim3(p.S, p.ncell, nj), 256, smem, c->stream>>>(p);
+      NID_LAUNCH_CHECK(c, "k_jac");
+      int total = nj * p.ncell * 6;
+      k_jac_final<<<(total + 255) / 256, 256, 0, c->stream>>>(p, nj);
+      NID_LAUNCH_CHECK(c, "k_jac_final");
+    }
+    if (nt > 0) {
+      k_entropy<<<dim3(p.ncell, nt), 256, smem, c->stream>>>(q);
+      NID_LAUNCH_CHECK(c, "k_entropy");
+    }
+  }
   if (nj > 0) {
-    k_jac<<<dim3(p.S, p.ncell, nj), 256, smem, c->stream>>>(p);
-    NID_LAUNCH_CHECK(c, "k_jac");
-    int total = nj * p.ncell * 6;
-    k_jac_final<<<(total + 255) / 256, 256, 0, c->stream>>>(p, nj);
-    NID_LAUNCH_CHECK(c, "k_jac_final");
     k_gn<<<(nj * 44 + 127) / 128, 128, 0, c->stream>>>(p, nj, 1);
     NID_LAUNCH_CHECK(c, "k_gn");
   }
   if (nt > 0) {
-    EvalParams q = p;
-    q.job0 = nj;
-    k_entropy<<<dim3(p.ncell, nt), 256, smem, c->stream>>>(q);
-    NID_LAUNCH_CHECK(c, "k_entropy");
     k_gn<<<(nt * 44 + 127) / 128, 128, 0, c->stream>>>(q, nt, 0);
     NID_LAUNCH_CHECK(c, "k_gn(chi2)");
   }

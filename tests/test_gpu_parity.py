@@ -9,12 +9,17 @@ pytestmark = pytest.mark.gpu
 DELTA = np.sqrt(0.95)
 
 
-def _setup(nid, orc, p, cell, bins, matrix_warp=True, **ctx_kw):
+NATURAL, SORTED = 1, 2  # nid_set_option("path", ...): both kernel families are held to the same parity bar
+
+
+def _setup(nid, orc, p, cell, bins, matrix_warp=True, path=0, **ctx_kw):
     pose0 = orc.reference_perturbation(p.T_wc1)
     P = orc.Problem(p.im0, p.depth0, p.im1, p.T_wc0, p.intr, cell, bins, threads=4)
     if matrix_warp:
         P.set_quirks(0, 1)  # warp with the 4x4 like the CUDA code does: bit-identical (u, v)
     ctx = nid.Context(p.rows, p.cols, cell, bins, **ctx_kw)
+    ctx.set_option("path", path)
+    ctx.set_option("keep_hist", 1)
     ctx.set_pair(0, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
     return P, ctx, pose0
 
@@ -37,10 +42,11 @@ def test_points3d(nid, orc, make_pair):
     assert np.array_equal(got[m], exp[m])  # same operation order, no contraction: bit-exact
 
 
+@pytest.mark.parametrize("path", [NATURAL, SORTED])
 @pytest.mark.parametrize("cell,bins,rows,cols", [(1, 8, 120, 160), (4, 16, 240, 320), (16, 10, 480, 640), (4, 32, 240, 320), (3, 12, 125, 170)])
-def test_prepare_eval_parity(nid, orc, make_pair, cell, bins, rows, cols):
+def test_prepare_eval_parity(nid, orc, make_pair, cell, bins, rows, cols, path):
     p = make_pair(1000, rows, cols)
-    P, ctx, pose0 = _setup(nid, orc, p, cell, bins)
+    P, ctx, pose0 = _setup(nid, orc, p, cell, bins, path=path)
     M0 = orc.se3_to_mat16(pose0)
     nc, href = ctx.prepare(0, M0)
     nco, hrefo = P.prepare(pose0)
@@ -61,14 +67,17 @@ def test_prepare_eval_parity(nid, orc, make_pair, cell, bins, rows, cols):
         np.testing.assert_allclose(err[act], erro[act], rtol=1e-10)
         # cost-only flavour gives the same entropies and leaves der alone
         Ht2, Hj2, J2 = ctx.eval(0, M, False)
+        if path == SORTED:  # fixed summation order: bit-identical
+            assert np.array_equal(Ht2[act], Ht[act]) and np.array_equal(Hj2[act], Hj[act])
         np.testing.assert_allclose(Ht2[act], Ht[act], rtol=1e-13)
         np.testing.assert_allclose(Hj2[act], Hj[act], rtol=1e-13)
         assert np.all(np.isnan(J2))
 
 
-def test_histograms(nid, orc, make_pair):
+@pytest.mark.parametrize("path", [NATURAL, SORTED])
+def test_histograms(nid, orc, make_pair, path):
     p = make_pair(1000, 240, 320)
-    P, ctx, pose0 = _setup(nid, orc, p, 4, 16)
+    P, ctx, pose0 = _setup(nid, orc, p, 4, 16, path=path)
     M0 = orc.se3_to_mat16(pose0)
     ctx.prepare(0, M0)
     P.prepare(pose0)
@@ -117,10 +126,11 @@ def test_warp_sample_per_pixel(nid, orc, make_pair):
     assert np.all(g4[~m] == 0)
 
 
-def test_out_of_bounds_and_inactive_cells(nid, orc, make_pair):
+@pytest.mark.parametrize("path", [NATURAL, SORTED])
+def test_out_of_bounds_and_inactive_cells(nid, orc, make_pair, path):
     """A pose that pushes a band of cells out of the image (n_c < 300 -> NaN) and leaves others partly in."""
     p = make_pair(1004, 240, 320, invalid_depth_frac=0.1)
-    P, ctx, pose0 = _setup(nid, orc, p, 8, 10)
+    P, ctx, pose0 = _setup(nid, orc, p, 8, 10, path=path)
     shift = orc.se3_mul(orc.se3_exp(np.array([0, 0.12, 0, 0, 0, 0])), pose0)  # ~60 px sideways
     M = orc.se3_to_mat16(shift)
     nc, href = ctx.prepare(0, M)
@@ -162,15 +172,29 @@ def test_eval_jobs_matches_single_evals(nid, orc, make_pair):
 
 
 def test_run_to_run_determinism(nid, orc, make_pair):
+    """The sorted path has no floating-point atomics and merges partials in a fixed order: results are
+    bit-identical run to run, across contexts, and whether 1 or several jobs are in flight."""
     p = make_pair(1000, 240, 320)
-    P, ctx, pose0 = _setup(nid, orc, p, 4, 16)
+    P, ctx, pose0 = _setup(nid, orc, p, 4, 16, path=SORTED, max_jobs=3)
     M0 = orc.se3_to_mat16(pose0)
     ctx.prepare(0, M0)
     a = ctx.eval(0, M0, True)
     for _ in range(3):
         b = ctx.eval(0, M0, True)
         for x, y in zip(a, b):
-            np.testing.assert_allclose(x, y, rtol=1e-13)
+            assert np.array_equal(x, y)
+    Ht, Hj, J = ctx.eval_jobs(np.tile(M0, 3), [0, 0, 0], True)
+    for k in range(3):
+        assert np.array_equal(Ht[k], a[0]) and np.array_equal(Hj[k], a[1]) and np.array_equal(J[k], a[2])
+    P2, ctx2, _ = _setup(nid, orc, p, 4, 16, path=SORTED)
+    ctx2.prepare(0, M0)
+    for x, y in zip(a, ctx2.eval(0, M0, True)):
+        assert np.array_equal(x, y)
+    # the natural-order path uses shared-memory fp64 atomics: equal to rounding only
+    P3, ctx3, _ = _setup(nid, orc, p, 4, 16, path=NATURAL)
+    ctx3.prepare(0, M0)
+    for x, y in zip(a, ctx3.eval(0, M0, True)):
+        np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-12)
 
 
 def test_gn_block_and_chi2(nid, orc, make_pair):
@@ -186,7 +210,7 @@ def test_gn_block_and_chi2(nid, orc, make_pair):
     np.testing.assert_allclose(b, bo, rtol=1e-7, atol=1e-9 * np.abs(bo).max())
 
 
-@pytest.mark.parametrize("cell,bins,rows,cols", [(4, 16, 240, 320), (16, 10, 480, 640)])
+@pytest.mark.parametrize("cell,bins,rows,cols", [(4, 16, 240, 320), (16, 10, 480, 640), (4, 16, 480, 640)])
 def test_lm_solve_matches_oracle(nid, orc, make_pair, cell, bins, rows, cols):
     """Converged pose within 1e-4 rad / 1e-4 x scene depth of the reference CPU path (north_star);
     in practice the whole LM trajectory coincides."""
