@@ -132,6 +132,68 @@ __device__ __forceinline__ void bspline4(double ub, int k, int bins, double w[4]
   }
 }
 
+// ---- fast variants used by the sorted kernels -----------------------------------------------------
+// exact small-integer -> double without the (slow) I2F.F64 path: bits(2^52 + v) - 2^52
+__device__ __forceinline__ double u2d(unsigned v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
+__device__ __forceinline__ double i2d_small(int v) {  // |v| < 2^20
+  return __hiloint2double(0x43300000, v + 1048576) - (4503599627370496.0 + 1048576.0);
+}
+
+// Cubic B-spline basis values (and derivatives) from the per-span polynomial table built at context
+// creation (nid_api.cu: build_bspline_table): coef[(k*4 + m)*4 + j] is the coefficient of f^j, f = ub - k,
+// of N_{k+m}. Same functions as bspline4<> (de Boor on the clamped knot vector), 16 loads + Horner.
+template <bool WANT_DER>
+__device__ __forceinline__ void bspline4_tab(const double* __restrict__ coef, double ub, int k, double w[4], double dw[4]) {
+  const double f = ub - u2d((unsigned)k);
+  const double2* c2 = reinterpret_cast<const double2*>(coef + (size_t)k * 16);
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const double2 a = c2[2 * m], b = c2[2 * m + 1];  // a = {c0, c1}, b = {c2, c3}
+    w[m] = fma(f, fma(f, fma(f, b.y, b.x), a.y), a.x);
+    if (WANT_DER) {
+      const double d = fma(f, fma(f, 3.0 * b.y, b.x + b.x), a.y);
+      dw[m] = (ub == 0.0) ? 0.0 : d;  // the reference's BsplineDer returns 0 at u == 0 (SURVEY A-3)
+    }
+  }
+}
+
+// Centre sample and central-difference gradient (types_six_dof_expmap.cpp:434-435 via .h:310-328) from
+// 12 taps instead of 5 x 4: for u,v >= 1 the five bilinear samples share their fractional weights.
+// The first image row/column (where (int)(u-1) truncates towards zero) takes the literal formula.
+__device__ __forceinline__ void sample_grad_u8(const uint8_t* __restrict__ im, int cols, double u, double v,
+                                               double& ic, double& gx, double& gy) {
+  const int ix = (int)u, iy = (int)v;
+  if (ix >= 1 && iy >= 1) {
+    const double dx = u - u2d((unsigned)ix), dy = v - u2d((unsigned)iy);
+    const double w11 = dx * dy, w10 = dy - w11, w01 = dx - w11, w00 = 1.0 - dx - dy + w11;
+    const uint8_t* r0 = im + (size_t)(iy - 1) * cols + (ix - 1);
+    const uint8_t* r1 = r0 + cols;
+    const uint8_t* r2 = r1 + cols;
+    const uint8_t* r3 = r2 + cols;
+    const int a01 = __ldg(r0 + 1), a02 = __ldg(r0 + 2);
+    const int a10 = __ldg(r1), a11 = __ldg(r1 + 1), a12 = __ldg(r1 + 2), a13 = __ldg(r1 + 3);
+    const int a20 = __ldg(r2), a21 = __ldg(r2 + 1), a22 = __ldg(r2 + 2), a23 = __ldg(r2 + 3);
+    const int a31 = __ldg(r3 + 1), a32 = __ldg(r3 + 2);
+    ic = w11 * u2d(a22) + w10 * u2d(a21) + w01 * u2d(a12) + w00 * u2d(a11);
+    gx = (w11 * i2d_small(a23 - a21) + w10 * i2d_small(a22 - a20) + w01 * i2d_small(a13 - a11) + w00 * i2d_small(a12 - a10)) * 0.5;
+    gy = (w11 * i2d_small(a32 - a12) + w10 * i2d_small(a31 - a11) + w01 * i2d_small(a22 - a02) + w00 * i2d_small(a21 - a01)) * 0.5;
+  } else {
+    ic = interp_u8(im, cols, u, v);
+    gx = (interp_u8(im, cols, u + 1.0, v) - interp_u8(im, cols, u - 1.0, v)) / 2;
+    gy = (interp_u8(im, cols, u, v + 1.0) - interp_u8(im, cols, u, v - 1.0)) / 2;
+  }
+}
+
+__device__ __forceinline__ double interp_u8_fast(const uint8_t* __restrict__ im, int cols, double x, double y) {
+  const int ix = (int)x, iy = (int)y;  // x, y >= 0 here
+  const double dx = x - u2d((unsigned)ix), dy = y - u2d((unsigned)iy);
+  const double dxdy = dx * dy;
+  const uint8_t* r0 = im + (size_t)iy * cols + ix;
+  const uint8_t* r1 = r0 + cols;
+  return dxdy * u2d(__ldg(r1 + 1)) + (dy - dxdy) * u2d(__ldg(r1)) + (dx - dxdy) * u2d(__ldg(r0 + 1)) +
+         (1.0 - dx - dy + dxdy) * u2d(__ldg(r0));
+}
+
 // deterministic block-wide sum (fixed tree): every thread gets the total. `scratch` >= blockDim/32 doubles.
 __device__ __forceinline__ double block_sum(double v, double* scratch) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -103,6 +103,9 @@ __global__ void __launch_bounds__(256) k_hist_sorted(EvalParams p) {
   const int job = blockIdx.y + p.job0;
   const int pair = p.job_pair[job];
   const int t = blockIdx.x * 8 + warp;
+  double* coef = sm + (size_t)8 * B * 32;  // [(B-3)*16] spline polynomial table
+  for (int i = threadIdx.x; i < (B - 3) * 16; i += blockDim.x) coef[i] = p.bs_coef[i];
+  __syncthreads();
   if (t >= p.ntasks[pair]) return;
   int start, count, cls, cell;
   unpack_task(p.tasks[(size_t)pair * p.max_tasks + t], start, count, cls, cell);
@@ -123,17 +126,17 @@ __global__ void __launch_bounds__(256) k_hist_sorted(EvalParams p) {
     double x1, y1, z1, u, v;
     warp_project(P, cam, sx[i], sy[i], sz[i], x1, y1, z1, u, v);
     if (!inb_cost(u, v, p.rows, p.cols)) continue;
-    const double ic = clamp_intensity(interp_u8(im1, p.cols, u, v));
+    const double ic = clamp_intensity(interp_u8_fast(im1, p.cols, u, v));
     const double ub = ic * s;
     const int kt = (int)ub;  // ub >= 0
     double wt[4], dw[4];
-    bspline4<false>(ub, kt, B, wt, dw);
+    bspline4_tab<false>(coef, ub, kt, wt, dw);
 #pragma unroll
     for (int n = 0; n < 4; n++) h[(kt + n) * 32 + lane] += wt[n];
   }
   __syncwarp();
   // fixed-order merge of the 32 lane-private copies: lane tt sums column tt (rotated start => no bank conflicts)
-  double* out = p.G + ((size_t)job * p.max_tasks + t) * B;
+  double* out = p.G + ((size_t)job * p.g_stride + t) * B;
   for (int tt = lane; tt < B; tt += 32) {
     double acc = 0.0;
 #pragma unroll 8
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(256) k_assemble(EvalParams p, int want_jac) {
   const int t0 = p.cell_task_start[pair * (p.ncell + 1) + c];
   const int t1 = p.cell_task_start[pair * (p.ncell + 1) + c + 1];
   const int2* tasks = p.tasks + (size_t)pair * p.max_tasks;
-  const double* G = p.G + (size_t)job * p.max_tasks * B;
+  const double* G = p.G + (size_t)job * p.g_stride * B;
   double acc[NID_ASM_MAXE];
 #pragma unroll
   for (int e = 0; e < NID_ASM_MAXE; e++) acc[e] = 0.0;
@@ -245,6 +248,9 @@ __global__ void __launch_bounds__(256) k_jac_sorted(EvalParams p) {
   const int job = blockIdx.y + p.job0;
   const int pair = p.job_pair[job];
   const int t = blockIdx.x * 8 + warp;
+  double* coef = sm + 8 * B;  // [(B-3)*16] spline polynomial table
+  for (int i = threadIdx.x; i < (B - 3) * 16; i += blockDim.x) coef[i] = p.bs_coef[i];
+  __syncthreads();
   if (t >= p.ntasks[pair]) return;
   int start, count, cls, cell;
   unpack_task(p.tasks[(size_t)pair * p.max_tasks + t], start, count, cls, cell);
@@ -277,13 +283,13 @@ __global__ void __launch_bounds__(256) k_jac_sorted(EvalParams p) {
     double x, y, z, u, v;
     warp_project(P, cam, sx[i], sy[i], sz[i], x, y, z, u, v);
     if (!inb_jac(u, v, p.rows, p.cols)) continue;
-    const double ic = clamp_intensity(interp_u8(im1, p.cols, u, v));
-    const double gx = (interp_u8(im1, p.cols, u + 1.0, v) - interp_u8(im1, p.cols, u - 1.0, v)) / 2;
-    const double gy = (interp_u8(im1, p.cols, u, v + 1.0) - interp_u8(im1, p.cols, u, v - 1.0)) / 2;
+    double ic, gx, gy;
+    sample_grad_u8(im1, p.cols, u, v, ic, gx, gy);
+    ic = clamp_intensity(ic);
     const double ub = ic * s;
     const int kt = (int)ub;
     double wt[4], dw[4];
-    bspline4<true>(ub, kt, B, wt, dw);
+    bspline4_tab<true>(coef, ub, kt, wt, dw);
     double ci = 0.0;
 #pragma unroll
     for (int m = 0; m < 4; m++) ci += dw[m] * wrow[kt + m];
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(256) k_jac_sorted(EvalParams p) {
     double vv = acc[0];
 #pragma unroll
     for (int k = 1; k < 6; k++) if (lane == k) vv = acc[k];
-    p.jpart[((size_t)job * p.max_tasks + t) * 6 + lane] = vv;
+    p.jpart[((size_t)job * p.g_stride + t) * 6 + lane] = vv;
   }
 }
 
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(256) k_jac_final_sorted(EvalParams p, int n_jo
   }
   const int t0 = p.cell_task_start[pair * (p.ncell + 1) + c];
   const int t1 = p.cell_task_start[pair * (p.ncell + 1) + c + 1];
-  const double* jp = p.jpart + (size_t)job * p.max_tasks * 6;
+  const double* jp = p.jpart + (size_t)job * p.g_stride * 6;
   double acc[6] = {0, 0, 0, 0, 0, 0};
   for (int t = t0 + lane; t < t1; t += 32) {
 #pragma unroll
@@ -357,7 +363,8 @@ int launch_scatter(nid_ctx* c, int pair) {
   return NID_OK;
 }
 
-size_t hist_sorted_smem(const nid_ctx* c) { return sizeof(double) * 8 * c->bins * 32; }
+size_t hist_sorted_smem(const nid_ctx* c) { return sizeof(double) * (8 * c->bins * 32 + (c->bins - 3) * 16); }
+size_t jac_sorted_smem(const nid_ctx* c) { return sizeof(double) * (8 * c->bins + (c->bins - 3) * 16); }
 size_t assemble_smem(const nid_ctx* c) { return sizeof(double) * (NID_ASM_BATCH * c->bins + c->bins * c->bins + c->bins); }
 
 int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int want_jac) {
@@ -372,7 +379,7 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
   NID_LAUNCH_CHECK(c, "k_assemble");
   ktime_mark(c, 2);
   if (want_jac) {
-    k_jac_sorted<<<dim3(tblocks, n_jobs), 256, sizeof(double) * 8 * c->bins, c->stream>>>(p);
+    k_jac_sorted<<<dim3(tblocks, n_jobs), 256, jac_sorted_smem(c), c->stream>>>(p);
     NID_LAUNCH_CHECK(c, "k_jac_sorted");
     ktime_mark(c, 3);
     const int warps = n_jobs * c->ncell;
