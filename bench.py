@@ -192,6 +192,9 @@ def main():
 
     n_slots = args.pairs
     ctx = nid.Context(ROWS, COLS, CELL, BINS, n_pairs=n_slots, max_jobs=n_slots, device=local_rank)
+    for kv in filter(None, os.environ.get("NID_OPTS", "").split(",")):  # developer knob, e.g. NID_OPTS=use_tex=0
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     pose0 = []
     distinct = [synth.make_pair(1000 + rank * DISTINCT_PAIRS + i, ROWS, COLS) for i in range(DISTINCT_PAIRS)]
     for i, p in enumerate(distinct):

@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnid_b200.so")
+LIB_PATH = os.environ.get("NID_B200_LIB") or os.path.join(_HERE, "libnid_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "nid_b200.h")
 
 _dp = C.POINTER(C.c_double)

@@ -62,7 +62,7 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.sx = c->sx; p.sy = c->sy; p.sz = c->sz;
   p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start;
   p.max_tasks = c->max_tasks; p.g_stride = (int)c->g_stride;
-  p.G = c->G; p.wv = c->wv;
+  p.G = c->G; p.qt = c->qt; p.pp = 1; p.tex = c->d_tex;
   return p;
 }
 
@@ -128,12 +128,19 @@ int ensure_job_buffers(nid_ctx* c) {
       OKR(dalloc(&c->jpart_s, J * need * 6, "jpart_s"));
       c->g_stride = need;
     }
-    if (!c->wv) OKR(dalloc(&c->wv, J * NC * hs, "wv"));
+    if (!c->qt) OKR(dalloc(&c->qt, J * NC * NID_NCLS * (size_t)(c->bins - 3) * 3, "qt"));
   } else if (!c->part) {
     c->part_slots = J + 2 * (size_t)c->sm_count + 64;
     OKR(dalloc(&c->part, c->part_slots * NC * hs, "part"));
     OKR(dalloc(&c->jpart, c->part_slots * NC * 6, "jpart"));
   }
+  return NID_OK;
+}
+
+static int update_texture(nid_ctx* c, int pair) {
+  if (!c->use_tex) return NID_OK;
+  CU(cudaMemcpy2DToArrayAsync(c->tex_arrays[pair], 0, 0, c->im1 + (size_t)pair * c->N, c->cols, c->cols, c->rows,
+                              cudaMemcpyDeviceToDevice, c->stream), "im1 -> texture array");
   return NID_OK;
 }
 
@@ -212,6 +219,35 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   OKR(dalloc(&c->cell_task_start, P * (NC + 1), "cell_task_start"));
   OKR(dalloc(&c->seg_start, P * (NC * NID_NCLS + 1), "seg_start"));
   c->h_ntasks.assign(P, 0);
+  // target images as gather-able textures (tex2Dgather needs a CUDA array created with cudaArrayTextureGather)
+  {
+    c->tex_arrays.assign(P, nullptr);
+    c->h_tex.assign(P, 0);
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc<unsigned char>();
+    bool ok = true;
+    for (size_t i = 0; i < P && ok; i++) {
+      if (cudaMallocArray(&c->tex_arrays[i], &cd, cols, rows, cudaArrayTextureGather) != cudaSuccess) { ok = false; break; }
+      cudaResourceDesc rd;
+      memset(&rd, 0, sizeof(rd));
+      rd.resType = cudaResourceTypeArray;
+      rd.res.array.array = c->tex_arrays[i];
+      cudaTextureDesc td;
+      memset(&td, 0, sizeof(td));
+      td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+      td.filterMode = cudaFilterModePoint;
+      td.readMode = cudaReadModeElementType;
+      td.normalizedCoords = 0;
+      if (cudaCreateTextureObject(&c->h_tex[i], &rd, &td, nullptr) != cudaSuccess) ok = false;
+    }
+    if (!ok) {
+      cudaGetLastError();
+      set_error("could not create gather textures for the target images");
+      return NID_ERR_CUDA;
+    }
+    OKR(dalloc(&c->d_tex, P, "d_tex"));
+    CU(cudaMemcpy(c->d_tex, c->h_tex.data(), sizeof(cudaTextureObject_t) * P, cudaMemcpyHostToDevice), "H2D tex handles");
+    c->use_tex = true;
+  }
   OKR(dalloc(&c->d_depth, N, "d_depth")); OKR(dalloc(&c->d_img64, N, "d_img64")); OKR(dalloc(&c->d_flag, 1, "d_flag"));
   OKR(dalloc(&c->lut_w, 256 * 4, "lut_w")); OKR(dalloc(&c->lut_k, 256, "lut_k"));
   OKR(dalloc(&c->poses, J * 16, "poses")); OKR(dalloc(&c->job_pair, J, "job_pair"));
@@ -244,13 +280,15 @@ int nid_destroy(nid_ctx* c) {
   void* ptrs[] = {c->pwx, c->pwy, c->pwz, c->im0, c->im1, c->inb0, c->n_c, c->href, c->cam, c->Twc0, c->cnt, c->d_depth,
                   c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
                   c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
-                  c->bs_coef, c->sx, c->sy, c->sz, c->tasks, c->ntasks, c->cell_task_start, c->seg_start, c->G, c->wv, c->jpart_s};
+                  c->bs_coef, c->sx, c->sy, c->sz, c->tasks, c->ntasks, c->cell_task_start, c->seg_start, c->G, c->qt, c->jpart_s, c->d_tex};
+  for (auto t : c->h_tex) if (t) cudaDestroyTextureObject(t);
+  for (auto arr : c->tex_arrays) if (arr) cudaFreeArray(arr);
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->h_poses) cudaFreeHost(c->h_poses);
   if (c->h_job_pair) cudaFreeHost(c->h_job_pair);
   if (c->h_out) cudaFreeHost(c->h_out);
   for (int i = 0; i < 2; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  for (int i = 0; i < 4; i++) if (c->kev[i]) cudaEventDestroy(c->kev[i]);
+  for (int i = 0; i < 5; i++) if (c->kev[i]) cudaEventDestroy(c->kev[i]);
   cudaStreamDestroy(c->stream);
   delete c;
   return NID_OK;
@@ -280,6 +318,7 @@ int nid_set_pair(nid_ctx* c, int pair, const double* depth, const uint8_t* im0, 
   OKR(set_pair_common(c, pair, depth, T_wc0, intr));
   CU(cudaMemcpyAsync(c->im0 + (size_t)pair * c->N, im0, c->N, cudaMemcpyDefault, c->stream), "H2D im0");
   CU(cudaMemcpyAsync(c->im1 + (size_t)pair * c->N, im1, c->N, cudaMemcpyDefault, c->stream), "H2D im1");
+  OKR(update_texture(c, pair));
   CU(cudaStreamSynchronize(c->stream), "sync set_pair");
   c->pair_set[pair] = 1;
   return NID_OK;
@@ -306,6 +345,7 @@ static int upload_images_f64(nid_ctx* c, int pair, const double* im0, const doub
   if (im1) {
     CU(cudaMemcpyAsync(c->d_img64, im1, sizeof(double) * c->N, cudaMemcpyDefault, c->stream), "H2D im1 f64");
     OKR(launch_check_integral(c, c->d_img64, c->im1 + (size_t)pair * c->N, 0));
+    OKR(update_texture(c, pair));
   }
   int flag = 0;
   CU(cudaMemcpyAsync(&flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream), "D2H flag");
@@ -383,10 +423,13 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
   int off = 0;
   for (int cell = 0; cell < NC; cell++) {
     cts[cell] = (int)tasks.size();
+    long long n_c = 0;
+    for (int v = 0; v < 256; v++) n_c += cnt[(size_t)cell * NID_NCLS + v];
+    const bool active = n_c >= NID_MIN_CELL_POINTS;  // inactive cells get no work at all
     for (int v = 0; v < NID_NCLS; v++) {
       const int len = (int)cnt[(size_t)cell * NID_NCLS + v];
       seg[(size_t)cell * NID_NCLS + v] = off;
-      for (int o = 0; o < len; o += NID_TASK_PX) {
+      for (int o = 0; active && o < len; o += NID_TASK_PX) {
         int2 t;
         t.x = off + o;
         t.y = std::min(NID_TASK_PX, len - o) | (v << 9) | (cell << 18);
@@ -725,6 +768,8 @@ int nid_set_option(nid_ctx* c, const char* key, int value) {
     return NID_OK;
   }
   if (!strcmp(key, "keep_hist")) { c->opt_keep_hist = value; return NID_OK; }
+  if (!strcmp(key, "tasks_per_warp")) { c->opt_tasks_per_warp = value; return NID_OK; }
+  if (!strcmp(key, "use_tex")) { c->use_tex = value != 0 && c->d_tex != nullptr; return NID_OK; }
   if (!strcmp(key, "time_kernels")) {
     c->opt_time_kernels = value;
     for (int i = 0; i < 4; i++) { c->kernel_ms[i] = 0; c->kernel_calls[i] = 0; }

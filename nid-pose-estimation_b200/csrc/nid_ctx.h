@@ -56,7 +56,9 @@ struct EvalParams {
   int max_tasks;        // task-table stride per pair
   int g_stride;         // partial-buffer stride per job (tasks)
   double* G;            // [jobs][g_stride][bins]
-  double* wv;           // [jobs][ncell][bins*bins+bins]
+  double* qt;           // [jobs][ncell][NID_NCLS][bins-3][3] per-class, per-span Jacobian quadratics
+  const cudaTextureObject_t* tex;  // [n_pairs] target image as a gather-able 2D texture
+  int pp;               // tasks per warp (sorted path)
 };
 
 }  // namespace nid
@@ -88,7 +90,12 @@ struct nid_ctx {
   std::vector<int> h_ntasks;
   int max_ntasks_prepared = 0;
   // sorted path, per job (grown on demand)
-  double *G = nullptr, *wv = nullptr, *jpart_s = nullptr;
+  double *G = nullptr, *qt = nullptr, *jpart_s = nullptr;
+  std::vector<cudaArray_t> tex_arrays;
+  std::vector<cudaTextureObject_t> h_tex;
+  cudaTextureObject_t* d_tex = nullptr;
+  bool use_tex = false;
+  int opt_tasks_per_warp = 0;
   size_t g_stride = 0;
   int opt_path = 0;            // 0 auto, 1 natural-order atomics (v1), 2 sorted
   int opt_keep_hist = 0;
