@@ -61,6 +61,7 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.ht = c->ht; p.hj = c->hj; p.err = c->err; p.der = c->der; p.gn = c->gn;
   p.sx = c->sx; p.sy = c->sy; p.sz = c->sz;
   p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start;
+  p.cls_task_start = c->cls_task_start; p.row_cls = c->row_cls; p.wv = c->wv;
   p.max_tasks = c->max_tasks; p.g_stride = (int)c->g_stride;
   p.G = c->G; p.qt = c->qt; p.pp = 1; p.tex = c->d_tex;
   return p;
@@ -129,6 +130,7 @@ int ensure_job_buffers(nid_ctx* c) {
       c->g_stride = need;
     }
     if (!c->qt) OKR(dalloc(&c->qt, J * NC * NID_NCLS * (size_t)(c->bins - 3) * 3, "qt"));
+    if (!c->wv) OKR(dalloc(&c->wv, J * NC * hs, "wv"));
   } else if (!c->part) {
     c->part_slots = J + 2 * (size_t)c->sm_count + 64;
     OKR(dalloc(&c->part, c->part_slots * NC * hs, "part"));
@@ -217,6 +219,21 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   OKR(dalloc(&c->ntasks, P, "ntasks"));
   CU(cudaMemset(c->ntasks, 0, sizeof(int) * P), "memset ntasks");
   OKR(dalloc(&c->cell_task_start, P * (NC + 1), "cell_task_start"));
+  OKR(dalloc(&c->cls_task_start, P * NC * (NID_NCLS + 1), "cls_task_start"));
+  {
+    // classes whose span index k_r = floor(v' (B-3)/255) lies in [r-3, r]  (v' = 254.999 for v = 255)
+    std::vector<int> rc(2 * (size_t)bins);
+    auto kr = [bins](int v) { double o = v >= 255 ? 254.999 : (double)v; return (int)std::floor(o * (bins - 3) / 255.0); };
+    for (int r = 0; r < bins; r++) {
+      int lo = 256, hi = 0;
+      for (int v = 0; v < 256; v++)
+        if (kr(v) >= r - 3 && kr(v) <= r) { lo = std::min(lo, v); hi = std::max(hi, v + 1); }
+      if (lo > hi) lo = hi = 0;
+      rc[2 * r] = lo; rc[2 * r + 1] = hi;
+    }
+    OKR(dalloc(&c->row_cls, rc.size(), "row_cls"));
+    CU(cudaMemcpy(c->row_cls, rc.data(), sizeof(int) * rc.size(), cudaMemcpyHostToDevice), "H2D row_cls");
+  }
   OKR(dalloc(&c->seg_start, P * (NC * NID_NCLS + 1), "seg_start"));
   c->h_ntasks.assign(P, 0);
   // target images as gather-able textures (tex2Dgather needs a CUDA array created with cudaArrayTextureGather)
@@ -280,7 +297,7 @@ int nid_destroy(nid_ctx* c) {
   void* ptrs[] = {c->pwx, c->pwy, c->pwz, c->im0, c->im1, c->inb0, c->n_c, c->href, c->cam, c->Twc0, c->cnt, c->d_depth,
                   c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
                   c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
-                  c->bs_coef, c->sx, c->sy, c->sz, c->tasks, c->ntasks, c->cell_task_start, c->seg_start, c->G, c->qt, c->jpart_s, c->d_tex};
+                  c->bs_coef, c->sx, c->sy, c->sz, c->tasks, c->ntasks, c->cell_task_start, c->seg_start, c->G, c->qt, c->jpart_s, c->d_tex, c->cls_task_start, c->row_cls, c->wv};
   for (auto t : c->h_tex) if (t) cudaDestroyTextureObject(t);
   for (auto arr : c->tex_arrays) if (arr) cudaFreeArray(arr);
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -417,7 +434,7 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
   CU(cudaMemcpyAsync(cnt.data(), c->cnt + (size_t)pair * NC * NID_NCLS, sizeof(unsigned int) * cnt.size(),
                      cudaMemcpyDeviceToHost, c->stream), "D2H cnt");
   CU(cudaStreamSynchronize(c->stream), "sync cnt");
-  std::vector<int> seg((size_t)NC * NID_NCLS + 1), cts(NC + 1);
+  std::vector<int> seg((size_t)NC * NID_NCLS + 1), cts(NC + 1), clsts((size_t)NC * (NID_NCLS + 1));
   std::vector<int2> tasks;
   tasks.reserve(c->max_tasks);
   int off = 0;
@@ -429,6 +446,7 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
     for (int v = 0; v < NID_NCLS; v++) {
       const int len = (int)cnt[(size_t)cell * NID_NCLS + v];
       seg[(size_t)cell * NID_NCLS + v] = off;
+      clsts[(size_t)cell * (NID_NCLS + 1) + v] = (int)tasks.size();
       for (int o = 0; active && o < len; o += NID_TASK_PX) {
         int2 t;
         t.x = off + o;
@@ -437,6 +455,7 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
       }
       off += len;
     }
+    clsts[(size_t)cell * (NID_NCLS + 1) + NID_NCLS] = (int)tasks.size();
   }
   seg[(size_t)NC * NID_NCLS] = off;
   cts[NC] = (int)tasks.size();
@@ -449,6 +468,8 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
   CU(cudaMemcpyAsync(c->cell_task_start + (size_t)pair * (NC + 1), cts.data(), sizeof(int) * (NC + 1),
                      cudaMemcpyHostToDevice, c->stream), "H2D cell_task_start");
   CU(cudaMemcpyAsync(c->ntasks + pair, &nt, sizeof(int), cudaMemcpyHostToDevice, c->stream), "H2D ntasks");
+  CU(cudaMemcpyAsync(c->cls_task_start + (size_t)pair * NC * (NID_NCLS + 1), clsts.data(), sizeof(int) * clsts.size(),
+                     cudaMemcpyHostToDevice, c->stream), "H2D cls_task_start");
   OKR(launch_scatter(c, pair));
   CU(cudaStreamSynchronize(c->stream), "sync scatter");  // host vectors go out of scope
   c->h_ntasks[pair] = nt;

@@ -53,6 +53,9 @@ struct EvalParams {
   const int2* tasks;    // [n_pairs][max_tasks] {start, count | cls<<9 | cell<<18}
   const int* ntasks;    // [n_pairs]
   const int* cell_task_start;  // [n_pairs][ncell+1]
+  const int* cls_task_start;   // [n_pairs][ncell][NID_NCLS+1] first task of every class
+  const int* row_cls;          // [bins][2] class range [lo, hi) whose k_r lies in [r-3, r]
+  double* wv;                  // [jobs][ncell][bins*bins+bins] scaled log tables (assemble -> qtable)
   int max_tasks;        // task-table stride per pair
   int g_stride;         // partial-buffer stride per job (tasks)
   double* G;            // [jobs][g_stride][bins]
@@ -85,6 +88,9 @@ struct nid_ctx {
   int2* tasks = nullptr;
   int* ntasks = nullptr;
   int* cell_task_start = nullptr;
+  int* cls_task_start = nullptr;
+  int* row_cls = nullptr;
+  double* wv = nullptr;
   int* seg_start = nullptr;    // [n_pairs][ncell*NID_NCLS+1]
   int max_tasks = 0;
   std::vector<int> h_ntasks;

@@ -34,8 +34,17 @@ __device__ __forceinline__ void warp_project(const Pose& P, const Cam& cam, doub
   x1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.m[0], x0), __dmul_rn(P.m[3], y0)), __dmul_rn(P.m[6], z0)), P.m[9]);
   y1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.m[1], x0), __dmul_rn(P.m[4], y0)), __dmul_rn(P.m[7], z0)), P.m[10]);
   z1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.m[2], x0), __dmul_rn(P.m[5], y0)), __dmul_rn(P.m[8], z0)), P.m[11]);
+#ifdef NID_ABL_NODIV
+  u = cam.fx * x1 * 0.38 + cam.cx;
+  v = cam.fy * y1 * 0.38 + cam.cy;
+#elif defined(NID_ABL_RCP)
+  const double rz = 1.0 / z1;
+  u = fma(cam.fx * x1, rz, cam.cx);
+  v = fma(cam.fy * y1, rz, cam.cy);
+#else
   u = __dadd_rn(__ddiv_rn(__dmul_rn(cam.fx, x1), z1), cam.cx);
   v = __dadd_rn(__ddiv_rn(__dmul_rn(cam.fy, y1), z1), cam.cy);
+#endif
 }
 
 // CudaPoints3d.cu:20-28 (same order, no contraction)

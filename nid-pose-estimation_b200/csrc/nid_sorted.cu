@@ -112,6 +112,9 @@ __device__ __forceinline__ double sample_center(cudaTextureObject_t tex, const u
   const double dx = u - u2d((unsigned)ix), dy = v - u2d((unsigned)iy);
   const double dxdy = dx * dy;
   unsigned p00, p01, p10, p11;
+#ifdef NID_ABL_NOTAP
+  p00 = ix & 255; p01 = iy & 255; p10 = (ix + iy) & 255; p11 = (ix ^ iy) & 255;
+#else
   if (TEX) {
     const uchar4 g = gather2x2(tex, ix, iy);
     p00 = g.w; p01 = g.z; p10 = g.x; p11 = g.y;
@@ -120,6 +123,7 @@ __device__ __forceinline__ double sample_center(cudaTextureObject_t tex, const u
     const uint8_t* r1 = r0 + cols;
     p00 = __ldg(r0); p01 = __ldg(r0 + 1); p10 = __ldg(r1); p11 = __ldg(r1 + 1);
   }
+#endif
   // types_six_dof_expmap.h:321-326, same term order
   return dxdy * u2d(p11) + (dy - dxdy) * u2d(p10) + (dx - dxdy) * u2d(p01) + (1.0 - dx - dy + dxdy) * u2d(p00);
 }
@@ -135,6 +139,9 @@ __device__ __forceinline__ void sample_grad(cudaTextureObject_t tex, const uint8
     const double dx = u - u2d((unsigned)ix), dy = v - u2d((unsigned)iy);
     const double w11 = dx * dy, w10 = dy - w11, w01 = dx - w11, w00 = 1.0 - dx - dy + w11;
     int a01, a02, a10, a11, a12, a13, a20, a21, a22, a23, a31, a32;
+#ifdef NID_ABL_NOTAP
+    a01 = ix & 255; a02 = iy & 255; a10 = 3; a11 = (ix + iy) & 255; a12 = 7; a13 = 9; a20 = 1; a21 = 100; a22 = ix & 127; a23 = 5; a31 = 8; a32 = 77;
+#else
     if (TEX) {
       const uchar4 A = gather2x2(tex, ix - 1, iy), Bq = gather2x2(tex, ix + 1, iy);
       const uchar4 C = gather2x2(tex, ix, iy - 1), D = gather2x2(tex, ix, iy + 1);
@@ -152,6 +159,7 @@ __device__ __forceinline__ void sample_grad(cudaTextureObject_t tex, const uint8
       a20 = __ldg(r2); a21 = __ldg(r2 + 1); a22 = __ldg(r2 + 2); a23 = __ldg(r2 + 3);
       a31 = __ldg(r3 + 1); a32 = __ldg(r3 + 2);
     }
+#endif
     ic = w11 * u2d(a22) + w10 * u2d(a21) + w01 * u2d(a12) + w00 * u2d(a11);
     gx = (w11 * i2d_small(a23 - a21) + w10 * i2d_small(a22 - a20) + w01 * i2d_small(a13 - a11) + w00 * i2d_small(a12 - a10)) * 0.5;
     gy = (w11 * i2d_small(a32 - a12) + w10 * i2d_small(a31 - a11) + w01 * i2d_small(a22 - a02) + w00 * i2d_small(a21 - a01)) * 0.5;
@@ -191,50 +199,21 @@ __device__ __forceinline__ WarpTasks warp_tasks_begin(const EvalParams& p, int p
   return w;
 }
 
-// Sum four per-lane values over the warp with a fixed butterfly (10 double shuffles instead of 20):
-// after it, every lane holds S_0..S_3 = the warp totals of v[0..3]. Deterministic.
-__device__ __forceinline__ void warp_sum4(double v[4], int lane) {
-  const unsigned F = 0xffffffffu;
-  const bool b0 = lane & 1, b1 = lane & 2;
-  // xor 1: even lanes keep (v0,v1), odd lanes keep (v2,v3)
-  double k0 = b0 ? v[2] : v[0], k1 = b0 ? v[3] : v[1];
-  double s0 = b0 ? v[0] : v[2], s1 = b0 ? v[1] : v[3];
-  k0 += __shfl_xor_sync(F, s0, 1);
-  k1 += __shfl_xor_sync(F, s1, 1);
-  // xor 2: keep one of the two
-  double k = b1 ? k1 : k0, s = b1 ? k0 : k1;
-  k += __shfl_xor_sync(F, s, 2);
-  k += __shfl_xor_sync(F, k, 4);
-  k += __shfl_xor_sync(F, k, 8);
-  k += __shfl_xor_sync(F, k, 16);
-  // lane l now holds the total of v[2*b0 + b1]: v0 in lane 0, v1 in lane 2, v2 in lane 1, v3 in lane 3
-  v[0] = __shfl_sync(F, k, 0);
-  v[1] = __shfl_sync(F, k, 2);
-  v[2] = __shfl_sync(F, k, 1);
-  v[3] = __shfl_sync(F, k, 3);
-}
-
 // ------------------------------------------------------------------------------------------------
-// Pass 1. For the pixels of a task that fall into spline span k (ub = k + f), the four basis functions
-// are cubics in f, so their sums over pixels need only the power sums S_j = sum f^j (j = 0..3):
-//     h[k+m] += sum_j coef[k][m][j] * S_j[k].
-// Each lane keeps the power sums of its current span in registers and spills them into lane-private
-// shared memory only when its span changes; at the end of a task the touched spans are reduced over the
-// warp (fixed butterfly), turned into h[B] with the polynomial table, and stored as the task's partial.
-// grid (ceil(ceil(max_tasks/pp)/W), jobs), W warps per CTA.
-#define NID_MROW 33  // row stride (doubles) of the lane-private moment store
+// Pass 1: per task the un-weighted target soft histogram h[B] of its pixels, accumulated in lane-private
+// shared memory (no atomics) and merged over the 32 lanes in a fixed order.
+// grid (ceil(ceil(max_tasks/pp)/8), jobs), 256 threads; shared: 8 warps x B x 32 doubles + spline table.
+// (A power-sum variant -- sum f^j per span, spline applied once per task -- was measured slower: its
+// per-task warp reductions outweigh the saved Horner evaluations at ~3 pixels per lane and task.)
 template <bool TEX>
 __global__ void __launch_bounds__(256) k_hist_sorted(EvalParams p) {
   extern __shared__ double sm[];
-  const int B = p.bins, NS = B - 3;
+  const int B = p.bins;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int job = blockIdx.y + p.job0;
   const int pair = p.job_pair[job];
-  double* coef = sm;                                    // [NS*16]
-  double* M = sm + NS * 16 + (size_t)warp * (NS * 4 * NID_MROW + B);  // [NS*4][NID_MROW] lane-private power sums
-  double* hout = M + NS * 4 * NID_MROW;                 // [B]
-  for (int i = threadIdx.x; i < NS * 16; i += blockDim.x) coef[i] = p.bs_coef[i];
-  for (int r = 0; r < NS * 4; r++) M[r * NID_MROW + lane] = 0.0;
+  double* coef = sm + (size_t)W * B * 32;  // [(B-3)*16] spline polynomial table
+  for (int i = threadIdx.x; i < (B - 3) * 16; i += blockDim.x) coef[i] = p.bs_coef[i];
   __syncthreads();
   const size_t base = (size_t)pair * p.N;
   const double* sxp = p.sx + base;
@@ -242,6 +221,7 @@ __global__ void __launch_bounds__(256) k_hist_sorted(EvalParams p) {
   const double* szp = p.sz + base;
   const WarpTasks wt_ = warp_tasks_begin(p, pair, lane, blockIdx.x * W + warp, sxp, syp, szp);
   if (wt_.n <= 0) return;
+  double* h = sm + (size_t)warp * B * 32;  // h[tt*32 + lane]
   const double* cp = p.cam + 4 * pair;
   const Cam cam{cp[0], cp[1], cp[2], cp[3]};
   const Pose P = load_pose(p.poses + 16 * job);
@@ -251,12 +231,10 @@ __global__ void __launch_bounds__(256) k_hist_sorted(EvalParams p) {
   for (int j = 0; j < wt_.n; j++) {
     const int start = __shfl_sync(0xffffffffu, wt_.mine.x, j);
     const int count = __shfl_sync(0xffffffffu, wt_.mine.y, j) & 0x1ff;
-    for (int tt = lane; tt < B; tt += 32) hout[tt] = 0.0;
+    for (int tt = 0; tt < B; tt++) h[tt * 32 + lane] = 0.0;
     const double* sx = sxp + start;
     const double* sy = syp + start;
     const double* sz = szp + start;
-    int cur_k = -1, kmin = 1 << 20, kmax = -1;
-    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
     int i = lane;
     bool have = i < count;
     double nx = 0, ny = 0, nz = 0;
@@ -271,65 +249,53 @@ __global__ void __launch_bounds__(256) k_hist_sorted(EvalParams p) {
       if (inb_cost(u, v, p.rows, p.cols)) {
         const double ic = clamp_intensity(sample_center<TEX>(tex, im1, p.cols, u, v));
         const double ub = ic * s;
-        const int k = (int)ub;  // ub >= 0
-        const double f = ub - u2d((unsigned)k);
-        if (k != cur_k) {
-          if (cur_k >= 0) {
-            double* m = M + (cur_k * 4) * NID_MROW + lane;
-            m[0] += r0; m[NID_MROW] += r1; m[2 * NID_MROW] += r2; m[3 * NID_MROW] += r3;
-          }
-          cur_k = k; r0 = 0.0; r1 = 0.0; r2 = 0.0; r3 = 0.0;
-          kmin = min(kmin, k); kmax = max(kmax, k);
-        }
-        const double f2 = f * f;
-        r0 += 1.0; r1 += f; r2 += f2; r3 += f2 * f;
-      }
-    }
-    if (cur_k >= 0) {
-      double* m = M + (cur_k * 4) * NID_MROW + lane;
-      m[0] += r0; m[NID_MROW] += r1; m[2 * NID_MROW] += r2; m[3 * NID_MROW] += r3;
-    }
+        const int kt = (int)ub;  // ub >= 0
+        double wt[4], dw[4];
+        bspline4_tab<false>(coef, ub, kt, wt, dw);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, off));
-      kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, off));
+        for (int n = 0; n < 4; n++) h[(kt + n) * 32 + lane] += wt[n];
+      }
     }
     __syncwarp();
-    for (int k = kmin; k <= kmax; k++) {
-      double* m = M + (k * 4) * NID_MROW + lane;
-      double S[4] = {m[0], m[NID_MROW], m[2 * NID_MROW], m[3 * NID_MROW]};
-      m[0] = 0.0; m[NID_MROW] = 0.0; m[2 * NID_MROW] = 0.0; m[3 * NID_MROW] = 0.0;
-      warp_sum4(S, lane);
-      if (lane < 4) {
-        const double* c = coef + (k * 4 + lane) * 4;
-        hout[k + lane] += c[0] * S[0] + c[1] * S[1] + c[2] * S[2] + c[3] * S[3];
-      }
-      __syncwarp();
-    }
+    // fixed-order merge of the 32 lane-private copies: lane tt sums column tt (rotated start => no bank
+    // conflicts), four independent chains to shorten the dependency
     double* out = p.G + ((size_t)job * p.g_stride + wt_.first + j) * B;
-    for (int tt = lane; tt < B; tt += 32) out[tt] = hout[tt];
+    for (int tt = lane; tt < B; tt += 32) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 32; q += 4) {
+        a0 += h[tt * 32 + ((q + tt) & 31)];
+        a1 += h[tt * 32 + ((q + 1 + tt) & 31)];
+        a2 += h[tt * 32 + ((q + 2 + tt) & 31)];
+        a3 += h[tt * 32 + ((q + 3 + tt) & 31)];
+      }
+      out[tt] = (a0 + a1) + (a2 + a3);
+    }
     __syncwarp();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Assembly (a7 + table half of a8): one CTA per (cell, job). Combines the task partials of the cell in
-// task order into P_t and P_j, normalises by n_c, computes H_t, H_j, err (computeH.cu:261-300;
-// types_six_dof_expmap.cpp:609-635, .h:227) and, when want_jac, the per-class / per-span quadratic
-//   c(f) = q0 + q1 f + q2 f^2 = sum_m N'_{k+m}(k+f) * Wv[v][k+m],
-//   Wv[v][t] = V[t] + sum_kk w_ref,v[kk] W[k_r(v)+kk][t],
+// task order into P_t and P_j,
+//     P_j[r][t] = sum_v w_ref,v[r - k_r(v)] * h_v[t]   over the classes v with k_r(v) in [r-3, r]
+//     P_t[t]    = sum_v h_v[t]
+// normalises by n_c, computes H_t, H_j, err (computeH.cu:261-300; types_six_dof_expmap.cpp:609-635,
+// .h:227) and, when want_jac, stores the scaled tables for k_qtable:
 //   W[r][t] = coefJ * (1 + log2 P_j[r][t]),  V[t] = coefT * (1 + log2 P_t[t])   (0 where P < 1e-30),
-//   coefJ = -(s/(n_c Hj^2)) (Ht + Href), coefT = (s/(n_c Hj^2)) Hj  (types_six_dof_expmap.cpp:486-528),
-// that pass 2 evaluates per pixel.
-#define NID_ASM_BATCH 64
-#define NID_ASM_MAXE 16  // ceil(64*64/256)
-__global__ void __launch_bounds__(256) k_assemble(EvalParams p, int want_jac) {
+//   coefJ = -(s/(n_c Hj^2)) (Ht + Href), coefT = (s/(n_c Hj^2)) Hj  (types_six_dof_expmap.cpp:486-528).
+// Tasks are ordered by class, and k_r(v) is monotone in v, so every histogram row only walks the
+// contiguous task range of its classes (cls_task_start).
+#define NID_ASM_THREADS 512
+#define NID_ASM_MAXE 8  // ceil(64*64/512)
+__global__ void __launch_bounds__(NID_ASM_THREADS) k_assemble(EvalParams p, int want_jac) {
   extern __shared__ double sm[];
-  __shared__ double scratch[8];
-  __shared__ int s_cls[NID_ASM_BATCH];
-  const int B = p.bins, BB = B * B, NS = B - 3;
-  double* Gs = sm;                        // [NID_ASM_BATCH][B]
-  double* Pall = sm + NID_ASM_BATCH * B;  // [BB + B]
+  __shared__ double scratch[NID_ASM_THREADS / 32];
+  __shared__ int s_cts[NID_NCLS + 1];
+  const int B = p.bins, BB = B * B;
+  double* Pall = sm;                 // [BB + B]
+  double* red = sm + BB + B;         // [NID_ASM_THREADS] partial sums of P_t
+  double* hvs = red + NID_ASM_THREADS;  // [NID_NCLS][B] per-class soft histograms
   const int c = blockIdx.x, job = blockIdx.y + p.job0;
   const int pair = p.job_pair[job];
   const int nc = p.n_c[pair * p.ncell + c];
@@ -338,52 +304,49 @@ __global__ void __launch_bounds__(256) k_assemble(EvalParams p, int want_jac) {
     if (threadIdx.x == 0) { p.ht[o] = nan(""); p.hj[o] = nan(""); p.err[o] = nan(""); }
     return;
   }
-  const int t0 = p.cell_task_start[pair * (p.ncell + 1) + c];
-  const int t1 = p.cell_task_start[pair * (p.ncell + 1) + c + 1];
-  const int2* tasks = p.tasks + (size_t)pair * p.max_tasks;
+  const int* cts = p.cls_task_start + ((size_t)pair * p.ncell + c) * (NID_NCLS + 1);
+  for (int i = threadIdx.x; i <= NID_NCLS; i += blockDim.x) s_cts[i] = cts[i];
+  __syncthreads();
   const double* G = p.G + (size_t)job * p.g_stride * B;
-  double acc[NID_ASM_MAXE];
-#pragma unroll
-  for (int e = 0; e < NID_ASM_MAXE; e++) acc[e] = 0.0;
-  double acc_t = 0.0;
-  for (int b0 = t0; b0 < t1; b0 += NID_ASM_BATCH) {
-    const int nb = min(NID_ASM_BATCH, t1 - b0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nb * B; i += blockDim.x) Gs[i] = G[(size_t)b0 * B + i];
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_cls[i] = (tasks[b0 + i].y >> 9) & 0x1ff;
-    __syncthreads();
-    if ((int)threadIdx.x < B)
-      for (int j = 0; j < nb; j++) acc_t += Gs[j * B + threadIdx.x];
-#pragma unroll
-    for (int e = 0; e < NID_ASM_MAXE; e++) {
-      const int idx = threadIdx.x + e * 256;
-      if (idx < BB) {
-        const int r = idx / B, tt = idx % B;
-        double a = acc[e];
-        for (int j = 0; j < nb; j++) {
-          const int v = s_cls[j];
-          if (v < 256) {
-            const int m = r - p.lut_k[v];
-            if (m >= 0 && m < 4) a += p.lut_w[4 * v + m] * Gs[j * B + tt];
-          }
-        }
-        acc[e] = a;
-      }
-    }
+  // ---- per-class sums over the class's tasks (task order), all classes in parallel
+  for (int i = threadIdx.x; i < NID_NCLS * B; i += blockDim.x) {
+    const int v = i / B, tt = i % B;
+    double hv = 0.0;
+    for (int t = s_cts[v]; t < s_cts[v + 1]; t++) hv += G[(size_t)t * B + tt];
+    hvs[i] = hv;
   }
   __syncthreads();
-  double ej = 0.0, et = 0.0;
+  // ---- P_j rows from the classes with k_r in [r-3, r] (class order)
+  double ej = 0.0;
 #pragma unroll
   for (int e = 0; e < NID_ASM_MAXE; e++) {
-    const int idx = threadIdx.x + e * 256;
+    const int idx = threadIdx.x + e * NID_ASM_THREADS;
     if (idx < BB) {
-      double q = acc[e] / (double)nc;
+      const int r = idx / B, tt = idx % B;
+      double a = 0.0;
+      const int vlo = p.row_cls[2 * r], vhi = p.row_cls[2 * r + 1];
+      for (int v = vlo; v < vhi; v++) a += p.lut_w[4 * v + (r - p.lut_k[v])] * hvs[v * B + tt];
+      const double q = a / (double)nc;
       Pall[idx] = q;
       ej -= (q < kSigma) ? 0.0 : q * log2(q);
     }
   }
+  // ---- P_t: thread (g, tt) sums classes g, g+ng, ... ; groups are then added in order
+  {
+    const int ng = NID_ASM_THREADS / B;
+    const int g = threadIdx.x / B, tt = threadIdx.x % B;
+    double a = 0.0;
+    if (g < ng)
+      for (int v = g; v < NID_NCLS; v += ng) a += hvs[v * B + tt];
+    red[threadIdx.x] = a;
+  }
+  __syncthreads();
+  double et = 0.0;
   if ((int)threadIdx.x < B) {
-    double q = acc_t / (double)nc;
+    const int ng = NID_ASM_THREADS / B;
+    double a = 0.0;
+    for (int g = 0; g < ng; g++) a += red[g * B + threadIdx.x];
+    const double q = a / (double)nc;
     Pall[BB + threadIdx.x] = q;
     et -= (q < kSigma) ? 0.0 : q * log2(q);
   }
@@ -400,39 +363,56 @@ __global__ void __launch_bounds__(256) k_assemble(EvalParams p, int want_jac) {
     const double s_over = ((double)(B - 3) / 255.0) / ((double)nc * Hj * Hj);
     const double coefJ = -s_over * (Ht + Href);
     const double coefT = s_over * Hj;
-    __syncthreads();
+    double* wv = p.wv + o * (size_t)(BB + B);
     for (int i = threadIdx.x; i < BB + B; i += blockDim.x) {
       const double q = Pall[i];
       const double L = (q < kSigma) ? 0.0 : (1.0 + log2(q));
-      Pall[i] = L * (i < BB ? coefJ : coefT);
-    }
-    __syncthreads();
-    double* qt = p.qt + o * (size_t)(NID_NCLS * NS * 3);
-    for (int i = threadIdx.x; i < NID_NCLS * NS; i += blockDim.x) {
-      const int v = i / NS, k = i % NS;
-      double wv[4];
-#pragma unroll
-      for (int m = 0; m < 4; m++) wv[m] = Pall[BB + k + m];
-      if (v < 256) {
-        const int kr = p.lut_k[v];
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-          const double wr = p.lut_w[4 * v + kk];
-#pragma unroll
-          for (int m = 0; m < 4; m++) wv[m] += wr * Pall[(kr + kk) * B + k + m];
-        }
-      }
-      double q0 = 0.0, q1 = 0.0, q2 = 0.0;
-#pragma unroll
-      for (int m = 0; m < 4; m++) {
-        const double* cf = p.bs_coef + (k * 4 + m) * 4;
-        q0 += cf[1] * wv[m];
-        q1 += 2.0 * cf[2] * wv[m];
-        q2 += 3.0 * cf[3] * wv[m];
-      }
-      qt[3 * i] = q0; qt[3 * i + 1] = q1; qt[3 * i + 2] = q2;
+      wv[i] = L * (i < BB ? coefJ : coefT);
     }
   }
+}
+
+// Per-class / per-span quadratic of pass 2, one thread per (class v, span k):
+//   c(f) = q0 + q1 f + q2 f^2 = sum_m N'_{k+m}(k+f) * Wv[v][k+m],
+//   Wv[v][t] = V[t] + sum_kk w_ref,v[kk] W[k_r(v)+kk][t]     (class 256: V only)
+// grid (ceil(257*NS/256), ncell, jobs)
+__global__ void __launch_bounds__(256) k_qtable(EvalParams p) {
+  extern __shared__ double sm[];  // W | V | spline table
+  const int B = p.bins, BB = B * B, NS = B - 3;
+  const int c = blockIdx.y, job = blockIdx.z + p.job0;
+  const int pair = p.job_pair[job];
+  if (p.n_c[pair * p.ncell + c] < NID_MIN_CELL_POINTS) return;
+  const size_t o = (size_t)job * p.ncell + c;
+  const double* wvg = p.wv + o * (size_t)(BB + B);
+  double* coef = sm + BB + B;
+  for (int i = threadIdx.x; i < BB + B; i += blockDim.x) sm[i] = wvg[i];
+  for (int i = threadIdx.x; i < NS * 16; i += blockDim.x) coef[i] = p.bs_coef[i];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NID_NCLS * NS) return;
+  const int v = i / NS, k = i % NS;
+  double wv[4];
+#pragma unroll
+  for (int m = 0; m < 4; m++) wv[m] = sm[BB + k + m];
+  if (v < 256) {
+    const int kr = p.lut_k[v];
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      const double wr = p.lut_w[4 * v + kk];
+#pragma unroll
+      for (int m = 0; m < 4; m++) wv[m] += wr * sm[(kr + kk) * B + k + m];
+    }
+  }
+  double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const double* cf = coef + (k * 4 + m) * 4;
+    q0 += cf[1] * wv[m];
+    q1 += 2.0 * cf[2] * wv[m];
+    q2 += 3.0 * cf[3] * wv[m];
+  }
+  double* qt = p.qt + o * (size_t)(NID_NCLS * NS * 3) + 3 * (size_t)i;
+  qt[0] = q0; qt[1] = q1; qt[2] = q2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -566,18 +546,19 @@ int launch_scatter(nid_ctx* c, int pair) {
   return NID_OK;
 }
 
-// warps per CTA of pass 1: as many as fit the lane-private moment store in shared memory (max 8)
+// warps per CTA of pass 1: as many as fit the lane-private histograms in shared memory (max 8)
 static int hist_warps(const nid_ctx* c) {
-  const size_t per_warp = sizeof(double) * ((size_t)(c->bins - 3) * 4 * NID_MROW + c->bins);
+  const size_t per_warp = sizeof(double) * (size_t)c->bins * 32;
   const size_t fixed = sizeof(double) * (size_t)(c->bins - 3) * 16;
   int w = (int)((200 * 1024 - fixed) / per_warp);
   return std::max(1, std::min(w, 8));
 }
 size_t hist_sorted_smem(const nid_ctx* c) {
-  return sizeof(double) * ((size_t)(c->bins - 3) * 16 + (size_t)hist_warps(c) * ((size_t)(c->bins - 3) * 4 * NID_MROW + c->bins));
+  return sizeof(double) * ((size_t)(c->bins - 3) * 16 + (size_t)hist_warps(c) * (size_t)c->bins * 32);
 }
 size_t jac_sorted_smem(const nid_ctx* c) { return sizeof(double) * 8 * (size_t)(c->bins - 3) * 3; }
-size_t assemble_smem(const nid_ctx* c) { return sizeof(double) * (NID_ASM_BATCH * c->bins + c->bins * c->bins + c->bins); }
+size_t assemble_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins); }
+size_t qtable_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)c->bins * c->bins + c->bins + (size_t)(c->bins - 3) * 16); }
 
 int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int want_jac) {
   EvalParams p = make_params(c, n_jobs_total);
@@ -597,8 +578,13 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
   else k_hist_sorted<false><<<dim3((nwarps + hw - 1) / hw, n_jobs), hw * 32, hist_sorted_smem(c), c->stream>>>(p);
   NID_LAUNCH_CHECK(c, "k_hist_sorted");
   ktime_mark(c, 1);
-  k_assemble<<<dim3(c->ncell, n_jobs), 256, assemble_smem(c), c->stream>>>(p, want_jac);
+  k_assemble<<<dim3(c->ncell, n_jobs), NID_ASM_THREADS, assemble_smem(c), c->stream>>>(p, want_jac);
   NID_LAUNCH_CHECK(c, "k_assemble");
+  if (want_jac) {
+    const int items = NID_NCLS * (c->bins - 3);
+    k_qtable<<<dim3((items + 255) / 256, c->ncell, n_jobs), 256, qtable_smem(c), c->stream>>>(p);
+    NID_LAUNCH_CHECK(c, "k_qtable");
+  }
   ktime_mark(c, 2);
   if (want_jac) {
     if (tex) k_jac_sorted<true><<<dim3((nwarps + 7) / 8, n_jobs), 256, jac_sorted_smem(c), c->stream>>>(p);
@@ -627,6 +613,8 @@ int sorted_init(nid_ctx* c) {
   cudaFuncSetAttribute(k_hist_sorted<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   e = cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assemble_smem(c));
   if (e != cudaSuccess) return check_cuda(e, "smem attr k_assemble");
+  e = cudaFuncSetAttribute(k_qtable, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qtable_smem(c));
+  if (e != cudaSuccess) return check_cuda(e, "smem attr k_qtable");
   return NID_OK;
 }
 
