@@ -59,11 +59,13 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   const bool sorted = use_sorted(c);
   p.part = c->part; p.jpart = sorted ? c->jpart_s : c->jpart; p.hist = c->opt_keep_hist ? c->hist : nullptr;
   p.ht = c->ht; p.hj = c->hj; p.err = c->err; p.der = c->der; p.gn = c->gn;
-  p.sx = c->sx; p.sy = c->sy; p.sz = c->sz;
+  p.sd0 = c->sd0; p.sd1 = c->sd1; p.sd2 = c->sd2; p.sid = c->sid;
+  p.sl_off = c->sl_off; p.sl_task = c->sl_task; p.nslices = c->nslices;
+  p.sell_cap = c->sell_cap; p.max_slices = c->max_slices; p.Twc0 = c->Twc0;
   p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start;
   p.cls_task_start = c->cls_task_start; p.row_cls = c->row_cls; p.wv = c->wv;
   p.max_tasks = c->max_tasks; p.g_stride = (int)c->g_stride;
-  p.G = c->G; p.qt = c->qt; p.pp = 1; p.tex = c->d_tex;
+  p.G = c->G; p.qt = c->qt; p.tex = c->d_tex; p.tex2 = c->d_tex2;
   return p;
 }
 
@@ -140,9 +142,11 @@ int ensure_job_buffers(nid_ctx* c) {
 }
 
 static int update_texture(nid_ctx* c, int pair) {
-  if (!c->use_tex) return NID_OK;
   CU(cudaMemcpy2DToArrayAsync(c->tex_arrays[pair], 0, 0, c->im1 + (size_t)pair * c->N, c->cols, c->cols, c->rows,
                               cudaMemcpyDeviceToDevice, c->stream), "im1 -> texture array");
+  OKR(launch_pack_tex(c, pair, c->d_pack));
+  CU(cudaMemcpy2DToArrayAsync(c->tex2_arrays[pair], 0, 0, c->d_pack, sizeof(unsigned) * c->cols, sizeof(unsigned) * c->cols,
+                              c->rows, cudaMemcpyDeviceToDevice, c->stream), "packed im1 -> texture array");
   return NID_OK;
 }
 
@@ -152,6 +156,10 @@ static int stage_jobs(nid_ctx* c, int n_jobs, const int* job_pair, const double*
     int pr = job_pair ? job_pair[j] : 0;
     if (pr < 0 || pr >= c->n_pairs) { set_error("job_pair out of range"); return NID_ERR_ARG; }
     if (!c->pair_prepared[pr]) { set_error("pair not prepared (call nid_prepare)"); return NID_ERR_STATE; }
+    if (use_sorted(c) && !c->pair_sorted[pr]) {
+      set_error("pair not prepared for the sorted path (call nid_prepare after selecting the path)");
+      return NID_ERR_STATE;
+    }
     c->h_job_pair[j] = pr;
   }
   memcpy(c->h_poses, poses, sizeof(double) * 16 * n_jobs);
@@ -186,6 +194,7 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   if (!out) { set_error("ctx out pointer is NULL"); return NID_ERR_ARG; }
   *out = nullptr;
   if (degree != 3) { set_error("only bs_degree == 3 (order-4 B-splines) is supported, as in the reference"); return NID_ERR_UNSUPPORTED; }
+  if (rows > 65535 || cols > 65535) { set_error("rows, cols must be < 65536"); return NID_ERR_ARG; }
   if (rows < 8 || cols < 8 || cell < 1 || bins < 7 || bins > 64 || n_pairs < 1 || max_jobs < 1 || cell > rows || cell > cols) {
     set_error("bad geometry (need rows,cols>=8, 1<=cell<=min(rows,cols), 7<=bins<=64, n_pairs,max_jobs>=1)");
     return NID_ERR_ARG;
@@ -213,8 +222,20 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   OKR(dalloc(&c->n_c, P * NC, "n_c")); OKR(dalloc(&c->href, P * NC, "href"));
   OKR(dalloc(&c->cam, P * 4, "cam")); OKR(dalloc(&c->Twc0, P * 16, "Twc0"));
   OKR(dalloc(&c->cnt, P * NC * NID_NCLS, "cnt"));
-  c->max_tasks = (int)(N / NID_TASK_PX + NC * NID_NCLS + 1);
-  OKR(dalloc(&c->sx, P * N, "sx")); OKR(dalloc(&c->sy, P * N, "sy")); OKR(dalloc(&c->sz, P * N, "sz"));
+  // pixels per task: short tasks when few evaluations are in flight (more threads), longer ones for batches
+  c->task_px = max_jobs >= 8 ? 64 : 32;
+  const int min_task_px = 16;
+  c->max_tasks = (int)(N / min_task_px + NC * NID_NCLS + 1);
+  c->max_slices = c->max_tasks / 32 + (int)NC + 1;
+  // pixel slots per pair: every task is padded to a multiple of 4 and every cell's slices to their longest task
+  c->sell_cap = (N + 3 * (size_t)c->max_tasks + NC * 32 * (size_t)(NID_TASK_PX_MAX + 4) + 255) / 128 * 128;
+  OKR(dalloc(&c->depth, P * N, "depth"));
+  OKR(dalloc(&c->sl_off, P * ((size_t)c->max_slices + 1), "sl_off"));
+  OKR(dalloc(&c->sl_task, P * (size_t)c->max_slices * 32, "sl_task"));
+  OKR(dalloc(&c->task_pos, P * (size_t)c->max_tasks, "task_pos"));
+  OKR(dalloc(&c->nslices, P, "nslices"));
+  CU(cudaMemset(c->nslices, 0, sizeof(int) * P), "memset nslices");
+  c->h_nslices.assign(P, 0);
   OKR(dalloc(&c->tasks, P * (size_t)c->max_tasks, "tasks"));
   OKR(dalloc(&c->ntasks, P, "ntasks"));
   CU(cudaMemset(c->ntasks, 0, sizeof(int) * P), "memset ntasks");
@@ -234,7 +255,6 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
     OKR(dalloc(&c->row_cls, rc.size(), "row_cls"));
     CU(cudaMemcpy(c->row_cls, rc.data(), sizeof(int) * rc.size(), cudaMemcpyHostToDevice), "H2D row_cls");
   }
-  OKR(dalloc(&c->seg_start, P * (NC * NID_NCLS + 1), "seg_start"));
   c->h_ntasks.assign(P, 0);
   // target images as gather-able textures (tex2Dgather needs a CUDA array created with cudaArrayTextureGather)
   {
@@ -263,7 +283,32 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
     }
     OKR(dalloc(&c->d_tex, P, "d_tex"));
     CU(cudaMemcpy(c->d_tex, c->h_tex.data(), sizeof(cudaTextureObject_t) * P, cudaMemcpyHostToDevice), "H2D tex handles");
-    c->use_tex = true;
+    // packed I | Gx | Gy texels, 32 bit
+    c->tex2_arrays.assign(P, nullptr);
+    c->h_tex2.assign(P, 0);
+    cudaChannelFormatDesc cd2 = cudaCreateChannelDesc<unsigned int>();
+    for (size_t i = 0; i < P && ok; i++) {
+      if (cudaMallocArray(&c->tex2_arrays[i], &cd2, cols, rows, cudaArrayTextureGather) != cudaSuccess) { ok = false; break; }
+      cudaResourceDesc rd;
+      memset(&rd, 0, sizeof(rd));
+      rd.resType = cudaResourceTypeArray;
+      rd.res.array.array = c->tex2_arrays[i];
+      cudaTextureDesc td;
+      memset(&td, 0, sizeof(td));
+      td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+      td.filterMode = cudaFilterModePoint;
+      td.readMode = cudaReadModeElementType;
+      td.normalizedCoords = 0;
+      if (cudaCreateTextureObject(&c->h_tex2[i], &rd, &td, nullptr) != cudaSuccess) ok = false;
+    }
+    if (!ok) {
+      cudaGetLastError();
+      set_error("could not create the packed gather textures for the target images");
+      return NID_ERR_CUDA;
+    }
+    OKR(dalloc(&c->d_tex2, P, "d_tex2"));
+    CU(cudaMemcpy(c->d_tex2, c->h_tex2.data(), sizeof(cudaTextureObject_t) * P, cudaMemcpyHostToDevice), "H2D tex2 handles");
+    OKR(dalloc(&c->d_pack, N, "d_pack"));
   }
   OKR(dalloc(&c->d_depth, N, "d_depth")); OKR(dalloc(&c->d_img64, N, "d_img64")); OKR(dalloc(&c->d_flag, 1, "d_flag"));
   OKR(dalloc(&c->lut_w, 256 * 4, "lut_w")); OKR(dalloc(&c->lut_k, 256, "lut_k"));
@@ -277,6 +322,7 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   CU(cudaMallocHost((void**)&c->h_out, sizeof(double) * J * (NC * 8 + 44)), "pinned out");
   c->pair_set.assign(P, 0);
   c->pair_prepared.assign(P, 0);
+  c->pair_sorted.assign(P, 0);
   OKR(launch_build_lut(c));
   {
     std::vector<double> coef;
@@ -297,9 +343,12 @@ int nid_destroy(nid_ctx* c) {
   void* ptrs[] = {c->pwx, c->pwy, c->pwz, c->im0, c->im1, c->inb0, c->n_c, c->href, c->cam, c->Twc0, c->cnt, c->d_depth,
                   c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
                   c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
-                  c->bs_coef, c->sx, c->sy, c->sz, c->tasks, c->ntasks, c->cell_task_start, c->seg_start, c->G, c->qt, c->jpart_s, c->d_tex, c->cls_task_start, c->row_cls, c->wv};
+                  c->bs_coef, c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->nslices, c->task_pos,
+                  c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->G, c->qt, c->jpart_s, c->d_tex, c->cls_task_start, c->row_cls, c->wv};
   for (auto t : c->h_tex) if (t) cudaDestroyTextureObject(t);
+  for (auto t : c->h_tex2) if (t) cudaDestroyTextureObject(t);
   for (auto arr : c->tex_arrays) if (arr) cudaFreeArray(arr);
+  for (auto arr : c->tex2_arrays) if (arr) cudaFreeArray(arr);
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->h_poses) cudaFreeHost(c->h_poses);
   if (c->h_job_pair) cudaFreeHost(c->h_job_pair);
@@ -320,7 +369,7 @@ static int set_pair_common(nid_ctx* c, int pair, const double* depth, const doub
   if (pair < 0 || pair >= c->n_pairs) { set_error("pair index out of range"); return NID_ERR_ARG; }
   if (!depth || !T_wc0 || !intr) { set_error("NULL argument"); return NID_ERR_ARG; }
   CU(cudaSetDevice(c->device), "cudaSetDevice");
-  CU(cudaMemcpyAsync(c->d_depth, depth, sizeof(double) * c->N, cudaMemcpyDefault, c->stream), "H2D depth");
+  CU(cudaMemcpyAsync(c->depth + (size_t)pair * c->N, depth, sizeof(double) * c->N, cudaMemcpyDefault, c->stream), "H2D depth");
   CU(cudaMemcpyAsync(c->Twc0 + 16 * pair, T_wc0, sizeof(double) * 16, cudaMemcpyDefault, c->stream), "H2D Twc0");
   CU(cudaMemcpyAsync(c->cam + 4 * pair, intr, sizeof(double) * 4, cudaMemcpyDefault, c->stream), "H2D intr");
   OKR(launch_points(c, pair));
@@ -385,6 +434,12 @@ int nid_set_pair_points(nid_ctx* c, int pair, const double* points_3d, const dou
     CU(cudaMemcpyAsync(c->cam + 4 * pair, intr, sizeof(double) * 4, cudaMemcpyDefault, c->stream), "H2D intr");
     OKR(launch_points_soa(c, pair, c->d_pix));
     c->pair_prepared[pair] = 0;
+    if (!c->sell_points) {
+      // caller-supplied world points cannot be rebuilt from (depth, pixel): the sorted store keeps the points
+      CU(cudaStreamSynchronize(c->stream), "sync before switching to the point form");
+      c->sell_points = true;
+      std::fill(c->pair_prepared.begin(), c->pair_prepared.end(), 0);
+    }
   }
   OKR(upload_images_f64(c, pair, im0, im1));
   c->pair_set[pair] = 1;
@@ -426,18 +481,29 @@ int nid_get_points3d(nid_ctx* c, int pair, double* points_3d) {
   return NID_OK;
 }
 
-// Regroup the pair's valid pixels by (cell, reference class) and cut the segments into warp tasks. The
-// class counts come from the device; offsets and the task table are integer bookkeeping done here.
+// Regroup the pair's valid pixels by (cell, reference class), cut the segments into tasks of at most
+// task_px pixels, order the tasks by length and pack them 32 to a slice (nid_sorted.cu). The class counts
+// come from the device; offsets and tables are integer bookkeeping done here, the pixels are moved by
+// k_scatter_sell.
 static int build_sorted_layout(nid_ctx* c, int pair) {
-  const int NC = c->ncell;
+  const int NC = c->ncell, L = c->task_px;
+  c->pair_sorted[pair] = 0;
+  if (!use_sorted(c)) return NID_OK;  // the natural-order kernels need none of this
+  if (!c->sd0) {
+    OKR(dalloc(&c->sd0, (size_t)c->n_pairs * c->sell_cap, "sd0"));
+    OKR(dalloc(&c->sid, (size_t)c->n_pairs * c->sell_cap, "sid"));
+  }
+  if (c->sell_points && !c->sd1) {
+    OKR(dalloc(&c->sd1, (size_t)c->n_pairs * c->sell_cap, "sd1"));
+    OKR(dalloc(&c->sd2, (size_t)c->n_pairs * c->sell_cap, "sd2"));
+  }
   std::vector<unsigned int> cnt((size_t)NC * NID_NCLS);
   CU(cudaMemcpyAsync(cnt.data(), c->cnt + (size_t)pair * NC * NID_NCLS, sizeof(unsigned int) * cnt.size(),
                      cudaMemcpyDeviceToHost, c->stream), "D2H cnt");
   CU(cudaStreamSynchronize(c->stream), "sync cnt");
-  std::vector<int> seg((size_t)NC * NID_NCLS + 1), cts(NC + 1), clsts((size_t)NC * (NID_NCLS + 1));
+  std::vector<int> cts(NC + 1), clsts((size_t)NC * (NID_NCLS + 1));
   std::vector<int2> tasks;
   tasks.reserve(c->max_tasks);
-  int off = 0;
   for (int cell = 0; cell < NC; cell++) {
     cts[cell] = (int)tasks.size();
     long long n_c = 0;
@@ -445,26 +511,60 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
     const bool active = n_c >= NID_MIN_CELL_POINTS;  // inactive cells get no work at all
     for (int v = 0; v < NID_NCLS; v++) {
       const int len = (int)cnt[(size_t)cell * NID_NCLS + v];
-      seg[(size_t)cell * NID_NCLS + v] = off;
       clsts[(size_t)cell * (NID_NCLS + 1) + v] = (int)tasks.size();
-      for (int o = 0; active && o < len; o += NID_TASK_PX) {
+      for (int o = 0; active && o < len; o += L) {
         int2 t;
-        t.x = off + o;
-        t.y = std::min(NID_TASK_PX, len - o) | (v << 9) | (cell << 18);
+        t.x = o;
+        t.y = std::min(L, len - o) | (v << 9) | (cell << 18);
         tasks.push_back(t);
       }
-      off += len;
     }
     clsts[(size_t)cell * (NID_NCLS + 1) + NID_NCLS] = (int)tasks.size();
   }
-  seg[(size_t)NC * NID_NCLS] = off;
   cts[NC] = (int)tasks.size();
   const int nt = (int)tasks.size();
   if (nt > c->max_tasks || NC > 0x3fff) { set_error("task table overflow"); return NID_ERR_STATE; }
-  CU(cudaMemcpyAsync(c->seg_start + (size_t)pair * (NC * NID_NCLS + 1), seg.data(), sizeof(int) * seg.size(),
-                     cudaMemcpyHostToDevice, c->stream), "H2D seg_start");
-  if (nt) CU(cudaMemcpyAsync(c->tasks + (size_t)pair * c->max_tasks, tasks.data(), sizeof(int2) * nt,
-                             cudaMemcpyHostToDevice, c->stream), "H2D tasks");
+  // Slices: the tasks of a cell ordered by length (longest first; counting sort, ties keep task order) and cut
+  // into groups of 32. Slices never mix cells: the lanes of a warp then sample one cell-sized region of the
+  // target image (texture-cache locality) and still run out of work together.
+  std::vector<int> sl_off(1, 0), sl_task, task_pos(std::max(nt, 1));
+  sl_task.reserve((size_t)nt + 32 * (size_t)NC);
+  long long off = 0;
+  {
+    std::vector<int> order, bucket(NID_TASK_PX_MAX + 2);
+    for (int cell = 0; cell < NC; cell++) {
+      const int t0 = cts[cell], t1 = cts[cell + 1];
+      if (t1 == t0) continue;
+      order.assign(t1 - t0, 0);
+      std::fill(bucket.begin(), bucket.end(), 0);
+      for (int t = t0; t < t1; t++) bucket[NID_TASK_PX_MAX - (tasks[t].y & 0x1ff) + 1]++;
+      for (int i = 1; i <= NID_TASK_PX_MAX + 1; i++) bucket[i] += bucket[i - 1];
+      for (int t = t0; t < t1; t++) order[bucket[NID_TASK_PX_MAX - (tasks[t].y & 0x1ff)]++] = t;
+      for (int s0 = 0; s0 < t1 - t0; s0 += 32) {
+        const int longest = tasks[order[s0]].y & 0x1ff;
+        for (int l = 0; l < 32; l++) {
+          const int t = s0 + l < t1 - t0 ? order[s0 + l] : -1;
+          sl_task.push_back(t);
+          if (t >= 0) task_pos[t] = (int)off + 4 * l;
+        }
+        off += (long long)((longest + 3) / 4) * 128;
+        sl_off.push_back((int)off);
+      }
+    }
+  }
+  const int ns = (int)sl_off.size() - 1;
+  if ((size_t)off > c->sell_cap || ns > c->max_slices) { set_error("sliced pixel store overflow"); return NID_ERR_STATE; }
+  if (nt) {
+    CU(cudaMemcpyAsync(c->tasks + (size_t)pair * c->max_tasks, tasks.data(), sizeof(int2) * nt, cudaMemcpyHostToDevice,
+                       c->stream), "H2D tasks");
+    CU(cudaMemcpyAsync(c->task_pos + (size_t)pair * c->max_tasks, task_pos.data(), sizeof(int) * nt,
+                       cudaMemcpyHostToDevice, c->stream), "H2D task_pos");
+    CU(cudaMemcpyAsync(c->sl_task + (size_t)pair * c->max_slices * 32, sl_task.data(), sizeof(int) * sl_task.size(),
+                       cudaMemcpyHostToDevice, c->stream), "H2D sl_task");
+  }
+  CU(cudaMemcpyAsync(c->sl_off + (size_t)pair * (c->max_slices + 1), sl_off.data(), sizeof(int) * (ns + 1),
+                     cudaMemcpyHostToDevice, c->stream), "H2D sl_off");
+  CU(cudaMemcpyAsync(c->nslices + pair, &ns, sizeof(int), cudaMemcpyHostToDevice, c->stream), "H2D nslices");
   CU(cudaMemcpyAsync(c->cell_task_start + (size_t)pair * (NC + 1), cts.data(), sizeof(int) * (NC + 1),
                      cudaMemcpyHostToDevice, c->stream), "H2D cell_task_start");
   CU(cudaMemcpyAsync(c->ntasks + pair, &nt, sizeof(int), cudaMemcpyHostToDevice, c->stream), "H2D ntasks");
@@ -473,8 +573,12 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
   OKR(launch_scatter(c, pair));
   CU(cudaStreamSynchronize(c->stream), "sync scatter");  // host vectors go out of scope
   c->h_ntasks[pair] = nt;
+  c->h_nslices[pair] = ns;
+  c->pair_sorted[pair] = 1;
   c->max_ntasks_prepared = 0;
   for (int v : c->h_ntasks) c->max_ntasks_prepared = std::max(c->max_ntasks_prepared, v);
+  c->max_nslices_prepared = 0;
+  for (int v : c->h_nslices) c->max_nslices_prepared = std::max(c->max_nslices_prepared, v);
   return NID_OK;
 }
 
@@ -591,7 +695,7 @@ int nid_solve_jobs(nid_ctx* c, int n, const int* job_pair, double* poses7, int m
     LM& s = st[j];
     s.pair = job_pair ? job_pair[j] : j;
     if (s.pair < 0 || s.pair >= c->n_pairs) { set_error("job_pair out of range"); return NID_ERR_ARG; }
-    if (!c->pair_prepared[s.pair]) { set_error("pair not prepared"); return NID_ERR_STATE; }
+    if (!c->pair_prepared[s.pair] || (use_sorted(c) && !c->pair_sorted[s.pair])) { set_error("pair not prepared"); return NID_ERR_STATE; }
     memcpy(s.est.t, poses7 + 7 * j, sizeof(double) * 3);
     memcpy(s.est.q, poses7 + 7 * j + 3, sizeof(double) * 4);
     s.phase = max_iters > 0 ? 0 : 2;
@@ -789,8 +893,16 @@ int nid_set_option(nid_ctx* c, const char* key, int value) {
     return NID_OK;
   }
   if (!strcmp(key, "keep_hist")) { c->opt_keep_hist = value; return NID_OK; }
-  if (!strcmp(key, "tasks_per_warp")) { c->opt_tasks_per_warp = value; return NID_OK; }
-  if (!strcmp(key, "use_tex")) { c->use_tex = value != 0 && c->d_tex != nullptr; return NID_OK; }
+  if (!strcmp(key, "ilp_hist")) { c->opt_ilp_hist = value; return NID_OK; }
+  if (!strcmp(key, "ilp_jac")) { c->opt_ilp_jac = value; return NID_OK; }
+  if (!strcmp(key, "task_px")) {
+    if (value < 16 || value > NID_TASK_PX_MAX || (value & 3)) { set_error("task_px must be a multiple of 4 in [16, 256]"); return NID_ERR_ARG; }
+    if (value != c->task_px) {
+      c->task_px = value;
+      std::fill(c->pair_prepared.begin(), c->pair_prepared.end(), 0);  // the pixel store is laid out per task
+    }
+    return NID_OK;
+  }
   if (!strcmp(key, "time_kernels")) {
     c->opt_time_kernels = value;
     for (int i = 0; i < 4; i++) { c->kernel_ms[i] = 0; c->kernel_calls[i] = 0; }

@@ -8,7 +8,7 @@
 #include "../../include/nid_b200.h"
 
 #define NID_NCLS 257  /* reference-intensity classes 0..255 + 256 = valid point without reference sample */
-#define NID_TASK_PX 256 /* pixels per warp task of the sorted path */
+#define NID_TASK_PX_MAX 256 /* upper bound of the pixels per task of the sorted path (option "task_px") */
 
 namespace nid {
 
@@ -46,11 +46,18 @@ struct EvalParams {
   double* gn;           // [jobs][44] : chi2, H[36], b[6], n_active
   double huber_delta;
   double huber_dsqr;
-  // sorted path
-  const double* sx;     // [n_pairs][N] world points regrouped by (cell, class)
-  const double* sy;
-  const double* sz;
-  const int2* tasks;    // [n_pairs][max_tasks] {start, count | cls<<9 | cell<<18}
+  // sorted path: sliced-ELL pixel store, see nid_sorted.cu
+  const double* sd0;    // [n_pairs][sell_cap] depth z (depth form) or world x (point form)
+  const double* sd1;    // point form only: world y
+  const double* sd2;    // point form only: world z
+  const unsigned* sid;  // [n_pairs][sell_cap] (row << 16) | col, 0xFFFFFFFF = padding
+  const int* sl_off;    // [n_pairs][max_slices+1] first pixel slot of every slice (multiples of 128)
+  const int* sl_task;   // [n_pairs][max_slices*32] task of every lane, -1 = none
+  const int* nslices;   // [n_pairs]
+  size_t sell_cap;      // pixel slots per pair
+  int max_slices;
+  const double* Twc0;   // [n_pairs][16]
+  const int2* tasks;    // [n_pairs][max_tasks] {rank of first pixel in its class segment, count | cls<<9 | cell<<18}
   const int* ntasks;    // [n_pairs]
   const int* cell_task_start;  // [n_pairs][ncell+1]
   const int* cls_task_start;   // [n_pairs][ncell][NID_NCLS+1] first task of every class
@@ -60,8 +67,8 @@ struct EvalParams {
   int g_stride;         // partial-buffer stride per job (tasks)
   double* G;            // [jobs][g_stride][bins]
   double* qt;           // [jobs][ncell][NID_NCLS][bins-3][3] per-class, per-span Jacobian quadratics
-  const cudaTextureObject_t* tex;  // [n_pairs] target image as a gather-able 2D texture
-  int pp;               // tasks per warp (sorted path)
+  const cudaTextureObject_t* tex;   // [n_pairs] target image as a gather-able 8-bit 2D texture
+  const cudaTextureObject_t* tex2;  // [n_pairs] packed I | Gx | Gy 32-bit texture (k_pack_tex)
 };
 
 }  // namespace nid
@@ -84,28 +91,36 @@ struct nid_ctx {
   double* Twc0 = nullptr;      // [n_pairs][16]
   unsigned int* cnt = nullptr; // [n_pairs][ncell][NID_NCLS] pixel counts per reference class at prepare
   // sorted path, per pair
-  double *sx = nullptr, *sy = nullptr, *sz = nullptr;
+  double* depth = nullptr;     // [n_pairs][N] reference depth as uploaded (depth form)
+  double *sd0 = nullptr, *sd1 = nullptr, *sd2 = nullptr;
+  unsigned* sid = nullptr;
+  size_t sell_cap = 0;
+  int *sl_off = nullptr, *sl_task = nullptr, *nslices = nullptr, *task_pos = nullptr;
+  int max_slices = 0;
+  std::vector<int> h_nslices;
+  int max_nslices_prepared = 0;
+  int task_px = 64;            // L: pixels per task
+  int opt_ilp_hist = 1, opt_ilp_jac = 1;  // pixels a lane processes together in pass 1 / pass 2
+  bool sell_points = false;    // pairs carry caller-supplied world points (nid_set_pair_points)
   int2* tasks = nullptr;
   int* ntasks = nullptr;
   int* cell_task_start = nullptr;
   int* cls_task_start = nullptr;
   int* row_cls = nullptr;
   double* wv = nullptr;
-  int* seg_start = nullptr;    // [n_pairs][ncell*NID_NCLS+1]
   int max_tasks = 0;
   std::vector<int> h_ntasks;
   int max_ntasks_prepared = 0;
   // sorted path, per job (grown on demand)
   double *G = nullptr, *qt = nullptr, *jpart_s = nullptr;
-  std::vector<cudaArray_t> tex_arrays;
-  std::vector<cudaTextureObject_t> h_tex;
-  cudaTextureObject_t* d_tex = nullptr;
-  bool use_tex = false;
-  int opt_tasks_per_warp = 0;
+  std::vector<cudaArray_t> tex_arrays, tex2_arrays;
+  std::vector<cudaTextureObject_t> h_tex, h_tex2;
+  cudaTextureObject_t *d_tex = nullptr, *d_tex2 = nullptr;
+  unsigned* d_pack = nullptr;  // [N] scratch for the packed texture
   size_t g_stride = 0;
   int opt_path = 0;            // 0 auto, 1 natural-order atomics (v1), 2 sorted
   int opt_keep_hist = 0;
-  std::vector<char> pair_set, pair_prepared;
+  std::vector<char> pair_set, pair_prepared, pair_sorted;
   // staging
   double* d_depth = nullptr;   // [N] scratch
   double* d_img64 = nullptr;   // [N] scratch for the f64 image entry point
@@ -167,6 +182,7 @@ int ensure_job_buffers(nid_ctx* c);
 int sorted_init(nid_ctx* c);
 int launch_count_classes(nid_ctx* c, int pair);
 int launch_scatter(nid_ctx* c, int pair);
+int launch_pack_tex(nid_ctx* c, int pair, unsigned* d_out);
 int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int want_jac);
 int launch_href(nid_ctx* c, int pair);
 

@@ -47,6 +47,14 @@ __device__ __forceinline__ void warp_project(const Pose& P, const Cam& cam, doub
 #endif
 }
 
+// The CPU edge projects a second time in linearizeOplus, as fx*(x/z)+cx (types_six_dof_expmap.cpp:407-421);
+// its Jacobian bounds test (:433) and gradient samples (:434-435) use this value, which can differ from
+// warp_project's (fx*x)/z+cx in the last bit -- visible only when (u, v) sits on an integer.
+__device__ __forceinline__ void project_jac(const Cam& cam, double x1, double y1, double z1, double& u2, double& v2) {
+  u2 = __dadd_rn(__dmul_rn(cam.fx, __ddiv_rn(x1, z1)), cam.cx);
+  v2 = __dadd_rn(__dmul_rn(cam.fy, __ddiv_rn(y1, z1)), cam.cy);
+}
+
 // CudaPoints3d.cu:20-28 (same order, no contraction)
 __device__ __forceinline__ void backproject(const double* __restrict__ T, const Cam& cam, double z, int row, int col,
                                             double& xw, double& yw, double& zw) {
@@ -72,12 +80,17 @@ __device__ __forceinline__ double interp_u8(const uint8_t* __restrict__ im, int 
   int iy = (int)y;
   double dx = x - (double)ix;
   double dy = y - (double)iy;
-  double dxdy = dx * dy;
+  double dxdy = __dmul_rn(dx, dy);
   const uint8_t* r0 = im + (size_t)iy * cols + ix;
   const uint8_t* r1 = r0 + cols;
   double p00 = (double)__ldg(r0), p01 = (double)__ldg(r0 + 1);
   double p10 = (double)__ldg(r1), p11 = (double)__ldg(r1 + 1);
-  return dxdy * p11 + (dy - dxdy) * p10 + (dx - dxdy) * p01 + (1.0 - dx - dy + dxdy) * p00;
+  // the reference's term order without fused multiply-adds: on a saturated plateau the `>= 255` clamp that
+  // follows sees the last bit of this sum
+  double a = __dmul_rn(dxdy, p11);
+  a = __dadd_rn(a, __dmul_rn(__dsub_rn(dy, dxdy), p10));
+  a = __dadd_rn(a, __dmul_rn(__dsub_rn(dx, dxdy), p01));
+  return __dadd_rn(a, __dmul_rn(__dadd_rn(__dsub_rn(__dsub_rn(1.0, dx), dy), dxdy), p00));
 }
 
 __device__ __forceinline__ double clamp_intensity(double ic) {

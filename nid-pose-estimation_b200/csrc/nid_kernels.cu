@@ -345,10 +345,12 @@ __global__ void __launch_bounds__(256) k_jac(EvalParams p) {
     if (isnan(x0)) continue;
     double x, y, z, u, v;
     warp_project(P, cam, x0, p.pwy[i], p.pwz[i], x, y, z, u, v);
-    if (!inb_jac(u, v, p.rows, p.cols)) continue;
+    double u2, v2;
+    project_jac(cam, x, y, z, u2, v2);
+    if (!inb_cost(u, v, p.rows, p.cols) || !inb_jac(u2, v2, p.rows, p.cols)) continue;
     const double ic = clamp_intensity(interp_u8(im1, p.cols, u, v));
-    const double gx = (interp_u8(im1, p.cols, u + 1.0, v) - interp_u8(im1, p.cols, u - 1.0, v)) / 2;
-    const double gy = (interp_u8(im1, p.cols, u, v + 1.0) - interp_u8(im1, p.cols, u, v - 1.0)) / 2;
+    const double gx = (interp_u8(im1, p.cols, u2 + 1.0, v2) - interp_u8(im1, p.cols, u2 - 1.0, v2)) / 2;
+    const double gy = (interp_u8(im1, p.cols, u2, v2 + 1.0) - interp_u8(im1, p.cols, u2, v2 - 1.0)) / 2;
     const double ub = __ddiv_rn(__dmul_rn(ic, scale), 255.0);
     const int kt = (int)floor(ub);
     double wt[4], dw[4];
@@ -529,13 +531,15 @@ __global__ void __launch_bounds__(256) k_warp_sample(EvalParams p, int pair, con
     if (!isnan(x0)) {
       double x1, y1;
       warp_project(P, cam, x0, p.pwy[base + i], p.pwz[base + i], x1, y1, z1, u, v);
+      double u2, v2;
+      project_jac(cam, x1, y1, z1, u2, v2);
       vc = inb_cost(u, v, p.rows, p.cols);
-      vj = inb_jac(u, v, p.rows, p.cols);
+      vj = vc && inb_jac(u2, v2, p.rows, p.cols);
       ic = 0; gx = 0; gy = 0;
       if (vc) ic = clamp_intensity(interp_u8(im1, p.cols, u, v));
       if (vj) {
-        gx = (interp_u8(im1, p.cols, u + 1.0, v) - interp_u8(im1, p.cols, u - 1.0, v)) / 2;
-        gy = (interp_u8(im1, p.cols, u, v + 1.0) - interp_u8(im1, p.cols, u, v - 1.0)) / 2;
+        gx = (interp_u8(im1, p.cols, u2 + 1.0, v2) - interp_u8(im1, p.cols, u2 - 1.0, v2)) / 2;
+        gy = (interp_u8(im1, p.cols, u2, v2 + 1.0) - interp_u8(im1, p.cols, u2, v2 - 1.0)) / 2;
       }
     }
     if (F64) {
@@ -569,7 +573,7 @@ int launch_build_lut(nid_ctx* c) {
 
 int launch_points(nid_ctx* c, int pair) {
   size_t b = (size_t)pair * c->N;
-  k_points<<<grid_for(c->N, 256, c->sm_count * 8), 256, 0, c->stream>>>(c->rows, c->cols, c->d_depth, c->Twc0 + 16 * pair,
+  k_points<<<grid_for(c->N, 256, c->sm_count * 8), 256, 0, c->stream>>>(c->rows, c->cols, c->depth + b, c->Twc0 + 16 * pair,
                                                                        c->cam + 4 * pair, c->pwx + b, c->pwy + b, c->pwz + b);
   NID_LAUNCH_CHECK(c, "k_points");
   return NID_OK;

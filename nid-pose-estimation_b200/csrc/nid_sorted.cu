@@ -1,21 +1,35 @@
 // "Sorted" evaluation path (the production path for cells of a few thousand pixels and more).
 //
-// Idea. The reference image never changes between the evaluations of one pair, and a pixel's four
-// reference spline weights depend only on its 8-bit reference intensity v. nid_prepare therefore
-// regroups the valid pixels of every cell by v (257 classes: 0..255, plus 256 = "no reference sample":
-// valid depth but out of bounds at the prepare pose, which the CPU edge still counts in the target
-// marginal, types_six_dof_expmap.cpp:593-602 with zero bs_value_ref_ rows). For a class the joint
-// histogram update  P_j[k_r+m][k_t+n] += w_ref[m] * w_t[n]  (types_six_dof_expmap.cpp:598-601)
-// factors into  w_ref[m] * ( sum_i w_t,i[n] ): one *un-weighted* soft histogram h_v[B] per class, 4
-// accumulations per pixel instead of 20, and
+// Idea 1 -- class factorisation. The reference image never changes between the evaluations of one pair,
+// and a pixel's four reference spline weights depend only on its 8-bit reference intensity v.
+// nid_prepare therefore regroups the valid pixels of every cell by v (257 classes: 0..255, plus 256 =
+// "no reference sample": valid depth but out of bounds at the prepare pose, which the CPU edge still
+// counts in the target marginal, types_six_dof_expmap.cpp:593-602 with zero bs_value_ref_ rows). For a
+// class the joint histogram update  P_j[k_r+m][k_t+n] += w_ref[m] * w_t[n]
+// (types_six_dof_expmap.cpp:598-601) factors into  w_ref[m] * ( sum_i w_t,i[n] ): one *un-weighted* soft
+// histogram h_v[B] per class, 4 accumulations per pixel instead of 20, and
 //     P_j[r][t] = sum_v w_ref,v[r - k_r(v)] * h_v[t],      P_t[t] = sum_v h_v[t].
-// The same factorisation turns the Jacobian's 16-term table lookup into a 4-term one against a
-// per-class row  Wv[t] = V[t] + sum_k w_ref,v[k] W[k_r(v)+k][t].
+// The same factorisation turns the Jacobian's 16-term table lookup into one quadratic per (class, span).
 //
-// Work unit = "task": up to 256 consecutive pixels of one (cell, class) segment, processed by ONE WARP
-// with lane-private accumulators in shared memory (no atomics: 64-bit shared atomics are CAS loops on
-// sm_100, profiles/r01_atom_bench_microbenchmark.txt), merged by the warp in a fixed lane order and
-// written as a partial. Partials are combined per cell in task order => results are bit-reproducible.
+// Idea 2 -- one lane per task, sliced-ELL storage. A "task" is up to L consecutive pixels of one
+// (cell, class) segment. 64-bit shared-memory atomics are CAS loops on sm_100
+// (profiles/r01_atom_bench_microbenchmark.txt), so nothing is shared: ONE THREAD owns a task, walks its
+// pixels sequentially and accumulates into a private shared-memory row (pass 1) or registers (pass 2).
+// Tasks are ordered by length and packed 32 to a "slice" (one warp); the pixels of a slice are stored
+// interleaved -- group g of lane l at slice_off + (g*32 + l)*4 -- so every warp load is a fully coalesced
+// 128-bit access and the lanes of a warp run out of work together (SELL-C-sigma, as in sparse mat-vec).
+// Each task writes one partial; partials are combined per cell in task order => no floating-point
+// atomics anywhere and bit-reproducible results.
+//
+// Idea 3 -- a fast path that cannot change a decision. Per pixel only the depth z and the pixel index are
+// stored (12 B); the camera-frame point is z * (M0 cxn + M1 cyn + M2) + M3 with M = T_cw1 * T_wc0 composed
+// once per job, and one reciprocal serves the projection and the Jacobian. That differs from the
+// reference's operation order (CudaPoints3d.cu:20-28, computeH.cu:152-158) by a few ulp, which is harmless
+// everywhere except at the reference's discontinuities: the in-bounds tests, the (int) truncation of
+// (u, v) and the `>= 255 -> 254.999` clamp on saturated plateaus. A pixel whose (u, v) lands within 2^-24
+// of an integer, or whose four taps are all 255, is therefore re-evaluated with the reference's exact
+// sequence (exact_uv), so every decision is bit-identical to the reference's and everything else agrees
+// to ~1e-13.
 #include <math.h>
 
 #include <algorithm>
@@ -32,34 +46,51 @@ namespace nid {
     if (e__ != cudaSuccess) return check_cuda(e__, what); \
   } while (0)
 
-__device__ __forceinline__ void unpack_task(int2 t, int& start, int& count, int& cls, int& cell) {
-  start = t.x;
-  count = t.y & 0x1ff;
-  cls = (t.y >> 9) & 0x1ff;
-  cell = (t.y >> 18) & 0x3fff;
+#define NID_PAD_ID 0xFFFFFFFFu
+
+// counts per (cell, class) from existing in-bounds flags (nid_import_prepare path)
+__global__ void k_count_classes(EvalParams p, int pair, unsigned int* __restrict__ cnt) {
+  const size_t base = (size_t)pair * p.N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.N; i += gridDim.x * blockDim.x) {
+    int row = i / p.cols, col = i % p.cols;
+    if (isnan(p.pwx[base + i]) || row >= p.rb * p.cell || col >= p.cb * p.cell) continue;
+    int c = (row / p.rb) * p.cell + (col / p.cb);
+    int key = p.inb0[base + i] ? (int)p.im0[base + i] : 256;
+    atomicAdd(&cnt[((size_t)pair * p.ncell + c) * NID_NCLS + key], 1u);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// prepare: stable counting-sort scatter of a cell's valid pixels into (class, row-major) order.
-// One CTA per cell. key: 0..255 reference intensity (in bounds at the prepare pose), 256 valid but out
-// of bounds, -1 invalid depth.
-__global__ void __launch_bounds__(256) k_scatter(EvalParams p, int pair, const int* __restrict__ seg_start,
-                                                 double* __restrict__ sx, double* __restrict__ sy,
-                                                 double* __restrict__ sz) {
+// prepare: stable counting-sort scatter of a cell's valid pixels into the sliced-ELL layout. One CTA per
+// cell. key: 0..255 reference intensity (in bounds at the prepare pose), 256 valid but out of bounds,
+// -1 invalid depth. The r-th pixel (row-major order) of class `key` goes to pixel o = r % L of task
+// cls_task_start[key] + r / L, i.e. to  task_pos[task] + (o/4)*128 + o%4.
+// PTS: store the world point (pairs set from caller-supplied points); else the depth z only.
+template <bool PTS>
+__global__ void __launch_bounds__(256) k_scatter_sell(EvalParams p, int pair, int L, const double* __restrict__ depth,
+                                                      const int* __restrict__ task_pos, double* __restrict__ sd0,
+                                                      double* __restrict__ sd1, double* __restrict__ sd2,
+                                                      unsigned* __restrict__ sid) {
   __shared__ int run[NID_NCLS];
+  __shared__ int s_cts[NID_NCLS + 1];
   const int c = blockIdx.x;
+  if (p.n_c[pair * p.ncell + c] < NID_MIN_CELL_POINTS) return;  // inactive cells have no tasks
   const size_t base = (size_t)pair * p.N;
-  for (int k = threadIdx.x; k < NID_NCLS; k += blockDim.x) run[k] = seg_start[c * NID_NCLS + k];
+  const int* cts = p.cls_task_start + ((size_t)pair * p.ncell + c) * (NID_NCLS + 1);
+  for (int k = threadIdx.x; k < NID_NCLS; k += blockDim.x) run[k] = 0;
+  for (int k = threadIdx.x; k <= NID_NCLS; k += blockDim.x) s_cts[k] = cts[k];
   __syncthreads();
   const int r0 = (c / p.cell) * p.rb, c0 = (c % p.cell) * p.cb;
   const int npx = p.rb * p.cb;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t sbase = (size_t)pair * p.sell_cap;
   for (int t0 = 0; t0 < npx; t0 += blockDim.x) {
     const int t = t0 + threadIdx.x;
-    int key = -1;
+    int key = -1, row = 0, col = 0;
     size_t i = 0;
     if (t < npx) {
-      i = base + (size_t)(r0 + t / p.cb) * p.cols + (c0 + t % p.cb);
+      row = r0 + t / p.cb; col = c0 + t % p.cb;
+      i = base + (size_t)row * p.cols + col;
       if (!isnan(p.pwx[i])) key = p.inb0[i] ? (int)p.im0[i] : 256;
     }
     const unsigned mask = __match_any_sync(0xffffffffu, key);
@@ -76,202 +107,319 @@ __global__ void __launch_bounds__(256) k_scatter(EvalParams p, int pair, const i
     }
     pos = __shfl_sync(0xffffffffu, pos, leader) + rank;
     if (key >= 0) {
-      sx[base + pos] = p.pwx[i];
-      sy[base + pos] = p.pwy[i];
-      sz[base + pos] = p.pwz[i];
+      const int task = s_cts[key] + pos / L, o = pos % L;
+      const size_t dst = sbase + (size_t)task_pos[task] + (size_t)(o >> 2) * 128 + (o & 3);
+      if (PTS) { sd0[dst] = p.pwx[i]; sd1[dst] = p.pwy[i]; sd2[dst] = p.pwz[i]; }
+      else sd0[dst] = depth[(size_t)row * p.cols + col];
+      sid[dst] = ((unsigned)row << 16) | (unsigned)col;
     }
   }
 }
 
-// counts per (cell, class) from existing in-bounds flags (nid_import_prepare path)
-__global__ void k_count_classes(EvalParams p, int pair, unsigned int* __restrict__ cnt) {
-  const size_t base = (size_t)pair * p.N;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.N; i += gridDim.x * blockDim.x) {
-    int row = i / p.cols, col = i % p.cols;
-    if (isnan(p.pwx[base + i]) || row >= p.rb * p.cell || col >= p.cb * p.cell) continue;
-    int c = (row / p.rb) * p.cell + (col / p.cb);
-    int key = p.inb0[base + i] ? (int)p.im0[base + i] : 256;
-    atomicAdd(&cnt[((size_t)pair * p.ncell + c) * NID_NCLS + key], 1u);
+// Packed target texture: texel = I | (Gx+256) << 8 | (Gy+256) << 17 with the central differences
+// Gx = I(x+1,y) - I(x-1,y), Gy = I(x,y+1) - I(x,y-1) (types_six_dof_expmap.cpp:434-435 before the /2);
+// one 2x2 gather then holds everything the bilinear samples of I, dI/du and dI/dv need. Border texels
+// use clamped neighbours and are never consumed (the first row/column takes the literal formula).
+__global__ void k_pack_tex(int rows, int cols, const uint8_t* __restrict__ im, unsigned* __restrict__ out) {
+  const int N = rows * cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const int y = i / cols, x = i % cols;
+    const int xm = max(x - 1, 0), xp = min(x + 1, cols - 1), ym = max(y - 1, 0), yp = min(y + 1, rows - 1);
+    const int I = im[i];
+    const int gx = (int)im[y * cols + xp] - (int)im[y * cols + xm];
+    const int gy = (int)im[yp * cols + x] - (int)im[ym * cols + x];
+    out[i] = (unsigned)I | ((unsigned)(gx + 256) << 8) | ((unsigned)(gy + 256) << 17);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Target-image taps. TEX = true fetches 2x2 footprints with tex2Dgather from a CUDA array (one
-// instruction per four taps, through the texture pipe, which leaves the L1 load/store pipe to the
-// shared-memory accumulators); TEX = false uses byte loads.
-// gather component order for the footprint with top-left texel (ix, iy):
-//   .w = (ix, iy)  .z = (ix+1, iy)  .x = (ix, iy+1)  .y = (ix+1, iy+1)
-__device__ __forceinline__ uchar4 gather2x2(cudaTextureObject_t tex, int ix, int iy) {
-  return tex2Dgather<uchar4>(tex, (float)ix + 1.0f, (float)iy + 1.0f, 0);
-}
-
-template <bool TEX>
-__device__ __forceinline__ double sample_center(cudaTextureObject_t tex, const uint8_t* __restrict__ im, int cols,
-                                                double u, double v) {
-  const int ix = (int)u, iy = (int)v;  // u, v >= 0
-  const double dx = u - u2d((unsigned)ix), dy = v - u2d((unsigned)iy);
-  const double dxdy = dx * dy;
-  unsigned p00, p01, p10, p11;
-#ifdef NID_ABL_NOTAP
-  p00 = ix & 255; p01 = iy & 255; p10 = (ix + iy) & 255; p11 = (ix ^ iy) & 255;
-#else
-  if (TEX) {
-    const uchar4 g = gather2x2(tex, ix, iy);
-    p00 = g.w; p01 = g.z; p10 = g.x; p11 = g.y;
-  } else {
-    const uint8_t* r0 = im + (size_t)iy * cols + ix;
-    const uint8_t* r1 = r0 + cols;
-    p00 = __ldg(r0); p01 = __ldg(r0 + 1); p10 = __ldg(r1); p11 = __ldg(r1 + 1);
-  }
-#endif
-  // types_six_dof_expmap.h:321-326, same term order
-  return dxdy * u2d(p11) + (dy - dxdy) * u2d(p10) + (dx - dxdy) * u2d(p01) + (1.0 - dx - dy + dxdy) * u2d(p00);
-}
-
-// centre sample + central-difference gradient (types_six_dof_expmap.cpp:434-435): for u,v >= 1 the five
-// bilinear samples share their fractional weights, so 12 taps (four 2x2 footprints) suffice; the first
-// image row/column, where (int)(u-1) truncates towards zero, takes the literal formula.
-template <bool TEX>
-__device__ __forceinline__ void sample_grad(cudaTextureObject_t tex, const uint8_t* __restrict__ im, int cols, double u,
-                                            double v, double& ic, double& gx, double& gy) {
-  const int ix = (int)u, iy = (int)v;
-  if (ix >= 1 && iy >= 1) {
-    const double dx = u - u2d((unsigned)ix), dy = v - u2d((unsigned)iy);
-    const double w11 = dx * dy, w10 = dy - w11, w01 = dx - w11, w00 = 1.0 - dx - dy + w11;
-    int a01, a02, a10, a11, a12, a13, a20, a21, a22, a23, a31, a32;
-#ifdef NID_ABL_NOTAP
-    a01 = ix & 255; a02 = iy & 255; a10 = 3; a11 = (ix + iy) & 255; a12 = 7; a13 = 9; a20 = 1; a21 = 100; a22 = ix & 127; a23 = 5; a31 = 8; a32 = 77;
-#else
-    if (TEX) {
-      const uchar4 A = gather2x2(tex, ix - 1, iy), Bq = gather2x2(tex, ix + 1, iy);
-      const uchar4 C = gather2x2(tex, ix, iy - 1), D = gather2x2(tex, ix, iy + 1);
-      a10 = A.w; a11 = A.z; a20 = A.x; a21 = A.y;
-      a12 = Bq.w; a13 = Bq.z; a22 = Bq.x; a23 = Bq.y;
-      a01 = C.w; a02 = C.z;
-      a31 = D.x; a32 = D.y;
-    } else {
-      const uint8_t* r0 = im + (size_t)(iy - 1) * cols + (ix - 1);
-      const uint8_t* r1 = r0 + cols;
-      const uint8_t* r2 = r1 + cols;
-      const uint8_t* r3 = r2 + cols;
-      a01 = __ldg(r0 + 1); a02 = __ldg(r0 + 2);
-      a10 = __ldg(r1); a11 = __ldg(r1 + 1); a12 = __ldg(r1 + 2); a13 = __ldg(r1 + 3);
-      a20 = __ldg(r2); a21 = __ldg(r2 + 1); a22 = __ldg(r2 + 2); a23 = __ldg(r2 + 3);
-      a31 = __ldg(r3 + 1); a32 = __ldg(r3 + 2);
-    }
-#endif
-    ic = w11 * u2d(a22) + w10 * u2d(a21) + w01 * u2d(a12) + w00 * u2d(a11);
-    gx = (w11 * i2d_small(a23 - a21) + w10 * i2d_small(a22 - a20) + w01 * i2d_small(a13 - a11) + w00 * i2d_small(a12 - a10)) * 0.5;
-    gy = (w11 * i2d_small(a32 - a12) + w10 * i2d_small(a31 - a11) + w01 * i2d_small(a22 - a02) + w00 * i2d_small(a21 - a01)) * 0.5;
-  } else {
-    ic = interp_u8(im, cols, u, v);
-    gx = (interp_u8(im, cols, u + 1.0, v) - interp_u8(im, cols, u - 1.0, v)) / 2;
-    gy = (interp_u8(im, cols, u, v + 1.0) - interp_u8(im, cols, u, v - 1.0)) / 2;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Shared front end of both passes. A warp owns `pp` consecutive tasks (contiguous in the sorted arrays):
-// lane l holds the descriptor of task l, the whole range is pushed towards L2 up front, and the pixel
-// loop keeps the next pixel's point in registers while the current one is processed.
-struct WarpTasks {
-  int first, n;  // first task index, number of tasks (<= 32)
-  int2 mine;     // descriptor held by this lane
+// Per-job geometry, built once per CTA in shared memory.
+struct Geo {
+  double M[12];   // fast path: T_cw1 * T_wc0 (depth form) or T_cw1 (point form), 3x4, M[3*c + r]
+  double T1[12];  // T_cw1, 3x4 (exact path)
+  double T0[16];  // T_wc0 column-major (exact path, depth form)
+  double fx, fy, cx, cy, ifx, ify, ncx, ncy;  // ncx = -cx/fx
 };
 
-__device__ __forceinline__ WarpTasks warp_tasks_begin(const EvalParams& p, int pair, int lane, int wg,
-                                                      const double* sx, const double* sy, const double* sz) {
-  WarpTasks w;
-  w.first = wg * p.pp;
-  w.n = min(p.pp, p.ntasks[pair] - w.first);
-  w.mine = make_int2(0, 0);
-  if (w.n <= 0) return w;
-  if (lane < w.n) w.mine = p.tasks[(size_t)pair * p.max_tasks + w.first + lane];
-  const int s0 = __shfl_sync(0xffffffffu, w.mine.x, 0);
-  const int sl = __shfl_sync(0xffffffffu, w.mine.x, w.n - 1);
-  const int cl = __shfl_sync(0xffffffffu, w.mine.y, w.n - 1) & 0x1ff;
-  const int s1 = sl + cl;
-  for (int o = s0 + lane * 16; o < s1; o += 32 * 16) {  // one 128-byte line per lane and array
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(sx + o));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(sy + o));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(sz + o));
+template <bool PTS>
+__device__ __forceinline__ void build_geo(const EvalParams& p, int job, int pair, Geo* g) {
+  if (threadIdx.x < 12) {
+    const int c = threadIdx.x / 3, r = threadIdx.x % 3;
+    const double* T1 = p.poses + 16 * job;
+    const double* T0 = p.Twc0 + 16 * pair;
+    g->T1[threadIdx.x] = T1[4 * c + r];
+    double m;
+    if (PTS) m = T1[4 * c + r];
+    else {
+      m = T1[r] * T0[4 * c] + T1[4 + r] * T0[4 * c + 1] + T1[8 + r] * T0[4 * c + 2];
+      if (c == 3) m += T1[12 + r];
+    }
+    g->M[threadIdx.x] = m;
+  } else if (threadIdx.x < 28) {
+    g->T0[threadIdx.x - 12] = p.Twc0[16 * pair + threadIdx.x - 12];
+  } else if (threadIdx.x == 28) {
+    const double* cp = p.cam + 4 * pair;
+    g->fx = cp[0]; g->fy = cp[1]; g->cx = cp[2]; g->cy = cp[3];
+    g->ifx = 1.0 / cp[0]; g->ify = 1.0 / cp[1];
+    g->ncx = -cp[2] / cp[0]; g->ncy = -cp[3] / cp[1];
   }
-  return w;
+}
+
+// The reference's exact sequence for one pixel: CudaPoints3d.cu:20-28 then computeH.cu:152-158.
+template <bool PTS>
+__device__ __noinline__ void exact_uv(const Geo* g, double a0, double a1, double a2, unsigned id, double* out5) {
+  const Cam cam{g->fx, g->fy, g->cx, g->cy};
+  double xw = a0, yw = a1, zw = a2;
+  if (!PTS) backproject(g->T0, cam, a0, (int)(id >> 16), (int)(id & 0xffffu), xw, yw, zw);
+  Pose P;
+#pragma unroll
+  for (int i = 0; i < 12; i++) P.m[i] = g->T1[i];
+  double x1, y1, z1, u, v;
+  warp_project(P, cam, xw, yw, zw, x1, y1, z1, u, v);
+  out5[0] = x1; out5[1] = y1; out5[2] = z1; out5[3] = u; out5[4] = v;
+}
+
+// Result of the shared front end of both passes.
+struct Px {
+  double x, y, z, rz;  // camera-frame point and 1/z
+  double dx, dy;       // fractional parts of (u, v)
+  int ix, iy;
+  bool cost, jac;      // in-bounds for the cost (u+3<=cols) / for the Jacobian (u+3<=cols-1)
+  bool exact;          // (u, v) came from the reference's exact sequence
+  bool fix;            // fast path could not decide: (u, v) within 2^-24 of an integer
+};
+
+// not near an integer: fraction in [2^-24, 1 - 2^-21)
+__device__ __forceinline__ bool frac_is_safe(double d) {
+  return (unsigned)(__double2hiint(d) - 0x3E700000) < (unsigned)(0x3FEFFFFF - 0x3E700000);
+}
+
+__device__ __forceinline__ void px_from_exact(const double* e, int rows, int cols, Px& r) {
+  r.x = e[0]; r.y = e[1]; r.z = e[2]; r.rz = 1.0 / e[2];  // types_six_dof_expmap.cpp:437
+  const double u = e[3], v = e[4];
+  r.cost = inb_cost(u, v, rows, cols);
+  r.jac = inb_jac(u, v, rows, cols);
+  r.ix = 0; r.iy = 0; r.dx = 0.0; r.dy = 0.0;
+  if (r.cost) {
+    r.ix = (int)u; r.iy = (int)v;
+    r.dx = u - (double)r.ix; r.dy = v - (double)r.iy;
+  }
+  r.exact = true;
+  r.fix = false;
+}
+
+// Branch-free fast path (so that the pixels of a group interleave). `valid` = not a padding slot.
+template <bool PTS>
+__device__ __forceinline__ void front(const Geo* g, int rows, int cols, double a0, double a1, double a2, unsigned id,
+                                      bool valid, Px& r) {
+  double x1, y1, z1;
+  if (PTS) {
+    x1 = fma(g->M[0], a0, fma(g->M[3], a1, fma(g->M[6], a2, g->M[9])));
+    y1 = fma(g->M[1], a0, fma(g->M[4], a1, fma(g->M[7], a2, g->M[10])));
+    z1 = fma(g->M[2], a0, fma(g->M[5], a1, fma(g->M[8], a2, g->M[11])));
+  } else {
+    const double cxn = fma(u2d(id & 0xffffu), g->ifx, g->ncx);
+    const double cyn = fma(u2d(id >> 16), g->ify, g->ncy);
+    const double d0 = fma(g->M[0], cxn, fma(g->M[3], cyn, g->M[6]));
+    const double d1 = fma(g->M[1], cxn, fma(g->M[4], cyn, g->M[7]));
+    const double d2 = fma(g->M[2], cxn, fma(g->M[5], cyn, g->M[8]));
+    x1 = fma(a0, d0, g->M[9]);
+    y1 = fma(a0, d1, g->M[10]);
+    z1 = fma(a0, d2, g->M[11]);
+  }
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z1));
+  double e = fma(-z1, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-z1, y, 1.0);
+  y = fma(y, e, y);
+  const double u = fma(g->fx * x1, y, g->cx);
+  const double v = fma(g->fy * y1, y, g->cy);
+  r.x = x1; r.y = y1; r.z = z1; r.rz = y;
+  r.exact = false;
+  const int ix = __double2int_rz(u), iy = __double2int_rz(v);  // NaN -> 0, saturating
+  // u <= -1 or u >= cols+1 (same for v) is out of bounds whatever the last bits are
+  const bool inr = valid && (unsigned)ix <= (unsigned)cols && (unsigned)iy <= (unsigned)rows;
+  const double dx = u - u2d((unsigned)ix), dy = v - u2d((unsigned)iy);
+  const bool safe = frac_is_safe(dx) && frac_is_safe(dy);
+  // with u, v not within 2^-24 of an integer the integer comparisons decide exactly like
+  // `u>=0 && u+3<=cols && v>=0 && v+3<=rows` (types_six_dof_expmap.cpp:565; :433 with cols-1)
+  r.cost = inr && safe && ix <= cols - 4 && iy <= rows - 4;
+  r.jac = inr && safe && ix <= cols - 5 && iy <= rows - 4;
+  r.fix = inr && !safe;
+  r.ix = r.cost ? ix : 0; r.iy = r.cost ? iy : 0;
+  r.dx = dx; r.dy = dy;
+}
+
+// saturated plateau: the clamp `>= 255 -> 254.999` (types_six_dof_expmap.cpp:572) depends on the last bit
+// of the bilinear weights, so the fractions must be the reference's own
+template <bool PTS>
+__device__ __forceinline__ void make_exact(const Geo* g, int rows, int cols, double a0, double a1, double a2, unsigned id,
+                                           Px& r) {
+  double ex[5];
+  exact_uv<PTS>(g, a0, a1, a2, id, ex);
+  px_from_exact(ex, rows, cols, r);
+}
+
+// types_six_dof_expmap.h:321-326 in the reference's term order, without contraction
+__device__ __forceinline__ double bilinear_ref(double dx, double dy, unsigned p00, unsigned p01, unsigned p10, unsigned p11) {
+  const double dxdy = __dmul_rn(dx, dy);
+  const double w00 = __dadd_rn(__dsub_rn(__dsub_rn(1.0, dx), dy), dxdy);
+  double a = __dmul_rn(dxdy, u2d(p11));
+  a = __dadd_rn(a, __dmul_rn(__dsub_rn(dy, dxdy), u2d(p10)));
+  a = __dadd_rn(a, __dmul_rn(__dsub_rn(dx, dxdy), u2d(p01)));
+  return __dadd_rn(a, __dmul_rn(w00, u2d(p00)));
+}
+
+// gather component order for the footprint with top-left texel (ix, iy):
+//   .w = (ix, iy)  .z = (ix+1, iy)  .x = (ix, iy+1)  .y = (ix+1, iy+1)
+__device__ __forceinline__ uchar4 gather_u8(cudaTextureObject_t tex, int ix, int iy) {
+  return tex2Dgather<uchar4>(tex, (float)ix + 1.0f, (float)iy + 1.0f, 0);
+}
+__device__ __forceinline__ uint4 gather_u32(cudaTextureObject_t tex, int ix, int iy) {
+  return tex2Dgather<uint4>(tex, (float)ix + 1.0f, (float)iy + 1.0f, 0);
+}
+
+// Cubic B-spline basis on span k, f = ub - k. Interior spans of the clamped uniform knot vector
+// (2 <= k <= NS-3) share the uniform cubic basis; the two spans at either end take the per-span
+// polynomial table (nid_api.cu: build_bspline_table).
+__device__ __forceinline__ void bspline4_uniform(double f, double w[4]) {
+  const double s6 = 1.0 / 6.0;
+  w[0] = fma(f, fma(f, fma(f, -s6, 0.5), -0.5), s6);
+  w[1] = fma(f * f, fma(f, 0.5, -1.0), 2.0 / 3.0);
+  w[2] = fma(f, fma(f, fma(f, -0.5, 0.5), 0.5), s6);
+  w[3] = f * f * f * s6;
+}
+__device__ __forceinline__ bool span_is_uniform(int k, int NS) { return (unsigned)(k - 2) <= (unsigned)(NS - 5); }
+__device__ __forceinline__ void bspline4_edge(const double* __restrict__ coef, int k, double f, double w[4]) {
+  const double2* c2 = reinterpret_cast<const double2*>(coef + (size_t)k * 16);
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const double2 a = c2[2 * m], b = c2[2 * m + 1];
+    w[m] = fma(f, fma(f, fma(f, b.y, b.x), a.y), a.x);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pass 1: per task the un-weighted target soft histogram h[B] of its pixels, accumulated in lane-private
-// shared memory (no atomics) and merged over the 32 lanes in a fixed order.
-// grid (ceil(ceil(max_tasks/pp)/8), jobs), 256 threads; shared: 8 warps x B x 32 doubles + spline table.
-// (A power-sum variant -- sum f^j per span, spline applied once per task -- was measured slower: its
-// per-task warp reductions outweigh the saved Horner evaluations at ~3 pixels per lane and task.)
-template <bool TEX>
-__global__ void __launch_bounds__(256) k_hist_sorted(EvalParams p) {
+// One group = four consecutive pixels of a lane's task (32 B of depths + 16 B of pixel ids per lane).
+template <bool PTS>
+struct Group {
+  unsigned id[4];
+  double a0[4], a1[4], a2[4];
+  __device__ __forceinline__ void load(const double* q0, const double* q1, const double* q2, const unsigned* qi, size_t o) {
+    const uint4 i4 = *reinterpret_cast<const uint4*>(qi + o);
+    id[0] = i4.x; id[1] = i4.y; id[2] = i4.z; id[3] = i4.w;
+    const double2 xa = *reinterpret_cast<const double2*>(q0 + o), xb = *reinterpret_cast<const double2*>(q0 + o + 2);
+    a0[0] = xa.x; a0[1] = xa.y; a0[2] = xb.x; a0[3] = xb.y;
+    if (PTS) {
+      const double2 ya = *reinterpret_cast<const double2*>(q1 + o), yb = *reinterpret_cast<const double2*>(q1 + o + 2);
+      const double2 za = *reinterpret_cast<const double2*>(q2 + o), zb = *reinterpret_cast<const double2*>(q2 + o + 2);
+      a1[0] = ya.x; a1[1] = ya.y; a1[2] = yb.x; a1[3] = yb.y;
+      a2[0] = za.x; a2[1] = za.y; a2[2] = zb.x; a2[3] = zb.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) { a1[j] = 0.0; a2[j] = 0.0; }
+    }
+  }
+};
+
+// Pass 1 on W pixels of a group at once: projection (branch-free), W gathers in flight, spline weights,
+// then the accumulations in pixel order into the lane's private row h[b * 256].
+template <bool PTS, int W>
+__device__ __forceinline__ void hist_pixels(const EvalParams& p, const Geo* g, const Group<PTS>& G, int j0,
+                                            cudaTextureObject_t tex, const double* __restrict__ coef, double s, int NS,
+                                            double* __restrict__ h) {
+  Px r[W];
+  bool anyfix = false;
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    front<PTS>(g, p.rows, p.cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], G.id[j0 + j] != NID_PAD_ID, r[j]);
+    anyfix |= r[j].fix;
+  }
+  if (anyfix) {
+#pragma unroll
+    for (int j = 0; j < W; j++)
+      if (r[j].fix) make_exact<PTS>(g, p.rows, p.cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
+  }
+  uchar4 t[W];
+#pragma unroll
+  for (int j = 0; j < W; j++) t[j] = gather_u8(tex, r[j].ix, r[j].iy);
+  bool sat = false;
+#pragma unroll
+  for (int j = 0; j < W; j++) sat |= r[j].cost && !r[j].exact && (t[j].x & t[j].y & t[j].z & t[j].w) == 255;
+  if (sat) {
+#pragma unroll
+    for (int j = 0; j < W; j++)
+      if (r[j].cost && !r[j].exact && (t[j].x & t[j].y & t[j].z & t[j].w) == 255) {
+        make_exact<PTS>(g, p.rows, p.cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
+        t[j] = gather_u8(tex, r[j].ix, r[j].iy);
+      }
+  }
+  double wt[W][4], fr[W];
+  int kt[W];
+  bool edge = false;
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    const double ic = clamp_intensity(bilinear_ref(r[j].dx, r[j].dy, t[j].w, t[j].z, t[j].x, t[j].y));
+    const double ub = ic * s;
+    kt[j] = r[j].cost ? (int)ub : 0;  // 0 <= ub < NS
+    fr[j] = ub - u2d((unsigned)kt[j]);
+    bspline4_uniform(fr[j], wt[j]);
+    edge |= r[j].cost && !span_is_uniform(kt[j], NS);
+  }
+  if (edge) {
+#pragma unroll
+    for (int j = 0; j < W; j++)
+      if (r[j].cost && !span_is_uniform(kt[j], NS)) bspline4_edge(coef, kt[j], fr[j], wt[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    if (!r[j].cost) continue;
+    double* hk = h + kt[j] * 256;
+#pragma unroll
+    for (int n = 0; n < 4; n++) hk[n * 256] += wt[j][n];
+  }
+}
+
+// Pass 1: per task the un-weighted target soft histogram h[B] of its pixels.
+// grid (jobs, ceil(max_slices/8)), 256 threads; shared: rows [B][256] + spline table + geometry. The job
+// index is the fast grid dimension and slices are ordered longest first, so the long CTAs of every job
+// start first and the short ones fill the tail.
+template <bool PTS, int W>
+__global__ void __launch_bounds__(256, W == 1 ? 4 : (W == 2 ? 3 : 2)) k_hist_sell(EvalParams p) {
   extern __shared__ double sm[];
-  const int B = p.bins;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-  const int job = blockIdx.y + p.job0;
+  __shared__ Geo geo;
+  const int B = p.bins, NS = B - 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int job = blockIdx.x + p.job0;
   const int pair = p.job_pair[job];
-  double* coef = sm + (size_t)W * B * 32;  // [(B-3)*16] spline polynomial table
-  for (int i = threadIdx.x; i < (B - 3) * 16; i += blockDim.x) coef[i] = p.bs_coef[i];
+  double* coef = sm + (size_t)B * 256;
+  for (int i = threadIdx.x; i < NS * 16; i += blockDim.x) coef[i] = p.bs_coef[i];
+  build_geo<PTS>(p, job, pair, &geo);
   __syncthreads();
-  const size_t base = (size_t)pair * p.N;
-  const double* sxp = p.sx + base;
-  const double* syp = p.sy + base;
-  const double* szp = p.sz + base;
-  const WarpTasks wt_ = warp_tasks_begin(p, pair, lane, blockIdx.x * W + warp, sxp, syp, szp);
-  if (wt_.n <= 0) return;
-  double* h = sm + (size_t)warp * B * 32;  // h[tt*32 + lane]
-  const double* cp = p.cam + 4 * pair;
-  const Cam cam{cp[0], cp[1], cp[2], cp[3]};
-  const Pose P = load_pose(p.poses + 16 * job);
-  const uint8_t* im1 = p.im1 + base;
-  const cudaTextureObject_t tex = TEX ? p.tex[pair] : 0;
-  const double s = (double)(B - 3) / 255.0;
-  for (int j = 0; j < wt_.n; j++) {
-    const int start = __shfl_sync(0xffffffffu, wt_.mine.x, j);
-    const int count = __shfl_sync(0xffffffffu, wt_.mine.y, j) & 0x1ff;
-    for (int tt = 0; tt < B; tt++) h[tt * 32 + lane] = 0.0;
-    const double* sx = sxp + start;
-    const double* sy = syp + start;
-    const double* sz = szp + start;
-    int i = lane;
-    bool have = i < count;
-    double nx = 0, ny = 0, nz = 0;
-    if (have) { nx = sx[i]; ny = sy[i]; nz = sz[i]; }
-    while (have) {
-      const double x0 = nx, y0 = ny, z0 = nz;
-      i += 32;
-      have = i < count;
-      if (have) { nx = sx[i]; ny = sy[i]; nz = sz[i]; }
-      double x1, y1, z1, u, v;
-      warp_project(P, cam, x0, y0, z0, x1, y1, z1, u, v);
-      if (inb_cost(u, v, p.rows, p.cols)) {
-        const double ic = clamp_intensity(sample_center<TEX>(tex, im1, p.cols, u, v));
-        const double ub = ic * s;
-        const int kt = (int)ub;  // ub >= 0
-        double wt[4], dw[4];
-        bspline4_tab<false>(coef, ub, kt, wt, dw);
+  const int slice = blockIdx.y * 8 + warp;
+  if (slice >= p.nslices[pair]) return;
+  const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
+  const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
+  const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
+  double* h = sm + threadIdx.x;  // h[b * 256]
+  for (int b = 0; b < B; b++) h[b * 256] = 0.0;
+  const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
+  const double* q0 = p.sd0 + sbase;
+  const double* q1 = PTS ? p.sd1 + sbase : nullptr;
+  const double* q2 = PTS ? p.sd2 + sbase : nullptr;
+  const unsigned* qi = p.sid + sbase;
+  const cudaTextureObject_t tex = p.tex[pair];
+  const double s = (double)NS / 255.0;
+  for (int gi = 0; gi < ngroups; gi++) {
+    Group<PTS> G;
+    G.load(q0, q1, q2, qi, (size_t)gi * 128);
 #pragma unroll
-        for (int n = 0; n < 4; n++) h[(kt + n) * 32 + lane] += wt[n];
-      }
-    }
-    __syncwarp();
-    // fixed-order merge of the 32 lane-private copies: lane tt sums column tt (rotated start => no bank
-    // conflicts), four independent chains to shorten the dependency
-    double* out = p.G + ((size_t)job * p.g_stride + wt_.first + j) * B;
-    for (int tt = lane; tt < B; tt += 32) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-      for (int q = 0; q < 32; q += 4) {
-        a0 += h[tt * 32 + ((q + tt) & 31)];
-        a1 += h[tt * 32 + ((q + 1 + tt) & 31)];
-        a2 += h[tt * 32 + ((q + 2 + tt) & 31)];
-        a3 += h[tt * 32 + ((q + 3 + tt) & 31)];
-      }
-      out[tt] = (a0 + a1) + (a2 + a3);
-    }
-    __syncwarp();
+    for (int j0 = 0; j0 < 4; j0 += W) hist_pixels<PTS, W>(p, &geo, G, j0, tex, coef, s, NS, h);
+  }
+  if (task >= 0) {
+    double* out = p.G + ((size_t)job * p.g_stride + task) * B;
+    for (int b = 0; b < B; b++) out[b] = h[b * 256];
   }
 }
 
@@ -418,85 +566,130 @@ __global__ void __launch_bounds__(256) k_qtable(EvalParams p) {
 // ------------------------------------------------------------------------------------------------
 // Pass 2: per task the partial of  J[a] = sum_i g_i[a] * c_i,  c_i = q0 + f_i (q1 + f_i q2) with the
 // quadratic of the pixel's (class, span); c_i = 0 at ub == 0 exactly (the reference's BsplineDer quirk).
-template <bool TEX>
-__global__ void __launch_bounds__(256) k_jac_sorted(EvalParams p) {
-  extern __shared__ double sm[];
-  const int B = p.bins, NS = B - 3;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-  const int job = blockIdx.y + p.job0;
-  const int pair = p.job_pair[job];
-  const size_t base = (size_t)pair * p.N;
-  const double* sxp = p.sx + base;
-  const double* syp = p.sy + base;
-  const double* szp = p.sz + base;
-  const WarpTasks wt_ = warp_tasks_begin(p, pair, lane, blockIdx.x * W + warp, sxp, syp, szp);
-  if (wt_.n <= 0) return;
-  double* wq = sm + warp * (NS * 3);
-  const double* cp = p.cam + 4 * pair;
-  const Cam cam{cp[0], cp[1], cp[2], cp[3]};
-  const Pose P = load_pose(p.poses + 16 * job);
-  const uint8_t* im1 = p.im1 + base;
-  const cudaTextureObject_t tex = TEX ? p.tex[pair] : 0;
-  const double s = (double)(B - 3) / 255.0;
-  for (int j = 0; j < wt_.n; j++) {
-    const int start = __shfl_sync(0xffffffffu, wt_.mine.x, j);
-    const int desc = __shfl_sync(0xffffffffu, wt_.mine.y, j);
-    const int count = desc & 0x1ff, cls = (desc >> 9) & 0x1ff, cell = (desc >> 18) & 0x3fff;
-    {
-      const double* row = p.qt + (((size_t)job * p.ncell + cell) * NID_NCLS + cls) * (NS * 3);
-      for (int tt = lane; tt < NS * 3; tt += 32) wq[tt] = row[tt];
-    }
-    __syncwarp();
-    const double* sx = sxp + start;
-    const double* sy = syp + start;
-    const double* sz = szp + start;
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    int i = lane;
-    bool have = i < count;
-    double nx = 0, ny = 0, nz = 0;
-    if (have) { nx = sx[i]; ny = sy[i]; nz = sz[i]; }
-    while (have) {
-      const double x0 = nx, y0 = ny, z0 = nz;
-      i += 32;
-      have = i < count;
-      if (have) { nx = sx[i]; ny = sy[i]; nz = sz[i]; }
-      double x, y, z, u, v;
-      warp_project(P, cam, x0, y0, z0, x, y, z, u, v);
-      if (inb_jac(u, v, p.rows, p.cols)) {
-        double ic, gx, gy;
-        sample_grad<TEX>(tex, im1, p.cols, u, v, ic, gx, gy);
-        ic = clamp_intensity(ic);
-        const double ub = ic * s;
-        const int k = (int)ub;
-        const double f = ub - u2d((unsigned)k);
-        const double* q = wq + 3 * k;
-        double ci = fma(f, fma(f, q[2], q[1]), q[0]);
-        if (ub == 0.0) ci = 0.0;
-        // d(u,v)/d(xi), types_six_dof_expmap.cpp:438-450
-        const double iz = 1.0 / z, iz2 = iz * iz;
-        const double a = ci * gx * cam.fx, b = ci * gy * cam.fy;
-        acc[0] += a * (-x * y * iz2) + b * (-(1.0 + y * y * iz2));
-        acc[1] += a * (1.0 + x * x * iz2) + b * (x * y * iz2);
-        acc[2] += a * (-y * iz) + b * (x * iz);
-        acc[3] += a * iz;
-        acc[4] += b * iz;
-        acc[5] += a * (-x * iz2) + b * (-y * iz2);
+// grid (ceil(max_slices/4), jobs), 128 threads; shared: the lanes' quadratic rows [3*NS][128].
+__device__ __forceinline__ double biased9_to_double(unsigned v) {  // v in [0, 511] -> (double)(v - 256), exact
+  return __hiloint2double(0x43300000, (int)v) - (4503599627370496.0 + 256.0);
+}
+
+// Pass-2 pixel by the reference's literal sequence: exact (u, v) for the cached intensity
+// (types_six_dof_expmap.cpp:562-575), the second projection fx*(x/z)+cx for the Jacobian bounds test and the
+// four gradient samples (:407-435). Taken when (u, v) is within 2^-24 of an integer, on saturated plateaus,
+// and in the first image row / column, where (int)(u-1) truncates towards zero so that the five bilinear
+// samples do not share their fractions. out: {x, y, z, 1/z, ic, 2 gx, 2 gy}; returns the Jacobian validity.
+template <bool PTS>
+__device__ __noinline__ bool jac_pixel_literal(const Geo* g, int rows, int cols, const uint8_t* __restrict__ im,
+                                               double a0, double a1, double a2, unsigned id, double* out7) {
+  double e[5];
+  exact_uv<PTS>(g, a0, a1, a2, id, e);
+  const Cam cam{g->fx, g->fy, g->cx, g->cy};
+  const double u = e[3], v = e[4];
+  double u2, v2;
+  project_jac(cam, e[0], e[1], e[2], u2, v2);
+  if (!inb_cost(u, v, rows, cols) || !inb_jac(u2, v2, rows, cols)) return false;
+  out7[0] = e[0]; out7[1] = e[1]; out7[2] = e[2]; out7[3] = 1.0 / e[2];
+  out7[4] = interp_u8(im, cols, u, v);
+  out7[5] = interp_u8(im, cols, u2 + 1.0, v2) - interp_u8(im, cols, u2 - 1.0, v2);
+  out7[6] = interp_u8(im, cols, u2, v2 + 1.0) - interp_u8(im, cols, u2, v2 - 1.0);
+  return true;
+}
+
+// Pass 2 on W pixels of a group at once; acc[6] are the lane's Jacobian partial sums.
+template <bool PTS, int W>
+__device__ __forceinline__ void jac_pixels(const EvalParams& p, const Geo* g, const Group<PTS>& G, int j0,
+                                           cudaTextureObject_t tex2, const uint8_t* __restrict__ im1, double s, double hfx,
+                                           double hfy, const double* __restrict__ wq, double acc[6]) {
+  Px r[W];
+#pragma unroll
+  for (int j = 0; j < W; j++)
+    front<PTS>(g, p.rows, p.cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], G.id[j0 + j] != NID_PAD_ID, r[j]);
+  uint4 t[W];
+#pragma unroll
+  for (int j = 0; j < W; j++) t[j] = gather_u32(tex2, r[j].jac ? r[j].ix : 0, r[j].jac ? r[j].iy : 0);
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    double ic = bilinear_ref(r[j].dx, r[j].dy, t[j].w & 0xffu, t[j].z & 0xffu, t[j].x & 0xffu, t[j].y & 0xffu);
+    const double w11 = r[j].dx * r[j].dy, w10 = r[j].dy - w11, w01 = r[j].dx - w11, w00 = 1.0 - r[j].dx - r[j].dy + w11;
+    double gx2 = fma(w11, biased9_to_double((t[j].y >> 8) & 0x1ffu),
+                     fma(w10, biased9_to_double((t[j].x >> 8) & 0x1ffu),
+                         fma(w01, biased9_to_double((t[j].z >> 8) & 0x1ffu), w00 * biased9_to_double((t[j].w >> 8) & 0x1ffu))));
+    double gy2 = fma(w11, biased9_to_double(t[j].y >> 17),
+                     fma(w10, biased9_to_double(t[j].x >> 17),
+                         fma(w01, biased9_to_double(t[j].z >> 17), w00 * biased9_to_double(t[j].w >> 17))));
+    // rare: undecided by the fast path, saturated plateau, or first image row / column
+    const bool sat = (t[j].x & t[j].y & t[j].z & t[j].w & 0xffu) == 0xffu;
+    if (r[j].fix || (r[j].jac && (sat || r[j].ix < 1 || r[j].iy < 1))) {
+      double o7[7];
+      r[j].jac = jac_pixel_literal<PTS>(g, p.rows, p.cols, im1, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], o7);
+      if (r[j].jac) {
+        r[j].x = o7[0]; r[j].y = o7[1]; r[j].z = o7[2]; r[j].rz = o7[3];
+        ic = o7[4]; gx2 = o7[5]; gy2 = o7[6];
       }
     }
+    ic = clamp_intensity(ic);
+    const double ub = r[j].jac ? ic * s : 0.0;
+    const int k = (int)ub;
+    const double f = ub - u2d((unsigned)k);
+    const double* q = wq + 3 * k * 128;
+    double ci = fma(f, fma(f, q[256], q[128]), q[0]);
+    if (ub == 0.0) ci = 0.0;  // the reference's BsplineDer quirk
+    if (!r[j].jac) continue;  // (a padding slot may carry z = 0 and non-finite coordinates)
+    // d(u,v)/d(xi), types_six_dof_expmap.cpp:438-450, in normalised coordinates xn = x/z, yn = y/z
+    const double iz = r[j].rz, xn = r[j].x * iz, yn = r[j].y * iz;
+    const double a = ci * gx2 * hfx, b = ci * gy2 * hfy;
+    const double xy = xn * yn;
+    acc[0] = fma(-b, fma(yn, yn, 1.0), fma(-a, xy, acc[0]));
+    acc[1] = fma(b, xy, fma(a, fma(xn, xn, 1.0), acc[1]));
+    acc[2] = fma(b, xn, fma(-a, yn, acc[2]));
+    const double aiz = a * iz, biz = b * iz;
+    acc[3] += aiz;
+    acc[4] += biz;
+    acc[5] = fma(-yn, biz, fma(-xn, aiz, acc[5]));
+  }
+}
+
+// grid (jobs, ceil(max_slices/4)), 128 threads; shared: the lanes' quadratic rows [3*NS][128].
+template <bool PTS, int W>
+__global__ void __launch_bounds__(128, W == 1 ? 5 : 4) k_jac_sell(EvalParams p) {
+  extern __shared__ double sm[];
+  __shared__ Geo geo;
+  const int B = p.bins, NS = B - 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int job = blockIdx.x + p.job0;
+  const int pair = p.job_pair[job];
+  build_geo<PTS>(p, job, pair, &geo);
+  __syncthreads();
+  const int slice = blockIdx.y * 4 + warp;
+  if (slice >= p.nslices[pair]) return;
+  const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
+  const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
+  const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
+  double* wq = sm + threadIdx.x;  // wq[i * 128]
+  if (task >= 0) {
+    const int desc = p.tasks[(size_t)pair * p.max_tasks + task].y;
+    const int cls = (desc >> 9) & 0x1ff, cell = (desc >> 18) & 0x3fff;
+    const double* row = p.qt + (((size_t)job * p.ncell + cell) * NID_NCLS + cls) * (NS * 3);
+    for (int i = 0; i < NS * 3; i++) wq[i * 128] = row[i];
+  }
+  const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
+  const double* q0 = p.sd0 + sbase;
+  const double* q1 = PTS ? p.sd1 + sbase : nullptr;
+  const double* q2 = PTS ? p.sd2 + sbase : nullptr;
+  const unsigned* qi = p.sid + sbase;
+  const cudaTextureObject_t tex2 = p.tex2[pair];
+  const uint8_t* im1 = p.im1 + (size_t)pair * p.N;
+  const double s = (double)NS / 255.0;
+  const double hfx = 0.5 * geo.fx, hfy = 0.5 * geo.fy;  // the /2 of the central differences folded in
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int gi = 0; gi < ngroups; gi++) {
+    Group<PTS> G;
+    G.load(q0, q1, q2, qi, (size_t)gi * 128);
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-      double vv = acc[k];
+    for (int j0 = 0; j0 < 4; j0 += W) jac_pixels<PTS, W>(p, &geo, G, j0, tex2, im1, s, hfx, hfy, wq, acc);
+  }
+  if (task >= 0) {
+    double* out = p.jpart + ((size_t)job * p.g_stride + task) * 6;
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) vv += __shfl_xor_sync(0xffffffffu, vv, off);
-      acc[k] = vv;
-    }
-    if (lane < 6) {
-      double vv = acc[0];
-#pragma unroll
-      for (int k = 1; k < 6; k++) if (lane == k) vv = acc[k];
-      p.jpart[((size_t)job * p.g_stride + wt_.first + j) * 6 + lane] = vv;
-    }
-    __syncwarp();
+    for (int k = 0; k < 6; k++) out[k] = acc[k];
   }
 }
 
@@ -541,42 +734,65 @@ int launch_count_classes(nid_ctx* c, int pair) {
 
 int launch_scatter(nid_ctx* c, int pair) {
   EvalParams p = make_params(c, 1);
-  k_scatter<<<c->ncell, 256, 0, c->stream>>>(p, pair, c->seg_start + (size_t)pair * (c->ncell * NID_NCLS + 1), c->sx, c->sy, c->sz);
-  NID_LAUNCH_CHECK(c, "k_scatter");
+  const size_t sb = (size_t)pair * c->sell_cap;
+  cudaError_t e = cudaMemsetAsync(c->sid + sb, 0xFF, sizeof(unsigned) * c->sell_cap, c->stream);
+  if (e != cudaSuccess) return check_cuda(e, "memset sid");
+  e = cudaMemsetAsync(c->sd0 + sb, 0, sizeof(double) * c->sell_cap, c->stream);
+  if (e != cudaSuccess) return check_cuda(e, "memset sd0");
+  const int* tp = c->task_pos + (size_t)pair * c->max_tasks;
+  const double* depth = c->depth + (size_t)pair * c->N;
+  if (c->sell_points) {
+    cudaMemsetAsync(c->sd1 + sb, 0, sizeof(double) * c->sell_cap, c->stream);
+    cudaMemsetAsync(c->sd2 + sb, 0, sizeof(double) * c->sell_cap, c->stream);
+    k_scatter_sell<true><<<c->ncell, 256, 0, c->stream>>>(p, pair, c->task_px, depth, tp, c->sd0, c->sd1, c->sd2, c->sid);
+  } else {
+    k_scatter_sell<false><<<c->ncell, 256, 0, c->stream>>>(p, pair, c->task_px, depth, tp, c->sd0, nullptr, nullptr, c->sid);
+  }
+  NID_LAUNCH_CHECK(c, "k_scatter_sell");
   return NID_OK;
 }
 
-// warps per CTA of pass 1: as many as fit the lane-private histograms in shared memory (max 8)
-static int hist_warps(const nid_ctx* c) {
-  const size_t per_warp = sizeof(double) * (size_t)c->bins * 32;
-  const size_t fixed = sizeof(double) * (size_t)(c->bins - 3) * 16;
-  int w = (int)((200 * 1024 - fixed) / per_warp);
-  return std::max(1, std::min(w, 8));
+int launch_pack_tex(nid_ctx* c, int pair, unsigned* d_out) {
+  int g = (c->N + 255) / 256;
+  if (g > c->sm_count * 8) g = c->sm_count * 8;
+  k_pack_tex<<<g, 256, 0, c->stream>>>(c->rows, c->cols, c->im1 + (size_t)pair * c->N, d_out);
+  NID_LAUNCH_CHECK(c, "k_pack_tex");
+  return NID_OK;
 }
-size_t hist_sorted_smem(const nid_ctx* c) {
-  return sizeof(double) * ((size_t)(c->bins - 3) * 16 + (size_t)hist_warps(c) * (size_t)c->bins * 32);
-}
-size_t jac_sorted_smem(const nid_ctx* c) { return sizeof(double) * 8 * (size_t)(c->bins - 3) * 3; }
+
+size_t hist_sell_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)c->bins * 256 + (size_t)(c->bins - 3) * 16); }
+size_t jac_sell_smem(const nid_ctx* c) { return sizeof(double) * (size_t)(c->bins - 3) * 3 * 128; }
 size_t assemble_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins); }
 size_t qtable_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)c->bins * c->bins + c->bins + (size_t)(c->bins - 3) * 16); }
+
+template <bool PTS>
+static void launch_hist_w(nid_ctx* c, const EvalParams& p, int ns, int n_jobs) {
+  const dim3 grid(n_jobs, (ns + 7) / 8);
+  const size_t sm = hist_sell_smem(c);
+  switch (c->opt_ilp_hist) {
+    case 1: k_hist_sell<PTS, 1><<<grid, 256, sm, c->stream>>>(p); break;
+    case 2: k_hist_sell<PTS, 2><<<grid, 256, sm, c->stream>>>(p); break;
+    default: k_hist_sell<PTS, 4><<<grid, 256, sm, c->stream>>>(p); break;
+  }
+}
+template <bool PTS>
+static void launch_jac_w(nid_ctx* c, const EvalParams& p, int ns, int n_jobs) {
+  const dim3 grid(n_jobs, (ns + 3) / 4);
+  const size_t sm = jac_sell_smem(c);
+  switch (c->opt_ilp_jac) {
+    case 1: k_jac_sell<PTS, 1><<<grid, 128, sm, c->stream>>>(p); break;
+    default: k_jac_sell<PTS, 2><<<grid, 128, sm, c->stream>>>(p); break;
+  }
+}
 
 int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int want_jac) {
   EvalParams p = make_params(c, n_jobs_total);
   p.job0 = job0;
-  // tasks per warp: enough warps to fill the machine a few times over, long-lived warps otherwise
-  {
-    const long long pieces = (long long)c->max_ntasks_prepared * n_jobs;
-    const long long target = (long long)c->sm_count * 16 * 4;
-    long long pp = c->opt_tasks_per_warp > 0 ? c->opt_tasks_per_warp : (pieces + target / 2) / target;
-    p.pp = (int)std::max(1LL, std::min(pp, 16LL));
-  }
-  const int nwarps = (c->max_ntasks_prepared + p.pp - 1) / p.pp;
-  const int hw = hist_warps(c);
-  const bool tex = c->use_tex;
+  const int ns = c->max_nslices_prepared;
+  const bool pts = c->sell_points;
   ktime_mark(c, 0);
-  if (tex) k_hist_sorted<true><<<dim3((nwarps + hw - 1) / hw, n_jobs), hw * 32, hist_sorted_smem(c), c->stream>>>(p);
-  else k_hist_sorted<false><<<dim3((nwarps + hw - 1) / hw, n_jobs), hw * 32, hist_sorted_smem(c), c->stream>>>(p);
-  NID_LAUNCH_CHECK(c, "k_hist_sorted");
+  if (pts) launch_hist_w<true>(c, p, ns, n_jobs); else launch_hist_w<false>(c, p, ns, n_jobs);
+  NID_LAUNCH_CHECK(c, "k_hist_sell");
   ktime_mark(c, 1);
   k_assemble<<<dim3(c->ncell, n_jobs), NID_ASM_THREADS, assemble_smem(c), c->stream>>>(p, want_jac);
   NID_LAUNCH_CHECK(c, "k_assemble");
@@ -587,9 +803,8 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
   }
   ktime_mark(c, 2);
   if (want_jac) {
-    if (tex) k_jac_sorted<true><<<dim3((nwarps + 7) / 8, n_jobs), 256, jac_sorted_smem(c), c->stream>>>(p);
-    else k_jac_sorted<false><<<dim3((nwarps + 7) / 8, n_jobs), 256, jac_sorted_smem(c), c->stream>>>(p);
-    NID_LAUNCH_CHECK(c, "k_jac_sorted");
+    if (pts) launch_jac_w<true>(c, p, ns, n_jobs); else launch_jac_w<false>(c, p, ns, n_jobs);
+    NID_LAUNCH_CHECK(c, "k_jac_sell");
     ktime_mark(c, 3);
     const int warps = n_jobs * c->ncell;
     k_jac_final_sorted<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(p, n_jobs);
@@ -605,16 +820,23 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
 }
 
 int sorted_init(nid_ctx* c) {
-  cudaError_t e = cudaFuncSetAttribute(k_hist_sorted<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_sorted_smem(c));
-  if (e != cudaSuccess) return check_cuda(e, "smem attr k_hist_sorted");
-  e = cudaFuncSetAttribute(k_hist_sorted<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_sorted_smem(c));
-  if (e != cudaSuccess) return check_cuda(e, "smem attr k_hist_sorted");
-  cudaFuncSetAttribute(k_hist_sorted<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(k_hist_sorted<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  e = cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assemble_smem(c));
-  if (e != cudaSuccess) return check_cuda(e, "smem attr k_assemble");
-  e = cudaFuncSetAttribute(k_qtable, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qtable_smem(c));
-  if (e != cudaSuccess) return check_cuda(e, "smem attr k_qtable");
+  cudaError_t e;
+#define NID_SMEM_ATTR(k, bytes)                                                                     \
+  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));            \
+  if (e != cudaSuccess) return check_cuda(e, "smem attr " #k);
+  NID_SMEM_ATTR((k_hist_sell<true, 1>), hist_sell_smem(c));
+  NID_SMEM_ATTR((k_hist_sell<false, 1>), hist_sell_smem(c));
+  NID_SMEM_ATTR((k_hist_sell<true, 2>), hist_sell_smem(c));
+  NID_SMEM_ATTR((k_hist_sell<false, 2>), hist_sell_smem(c));
+  NID_SMEM_ATTR((k_hist_sell<true, 4>), hist_sell_smem(c));
+  NID_SMEM_ATTR((k_hist_sell<false, 4>), hist_sell_smem(c));
+  NID_SMEM_ATTR((k_jac_sell<true, 1>), jac_sell_smem(c));
+  NID_SMEM_ATTR((k_jac_sell<false, 1>), jac_sell_smem(c));
+  NID_SMEM_ATTR((k_jac_sell<true, 2>), jac_sell_smem(c));
+  NID_SMEM_ATTR((k_jac_sell<false, 2>), jac_sell_smem(c));
+  NID_SMEM_ATTR(k_assemble, assemble_smem(c));
+  NID_SMEM_ATTR(k_qtable, qtable_smem(c));
+#undef NID_SMEM_ATTR
   return NID_OK;
 }
 

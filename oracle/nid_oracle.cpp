@@ -820,8 +820,12 @@ void orc_pixels(const orc_problem* P, const double pose7[7], double* out) {
     double v = P->fy * pc[1] / pc[2] + P->cy;
     double* o = &out[8 * id];
     o[0] = u; o[1] = v; o[7] = pc[2];
+    // the CPU edge projects a second time in linearizeOplus, as fx*(x/z)+cx (types_six_dof_expmap.cpp:407-421);
+    // its bounds test (:433) and gradient samples (:434-435) use that value
+    double u2 = P->fx * (pc[0] / pc[2]) + P->cx;
+    double v2 = P->fy * (pc[1] / pc[2]) + P->cy;
     bool vc = (u >= 0 && u + 3 <= P->cols && v >= 0 && v + 3 <= P->rows);
-    bool vj = (u >= 0 && u + 3 <= jac_cols && v >= 0 && v + 3 <= P->rows);
+    bool vj = vc && (u2 >= 0 && u2 + 3 <= jac_cols && v2 >= 0 && v2 + 3 <= P->rows);
     o[5] = vc ? 1.0 : 0.0;
     o[6] = vj ? 1.0 : 0.0;
     o[2] = 0; o[3] = 0; o[4] = 0;
@@ -832,8 +836,8 @@ void orc_pixels(const orc_problem* P, const double pose7[7], double* out) {
       o[2] = ic;
     }
     if (vj) {
-      o[3] = (interp(*P, u + 1, v) - interp(*P, u - 1, v)) / 2;
-      o[4] = (interp(*P, u, v + 1) - interp(*P, u, v - 1)) / 2;
+      o[3] = (interp(*P, u2 + 1, v2) - interp(*P, u2 - 1, v2)) / 2;
+      o[4] = (interp(*P, u2, v2 + 1) - interp(*P, u2, v2 - 1)) / 2;
     }
   }
 }

@@ -287,3 +287,80 @@ def test_state_errors(nid, orc, make_pair):
         ctx.eval(0, M, True)
     with pytest.raises(nid.NidError):
         ctx.eval_jobs(np.tile(M, 2), [0, 0], True)  # more jobs than max_jobs
+
+
+def _saturate(p, lo=110, hi=190):
+    """A copy of the pair whose images are stretched so that large plateaus sit at exactly 0 and 255."""
+    import dataclasses
+    def stretch(im):
+        v = (im.astype(np.float64) - lo) * 255.0 / (hi - lo)
+        return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+    return dataclasses.replace(p, im0=stretch(p.im0), im1=stretch(p.im1))
+
+
+@pytest.mark.parametrize("path", [NATURAL, SORTED])
+def test_saturated_plateaus(nid, orc, make_pair, path):
+    """The reference clamps `>= 255 -> 254.999` after the bilinear sample and returns a zero B-spline
+    derivative at exactly 0: on saturated plateaus the result depends on the last bit of the bilinear
+    weights. The sorted path re-evaluates such pixels with the reference's exact sequence."""
+    p = _saturate(make_pair(1000, 240, 320))
+    assert (p.im1 == 255).mean() > 0.05 and (p.im1 == 0).mean() > 0.05
+    P, ctx, pose0 = _setup(nid, orc, p, 4, 16, path=path)
+    M0 = orc.se3_to_mat16(pose0)
+    nc, href = ctx.prepare(0, M0)
+    nco, hrefo = P.prepare(pose0)
+    assert np.array_equal(nc, nco)
+    pose = orc.se3_mul(orc.se3_exp(np.array([0.002, -0.001, 0.0015, 0.004, -0.003, 0.002])), pose0)
+    Ht, Hj, J = ctx.eval(0, orc.se3_to_mat16(pose), True)
+    Hto, Hjo, erro, Jo = P.eval(pose, True)
+    np.testing.assert_allclose(Ht, Hto, rtol=1e-11)
+    np.testing.assert_allclose(Hj, Hjo, rtol=1e-11)
+    assert _jrel(J, Jo) < 1e-8
+
+
+@pytest.mark.parametrize("path", [NATURAL, SORTED])
+def test_integer_aligned_warp(nid, orc, make_pair, synth, path):
+    """T_cw1 = T_wc0^-1: every pixel maps onto (almost exactly) itself, so u and v sit on integers, where
+    the in-bounds tests, the (int) truncation and the first-row/column gradient quirk all switch. The
+    decisions must be the reference's."""
+    p = make_pair(1000, 120, 160)
+    import dataclasses
+    depth = p.depth0.copy()
+    # u == 0 or v == 0 exactly makes the reference's gradient read column / row -1 (outside the image,
+    # types_six_dof_expmap.h:310-328 with ix = -1): undefined upstream, so keep those pixels out
+    depth[0, :] = 0.0
+    depth[:, 0] = 0.0
+    p = dataclasses.replace(p, im1=p.im0.copy(), depth0=depth)
+    pose_id = orc.se3_from_mat16(synth.mat16_inverse(p.T_wc0))
+    P = orc.Problem(p.im0, p.depth0, p.im1, p.T_wc0, p.intr, 2, 16, threads=4)
+    P.set_quirks(0, 1)
+    ctx = nid.Context(p.rows, p.cols, 2, 16)
+    ctx.set_option("path", path)
+    ctx.set_pair(0, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+    M = orc.se3_to_mat16(pose_id)
+    nc, href = ctx.prepare(0, M)
+    nco, hrefo = P.prepare(pose_id)
+    assert np.array_equal(nc, nco)
+    Ht, Hj, J = ctx.eval(0, M, True)
+    Hto, Hjo, erro, Jo = P.eval(pose_id, True)
+    np.testing.assert_allclose(Ht, Hto, rtol=1e-11)
+    np.testing.assert_allclose(Hj, Hjo, rtol=1e-11)
+    assert _jrel(J, Jo) < 1e-8
+
+
+@pytest.mark.parametrize("task_px", [16, 32, 128, 256])
+def test_task_length_does_not_change_results(nid, orc, make_pair, task_px):
+    p = make_pair(1000, 240, 320)
+    P, ctx, pose0 = _setup(nid, orc, p, 4, 16, path=SORTED)
+    M0 = orc.se3_to_mat16(pose0)
+    ctx.prepare(0, M0)
+    a = ctx.eval(0, M0, True)
+    ctx.set_option("task_px", 64)
+    ctx.set_option("task_px", task_px)  # a different task length invalidates the pixel store
+    with pytest.raises(nid.NidError, match="not prepared"):
+        ctx.eval(0, M0, True)
+    ctx.prepare(0, M0)
+    b = ctx.eval(0, M0, True)
+    np.testing.assert_allclose(b[0], a[0], rtol=1e-12)
+    np.testing.assert_allclose(b[1], a[1], rtol=1e-12)
+    np.testing.assert_allclose(b[2], a[2], rtol=1e-8, atol=1e-11)
