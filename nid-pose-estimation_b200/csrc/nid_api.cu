@@ -62,16 +62,17 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.sd0 = c->sd0; p.sd1 = c->sd1; p.sd2 = c->sd2; p.sid = c->sid;
   p.sl_off = c->sl_off; p.sl_task = c->sl_task; p.nslices = c->nslices;
   p.sell_cap = c->sell_cap; p.max_slices = c->max_slices; p.Twc0 = c->Twc0;
-  p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start;
-  p.cls_task_start = c->cls_task_start; p.row_cls = c->row_cls; p.wv = c->wv;
+  p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start; p.cell_slice_start = c->cell_slice_start;
+  p.cls_task_start = c->cls_task_start; p.span_start = c->span_start; p.hvs = c->hvs; p.wv = c->wv;
   p.max_tasks = c->max_tasks; p.g_stride = (int)c->g_stride;
-  p.G = c->G; p.qt = c->qt; p.tex = c->d_tex; p.tex2 = c->d_tex2;
+  p.G = c->G; p.tex = c->d_tex; p.tex2 = c->d_tex2;
   return p;
 }
 
 // The sorted path pays a fixed cost per (cell, class) segment; below ~12 pixels per segment on average
 // (e.g. the reference's default 16x16 cells at 640x480) the natural-order kernels are used instead.
 bool use_sorted(const nid_ctx* c) {
+  if (c->bins > NID_SORTED_MAX_BINS) return false;  // the assembly tables would not fit in shared memory
   if (c->opt_path == 1) return false;
   if (c->opt_path == 2) return true;
   return (double)c->N / ((double)c->ncell * NID_NCLS) >= 12.0;
@@ -125,14 +126,13 @@ int ensure_job_buffers(nid_ctx* c) {
     if (c->g_stride < need) {
       CU(cudaStreamSynchronize(c->stream), "sync before growing job buffers");
       if (c->G) cudaFree(c->G);
-      if (c->jpart_s) cudaFree(c->jpart_s);
-      c->G = nullptr; c->jpart_s = nullptr;
+      c->G = nullptr;
       OKR(dalloc(&c->G, J * need * c->bins, "G"));
-      OKR(dalloc(&c->jpart_s, J * need * 6, "jpart_s"));
       c->g_stride = need;
     }
-    if (!c->qt) OKR(dalloc(&c->qt, J * NC * NID_NCLS * (size_t)(c->bins - 3) * 3, "qt"));
+    if (!c->jpart_s) OKR(dalloc(&c->jpart_s, J * (size_t)c->max_slices * 6, "jpart_s"));  // one partial per slice
     if (!c->wv) OKR(dalloc(&c->wv, J * NC * hs, "wv"));
+    if (!c->hvs) OKR(dalloc(&c->hvs, J * NC * NID_NCLS * (size_t)c->bins, "hvs"));
   } else if (!c->part) {
     c->part_slots = J + 2 * (size_t)c->sm_count + 64;
     OKR(dalloc(&c->part, c->part_slots * NC * hs, "part"));
@@ -223,7 +223,7 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   OKR(dalloc(&c->cam, P * 4, "cam")); OKR(dalloc(&c->Twc0, P * 16, "Twc0"));
   OKR(dalloc(&c->cnt, P * NC * NID_NCLS, "cnt"));
   // pixels per task: short tasks when few evaluations are in flight (more threads), longer ones for batches
-  c->task_px = max_jobs >= 8 ? 64 : 32;
+  c->task_px = 32;
   const int min_task_px = 16;
   c->max_tasks = (int)(N / min_task_px + NC * NID_NCLS + 1);
   c->max_slices = c->max_tasks / 32 + (int)NC + 1;
@@ -240,20 +240,18 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   OKR(dalloc(&c->ntasks, P, "ntasks"));
   CU(cudaMemset(c->ntasks, 0, sizeof(int) * P), "memset ntasks");
   OKR(dalloc(&c->cell_task_start, P * (NC + 1), "cell_task_start"));
+  OKR(dalloc(&c->cell_slice_start, P * (NC + 1), "cell_slice_start"));
   OKR(dalloc(&c->cls_task_start, P * NC * (NID_NCLS + 1), "cls_task_start"));
   {
-    // classes whose span index k_r = floor(v' (B-3)/255) lies in [r-3, r]  (v' = 254.999 for v = 255)
-    std::vector<int> rc(2 * (size_t)bins);
+    // first class of every span: k_r(v) = floor(v' (B-3)/255), v' = 254.999 for v = 255, is monotone in v
+    const int NS = bins - 3;
+    std::vector<int> ss(NS + 1, 256);
     auto kr = [bins](int v) { double o = v >= 255 ? 254.999 : (double)v; return (int)std::floor(o * (bins - 3) / 255.0); };
-    for (int r = 0; r < bins; r++) {
-      int lo = 256, hi = 0;
-      for (int v = 0; v < 256; v++)
-        if (kr(v) >= r - 3 && kr(v) <= r) { lo = std::min(lo, v); hi = std::max(hi, v + 1); }
-      if (lo > hi) lo = hi = 0;
-      rc[2 * r] = lo; rc[2 * r + 1] = hi;
-    }
-    OKR(dalloc(&c->row_cls, rc.size(), "row_cls"));
-    CU(cudaMemcpy(c->row_cls, rc.data(), sizeof(int) * rc.size(), cudaMemcpyHostToDevice), "H2D row_cls");
+    for (int v = 255; v >= 0; v--)
+      for (int k = 0; k <= kr(v) && k <= NS; k++) ss[k] = v;
+    ss[NS] = 256;
+    OKR(dalloc(&c->span_start, ss.size(), "span_start"));
+    CU(cudaMemcpy(c->span_start, ss.data(), sizeof(int) * ss.size(), cudaMemcpyHostToDevice), "H2D span_start");
   }
   c->h_ntasks.assign(P, 0);
   // target images as gather-able textures (tex2Dgather needs a CUDA array created with cudaArrayTextureGather)
@@ -344,7 +342,7 @@ int nid_destroy(nid_ctx* c) {
                   c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
                   c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
                   c->bs_coef, c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->nslices, c->task_pos,
-                  c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->G, c->qt, c->jpart_s, c->d_tex, c->cls_task_start, c->row_cls, c->wv};
+                  c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->d_tex, c->cls_task_start, c->span_start, c->hvs, c->wv};
   for (auto t : c->h_tex) if (t) cudaDestroyTextureObject(t);
   for (auto t : c->h_tex2) if (t) cudaDestroyTextureObject(t);
   for (auto arr : c->tex_arrays) if (arr) cudaFreeArray(arr);
@@ -527,12 +525,13 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
   // Slices: the tasks of a cell ordered by length (longest first; counting sort, ties keep task order) and cut
   // into groups of 32. Slices never mix cells: the lanes of a warp then sample one cell-sized region of the
   // target image (texture-cache locality) and still run out of work together.
-  std::vector<int> sl_off(1, 0), sl_task, task_pos(std::max(nt, 1));
+  std::vector<int> sl_off(1, 0), sl_task, task_pos(std::max(nt, 1)), css(NC + 1, 0);
   sl_task.reserve((size_t)nt + 32 * (size_t)NC);
   long long off = 0;
   {
     std::vector<int> order, bucket(NID_TASK_PX_MAX + 2);
     for (int cell = 0; cell < NC; cell++) {
+      css[cell] = (int)sl_off.size() - 1;
       const int t0 = cts[cell], t1 = cts[cell + 1];
       if (t1 == t0) continue;
       order.assign(t1 - t0, 0);
@@ -553,6 +552,7 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
     }
   }
   const int ns = (int)sl_off.size() - 1;
+  css[NC] = ns;
   if ((size_t)off > c->sell_cap || ns > c->max_slices) { set_error("sliced pixel store overflow"); return NID_ERR_STATE; }
   if (nt) {
     CU(cudaMemcpyAsync(c->tasks + (size_t)pair * c->max_tasks, tasks.data(), sizeof(int2) * nt, cudaMemcpyHostToDevice,
@@ -567,6 +567,8 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
   CU(cudaMemcpyAsync(c->nslices + pair, &ns, sizeof(int), cudaMemcpyHostToDevice, c->stream), "H2D nslices");
   CU(cudaMemcpyAsync(c->cell_task_start + (size_t)pair * (NC + 1), cts.data(), sizeof(int) * (NC + 1),
                      cudaMemcpyHostToDevice, c->stream), "H2D cell_task_start");
+  CU(cudaMemcpyAsync(c->cell_slice_start + (size_t)pair * (NC + 1), css.data(), sizeof(int) * (NC + 1),
+                     cudaMemcpyHostToDevice, c->stream), "H2D cell_slice_start");
   CU(cudaMemcpyAsync(c->ntasks + pair, &nt, sizeof(int), cudaMemcpyHostToDevice, c->stream), "H2D ntasks");
   CU(cudaMemcpyAsync(c->cls_task_start + (size_t)pair * NC * (NID_NCLS + 1), clsts.data(), sizeof(int) * clsts.size(),
                      cudaMemcpyHostToDevice, c->stream), "H2D cls_task_start");
@@ -889,6 +891,7 @@ int nid_set_option(nid_ctx* c, const char* key, int value) {
   if (!strcmp(key, "force_strips")) { c->opt_force_strips = value; return NID_OK; }
   if (!strcmp(key, "path")) {
     if (value < 0 || value > 2) { set_error("path must be 0 (auto), 1 (natural) or 2 (sorted)"); return NID_ERR_ARG; }
+    if (value == 2 && c->bins > NID_SORTED_MAX_BINS) { set_error("the sorted path supports at most 40 bins"); return NID_ERR_UNSUPPORTED; }
     c->opt_path = value;
     return NID_OK;
   }

@@ -8,6 +8,7 @@
 #include "../../include/nid_b200.h"
 
 #define NID_NCLS 257  /* reference-intensity classes 0..255 + 256 = valid point without reference sample */
+#define NID_SORTED_MAX_BINS 40 /* k_assemble keeps 5*B^2 + 257*B doubles in shared memory */
 #define NID_TASK_PX_MAX 256 /* upper bound of the pixels per task of the sorted path (option "task_px") */
 
 namespace nid {
@@ -60,13 +61,14 @@ struct EvalParams {
   const int2* tasks;    // [n_pairs][max_tasks] {rank of first pixel in its class segment, count | cls<<9 | cell<<18}
   const int* ntasks;    // [n_pairs]
   const int* cell_task_start;  // [n_pairs][ncell+1]
+  const int* cell_slice_start; // [n_pairs][ncell+1] first slice of every cell (slices never mix cells)
   const int* cls_task_start;   // [n_pairs][ncell][NID_NCLS+1] first task of every class
-  const int* row_cls;          // [bins][2] class range [lo, hi) whose k_r lies in [r-3, r]
-  double* wv;                  // [jobs][ncell][bins*bins+bins] scaled log tables (assemble -> qtable)
+  const int* span_start;       // [bins-2] first class whose k_r is >= k (classes of span k: [k], [k+1])
+  double* hvs;                 // [jobs][ncell][NID_NCLS][bins] per-class soft histograms (class_sum -> assemble)
+  double* wv;                  // [jobs][ncell][bins*bins+bins] scaled log tables (assemble -> pass 2)
   int max_tasks;        // task-table stride per pair
   int g_stride;         // partial-buffer stride per job (tasks)
   double* G;            // [jobs][g_stride][bins]
-  double* qt;           // [jobs][ncell][NID_NCLS][bins-3][3] per-class, per-span Jacobian quadratics
   const cudaTextureObject_t* tex;   // [n_pairs] target image as a gather-able 8-bit 2D texture
   const cudaTextureObject_t* tex2;  // [n_pairs] packed I | Gx | Gy 32-bit texture (k_pack_tex)
 };
@@ -99,20 +101,22 @@ struct nid_ctx {
   int max_slices = 0;
   std::vector<int> h_nslices;
   int max_nslices_prepared = 0;
-  int task_px = 64;            // L: pixels per task
-  int opt_ilp_hist = 1, opt_ilp_jac = 1;  // pixels a lane processes together in pass 1 / pass 2
+  int task_px = 32;            // L: pixels per task
+  int opt_ilp_hist = 4, opt_ilp_jac = 2;  // pixels a lane processes together in pass 1 / pass 2
   bool sell_points = false;    // pairs carry caller-supplied world points (nid_set_pair_points)
   int2* tasks = nullptr;
   int* ntasks = nullptr;
   int* cell_task_start = nullptr;
+  int* cell_slice_start = nullptr;
   int* cls_task_start = nullptr;
-  int* row_cls = nullptr;
+  int* span_start = nullptr;
+  double* hvs = nullptr;
   double* wv = nullptr;
   int max_tasks = 0;
   std::vector<int> h_ntasks;
   int max_ntasks_prepared = 0;
   // sorted path, per job (grown on demand)
-  double *G = nullptr, *qt = nullptr, *jpart_s = nullptr;
+  double *G = nullptr, *jpart_s = nullptr;
   std::vector<cudaArray_t> tex_arrays, tex2_arrays;
   std::vector<cudaTextureObject_t> h_tex, h_tex2;
   cudaTextureObject_t *d_tex = nullptr, *d_tex2 = nullptr;

@@ -424,26 +424,42 @@ __global__ void __launch_bounds__(256, W == 1 ? 4 : (W == 2 ? 3 : 2)) k_hist_sel
 }
 
 // ------------------------------------------------------------------------------------------------
-// Assembly (a7 + table half of a8): one CTA per (cell, job). Combines the task partials of the cell in
-// task order into P_t and P_j,
-//     P_j[r][t] = sum_v w_ref,v[r - k_r(v)] * h_v[t]   over the classes v with k_r(v) in [r-3, r]
+// Per-class soft histograms: hvs[job][cell][v][t] = sum over the tasks of class v (task order) of G[task][t].
+// One thread per output, grid (ceil(257*B/256), ncell, jobs): ~1.6 M independent short sums, full occupancy.
+__global__ void __launch_bounds__(256) k_class_sum(EvalParams p) {
+  const int B = p.bins;
+  const int c = blockIdx.y, job = blockIdx.z + p.job0;
+  const int pair = p.job_pair[job];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NID_NCLS * B) return;
+  if (p.n_c[pair * p.ncell + c] < NID_MIN_CELL_POINTS) return;
+  const int v = i / B, tt = i % B;
+  const int* cts = p.cls_task_start + ((size_t)pair * p.ncell + c) * (NID_NCLS + 1);
+  const int t0 = cts[v], t1 = cts[v + 1];
+  const double* G = p.G + (size_t)job * p.g_stride * B + tt;
+  double hv = 0.0;
+  for (int t = t0; t < t1; t++) hv += G[(size_t)t * B];
+  p.hvs[((size_t)job * p.ncell + c) * (NID_NCLS * B) + i] = hv;
+}
+
+// Assembly (a7 + table half of a8): one CTA per (cell, job). From the per-class soft histograms h_v,
+//     P_j[r][t] = sum_kk sum_{v: k_r(v) = r-kk} w_ref,v[kk] * h_v[t]     (kk = 0..3, classes in order)
 //     P_t[t]    = sum_v h_v[t]
 // normalises by n_c, computes H_t, H_j, err (computeH.cu:261-300; types_six_dof_expmap.cpp:609-635,
-// .h:227) and, when want_jac, stores the scaled tables for k_qtable:
+// .h:227) and, when want_jac, stores the scaled tables for pass 2:
 //   W[r][t] = coefJ * (1 + log2 P_j[r][t]),  V[t] = coefT * (1 + log2 P_t[t])   (0 where P < 1e-30),
 //   coefJ = -(s/(n_c Hj^2)) (Ht + Href), coefT = (s/(n_c Hj^2)) Hj  (types_six_dof_expmap.cpp:486-528).
-// Tasks are ordered by class, and k_r(v) is monotone in v, so every histogram row only walks the
-// contiguous task range of its classes (cls_task_start).
+// k_r(v) is monotone in v, so the classes of a span are a contiguous range (span_start).
 #define NID_ASM_THREADS 512
-#define NID_ASM_MAXE 8  // ceil(64*64/512)
-__global__ void __launch_bounds__(NID_ASM_THREADS) k_assemble(EvalParams p, int want_jac) {
+__global__ void __launch_bounds__(NID_ASM_THREADS, 2) k_assemble(EvalParams p, int want_jac) {
   extern __shared__ double sm[];
   __shared__ double scratch[NID_ASM_THREADS / 32];
-  __shared__ int s_cts[NID_NCLS + 1];
-  const int B = p.bins, BB = B * B;
-  double* Pall = sm;                 // [BB + B]
-  double* red = sm + BB + B;         // [NID_ASM_THREADS] partial sums of P_t
+  const int B = p.bins, BB = B * B, NS = B - 3;
+  double* Pall = sm;                    // [BB + B]
+  double* red = sm + BB + B;            // [NID_ASM_THREADS] partial sums of P_t
   double* hvs = red + NID_ASM_THREADS;  // [NID_NCLS][B] per-class soft histograms
+  double* part = hvs + NID_NCLS * B;    // [4][BB] per-span partial sums of P_j
+  double* wl = part + 4 * BB;           // [256][4] reference weights
   const int c = blockIdx.x, job = blockIdx.y + p.job0;
   const int pair = p.job_pair[job];
   const int nc = p.n_c[pair * p.ncell + c];
@@ -452,32 +468,23 @@ __global__ void __launch_bounds__(NID_ASM_THREADS) k_assemble(EvalParams p, int 
     if (threadIdx.x == 0) { p.ht[o] = nan(""); p.hj[o] = nan(""); p.err[o] = nan(""); }
     return;
   }
-  const int* cts = p.cls_task_start + ((size_t)pair * p.ncell + c) * (NID_NCLS + 1);
-  for (int i = threadIdx.x; i <= NID_NCLS; i += blockDim.x) s_cts[i] = cts[i];
-  __syncthreads();
-  const double* G = p.G + (size_t)job * p.g_stride * B;
-  // ---- per-class sums over the class's tasks (task order), all classes in parallel
-  for (int i = threadIdx.x; i < NID_NCLS * B; i += blockDim.x) {
-    const int v = i / B, tt = i % B;
-    double hv = 0.0;
-    for (int t = s_cts[v]; t < s_cts[v + 1]; t++) hv += G[(size_t)t * B + tt];
-    hvs[i] = hv;
+  {
+    const double* src = p.hvs + o * (size_t)(NID_NCLS * B);
+    for (int i = threadIdx.x; i < NID_NCLS * B; i += blockDim.x) hvs[i] = src[i];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) wl[i] = p.lut_w[i];
   }
   __syncthreads();
-  // ---- P_j rows from the classes with k_r in [r-3, r] (class order)
-  double ej = 0.0;
-#pragma unroll
-  for (int e = 0; e < NID_ASM_MAXE; e++) {
-    const int idx = threadIdx.x + e * NID_ASM_THREADS;
-    if (idx < BB) {
-      const int r = idx / B, tt = idx % B;
-      double a = 0.0;
-      const int vlo = p.row_cls[2 * r], vhi = p.row_cls[2 * r + 1];
-      for (int v = vlo; v < vhi; v++) a += p.lut_w[4 * v + (r - p.lut_k[v])] * hvs[v * B + tt];
-      const double q = a / (double)nc;
-      Pall[idx] = q;
-      ej -= (q < kSigma) ? 0.0 : q * log2(q);
+  // ---- P_j: item (kk, r, t) sums the classes of span r-kk
+  for (int it = threadIdx.x; it < 4 * BB; it += blockDim.x) {
+    const int kk = it / BB, idx = it % BB;
+    const int r = idx / B, tt = idx % B;
+    const int k = r - kk;
+    double a = 0.0;
+    if (k >= 0 && k < NS) {
+      const int vlo = p.span_start[k], vhi = p.span_start[k + 1];
+      for (int v = vlo; v < vhi; v++) a += wl[4 * v + kk] * hvs[v * B + tt];
     }
+    part[it] = a;
   }
   // ---- P_t: thread (g, tt) sums classes g, g+ng, ... ; groups are then added in order
   {
@@ -489,13 +496,20 @@ __global__ void __launch_bounds__(NID_ASM_THREADS) k_assemble(EvalParams p, int 
     red[threadIdx.x] = a;
   }
   __syncthreads();
-  double et = 0.0;
-  if ((int)threadIdx.x < B) {
+  double ej = 0.0, et = 0.0;
+  for (int idx = threadIdx.x; idx < BB; idx += blockDim.x) {
+    const double a = ((part[idx] + part[BB + idx]) + part[2 * BB + idx]) + part[3 * BB + idx];
+    const double q = a / (double)nc;
+    Pall[idx] = q;
+    ej -= (q < kSigma) ? 0.0 : q * log2(q);
+  }
+  if ((int)threadIdx.x >= NID_ASM_THREADS - B) {  // the last B threads (idle in the loop above for B <= 22)
+    const int tt = threadIdx.x - (NID_ASM_THREADS - B);
     const int ng = NID_ASM_THREADS / B;
     double a = 0.0;
-    for (int g = 0; g < ng; g++) a += red[g * B + threadIdx.x];
+    for (int g = 0; g < ng; g++) a += red[g * B + tt];
     const double q = a / (double)nc;
-    Pall[BB + threadIdx.x] = q;
+    Pall[BB + tt] = q;
     et -= (q < kSigma) ? 0.0 : q * log2(q);
   }
   const double Hj = block_sum(ej, scratch);
@@ -518,49 +532,6 @@ __global__ void __launch_bounds__(NID_ASM_THREADS) k_assemble(EvalParams p, int 
       wv[i] = L * (i < BB ? coefJ : coefT);
     }
   }
-}
-
-// Per-class / per-span quadratic of pass 2, one thread per (class v, span k):
-//   c(f) = q0 + q1 f + q2 f^2 = sum_m N'_{k+m}(k+f) * Wv[v][k+m],
-//   Wv[v][t] = V[t] + sum_kk w_ref,v[kk] W[k_r(v)+kk][t]     (class 256: V only)
-// grid (ceil(257*NS/256), ncell, jobs)
-__global__ void __launch_bounds__(256) k_qtable(EvalParams p) {
-  extern __shared__ double sm[];  // W | V | spline table
-  const int B = p.bins, BB = B * B, NS = B - 3;
-  const int c = blockIdx.y, job = blockIdx.z + p.job0;
-  const int pair = p.job_pair[job];
-  if (p.n_c[pair * p.ncell + c] < NID_MIN_CELL_POINTS) return;
-  const size_t o = (size_t)job * p.ncell + c;
-  const double* wvg = p.wv + o * (size_t)(BB + B);
-  double* coef = sm + BB + B;
-  for (int i = threadIdx.x; i < BB + B; i += blockDim.x) sm[i] = wvg[i];
-  for (int i = threadIdx.x; i < NS * 16; i += blockDim.x) coef[i] = p.bs_coef[i];
-  __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= NID_NCLS * NS) return;
-  const int v = i / NS, k = i % NS;
-  double wv[4];
-#pragma unroll
-  for (int m = 0; m < 4; m++) wv[m] = sm[BB + k + m];
-  if (v < 256) {
-    const int kr = p.lut_k[v];
-#pragma unroll
-    for (int kk = 0; kk < 4; kk++) {
-      const double wr = p.lut_w[4 * v + kk];
-#pragma unroll
-      for (int m = 0; m < 4; m++) wv[m] += wr * sm[(kr + kk) * B + k + m];
-    }
-  }
-  double q0 = 0.0, q1 = 0.0, q2 = 0.0;
-#pragma unroll
-  for (int m = 0; m < 4; m++) {
-    const double* cf = coef + (k * 4 + m) * 4;
-    q0 += cf[1] * wv[m];
-    q1 += 2.0 * cf[2] * wv[m];
-    q2 += 3.0 * cf[3] * wv[m];
-  }
-  double* qt = p.qt + o * (size_t)(NID_NCLS * NS * 3) + 3 * (size_t)i;
-  qt[0] = q0; qt[1] = q1; qt[2] = q2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -657,6 +628,14 @@ __global__ void __launch_bounds__(128, W == 1 ? 5 : 4) k_jac_sell(EvalParams p) 
   const int job = blockIdx.x + p.job0;
   const int pair = p.job_pair[job];
   build_geo<PTS>(p, job, pair, &geo);
+  {
+    // derivative of the per-span basis polynomials: dco[k][j][m] = (j+1) * coef[k][m][j+1]
+    double* dco = sm + 3 * NS * 128 + 4 * (B * (B + 1) + B);
+    for (int i = threadIdx.x; i < NS * 12; i += blockDim.x) {
+      const int k = i / 12, j = (i % 12) / 4, m = i % 4;
+      dco[i] = (double)(j + 1) * p.bs_coef[(k * 4 + m) * 4 + j + 1];
+    }
+  }
   __syncthreads();
   const int slice = blockIdx.y * 4 + warp;
   if (slice >= p.nslices[pair]) return;
@@ -664,11 +643,50 @@ __global__ void __launch_bounds__(128, W == 1 ? 5 : 4) k_jac_sell(EvalParams p) 
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
   const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
   double* wq = sm + threadIdx.x;  // wq[i * 128]
-  if (task >= 0) {
-    const int desc = p.tasks[(size_t)pair * p.max_tasks + task].y;
-    const int cls = (desc >> 9) & 0x1ff, cell = (desc >> 18) & 0x3fff;
-    const double* row = p.qt + (((size_t)job * p.ncell + cell) * NID_NCLS + cls) * (NS * 3);
-    for (int i = 0; i < NS * 3; i++) wq[i * 128] = row[i];
+  // ---- per-class / per-span quadratic of the lane's task (class v, cell of the slice):
+  //   c(f) = q0 + q1 f + q2 f^2 = sum_m N'_{k+m}(k+f) * Wv[k+m],
+  //   Wv[t] = V[t] + sum_kk w_ref,v[kk] W[k_r(v)+kk][t]     (class 256: V only)
+  // from the cell's scaled log tables W|V (k_assemble), staged per warp with rows padded to B+1.
+  {
+    const int BP = B + 1;
+    double* Ww = sm + 3 * NS * 128 + warp * (B * BP + B);
+    double* Vw = Ww + B * BP;
+    const double* dco = sm + 3 * NS * 128 + 4 * (B * BP + B);  // [NS][3][4] derivative coefficients
+    const int desc = task >= 0 ? p.tasks[(size_t)pair * p.max_tasks + task].y : 0;
+    const int cell = __shfl_sync(0xffffffffu, (desc >> 18) & 0x3fff, 0);  // lane 0 always owns a task
+    const double* wvg = p.wv + ((size_t)job * p.ncell + cell) * (size_t)(B * B + B);
+    for (int i = lane; i < B * B; i += 32) Ww[(i / B) * BP + i % B] = wvg[i];
+    for (int i = lane; i < B; i += 32) Vw[i] = wvg[B * B + i];
+    __syncwarp();
+    if (task >= 0) {
+      const int cls = (desc >> 9) & 0x1ff;
+      double wr[4] = {0.0, 0.0, 0.0, 0.0};
+      int kr = 0;
+      if (cls < 256) {
+        kr = p.lut_k[cls];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) wr[kk] = p.lut_w[4 * cls + kk];
+      }
+      const double* Wr = Ww + kr * BP;
+      auto wv_at = [&](int t) {
+        double a = Vw[t];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) a += wr[kk] * Wr[kk * BP + t];
+        return a;
+      };
+      double w0 = wv_at(0), w1 = wv_at(1), w2 = wv_at(2), w3;
+      for (int k = 0; k < NS; k++) {
+        w3 = wv_at(k + 3);
+        const double* cf = dco + k * 12;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        a0 += cf[0] * w0; a1 += cf[4] * w0; a2 += cf[8] * w0;
+        a0 += cf[1] * w1; a1 += cf[5] * w1; a2 += cf[9] * w1;
+        a0 += cf[2] * w2; a1 += cf[6] * w2; a2 += cf[10] * w2;
+        a0 += cf[3] * w3; a1 += cf[7] * w3; a2 += cf[11] * w3;
+        wq[(3 * k) * 128] = a0; wq[(3 * k + 1) * 128] = a1; wq[(3 * k + 2) * 128] = a2;
+        w0 = w1; w1 = w2; w2 = w3;
+      }
+    }
   }
   const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
   const double* q0 = p.sd0 + sbase;
@@ -686,14 +704,23 @@ __global__ void __launch_bounds__(128, W == 1 ? 5 : 4) k_jac_sell(EvalParams p) 
 #pragma unroll
     for (int j0 = 0; j0 < 4; j0 += W) jac_pixels<PTS, W>(p, &geo, G, j0, tex2, im1, s, hfx, hfy, wq, acc);
   }
-  if (task >= 0) {
-    double* out = p.jpart + ((size_t)job * p.g_stride + task) * 6;
+  // one partial per slice: fixed-order butterfly over the 32 lanes (lanes without a task hold zeros)
 #pragma unroll
-    for (int k = 0; k < 6; k++) out[k] = acc[k];
+  for (int k = 0; k < 6; k++) {
+    double vv = acc[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) vv += __shfl_xor_sync(0xffffffffu, vv, off);
+    acc[k] = vv;
+  }
+  if (lane < 6) {
+    double vv = acc[0];
+#pragma unroll
+    for (int k = 1; k < 6; k++) vv = lane == k ? acc[k] : vv;
+    p.jpart[((size_t)job * p.max_slices + slice) * 6 + lane] = vv;
   }
 }
 
-// a8 tail: one warp per (job, cell): task partials summed in a fixed order -> der[6]
+// a8 tail: one warp per (job, cell): the slice partials of the cell summed in a fixed order -> der[6]
 __global__ void __launch_bounds__(256) k_jac_final_sorted(EvalParams p, int n_jobs) {
   const int lane = threadIdx.x & 31;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -705,11 +732,11 @@ __global__ void __launch_bounds__(256) k_jac_final_sorted(EvalParams p, int n_jo
     if (lane < 6) der[lane] = nan("");
     return;
   }
-  const int t0 = p.cell_task_start[pair * (p.ncell + 1) + c];
-  const int t1 = p.cell_task_start[pair * (p.ncell + 1) + c + 1];
-  const double* jp = p.jpart + (size_t)job * p.g_stride * 6;
+  const int s0 = p.cell_slice_start[pair * (p.ncell + 1) + c];
+  const int s1 = p.cell_slice_start[pair * (p.ncell + 1) + c + 1];
+  const double* jp = p.jpart + (size_t)job * p.max_slices * 6;
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  for (int t = t0 + lane; t < t1; t += 32) {
+  for (int t = s0 + lane; t < s1; t += 32) {
 #pragma unroll
     for (int k = 0; k < 6; k++) acc[k] += jp[(size_t)t * 6 + k];
   }
@@ -761,9 +788,11 @@ int launch_pack_tex(nid_ctx* c, int pair, unsigned* d_out) {
 }
 
 size_t hist_sell_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)c->bins * 256 + (size_t)(c->bins - 3) * 16); }
-size_t jac_sell_smem(const nid_ctx* c) { return sizeof(double) * (size_t)(c->bins - 3) * 3 * 128; }
-size_t assemble_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins); }
-size_t qtable_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)c->bins * c->bins + c->bins + (size_t)(c->bins - 3) * 16); }
+size_t jac_sell_smem(const nid_ctx* c) {
+  const size_t B = c->bins, NS = B - 3;
+  return sizeof(double) * (NS * 3 * 128 + 4 * (B * (B + 1) + B) + NS * 12);
+}
+size_t assemble_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)5 * c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins + 1024); }
 
 template <bool PTS>
 static void launch_hist_w(nid_ctx* c, const EvalParams& p, int ns, int n_jobs) {
@@ -794,13 +823,10 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
   if (pts) launch_hist_w<true>(c, p, ns, n_jobs); else launch_hist_w<false>(c, p, ns, n_jobs);
   NID_LAUNCH_CHECK(c, "k_hist_sell");
   ktime_mark(c, 1);
+  k_class_sum<<<dim3((NID_NCLS * c->bins + 255) / 256, c->ncell, n_jobs), 256, 0, c->stream>>>(p);
+  NID_LAUNCH_CHECK(c, "k_class_sum");
   k_assemble<<<dim3(c->ncell, n_jobs), NID_ASM_THREADS, assemble_smem(c), c->stream>>>(p, want_jac);
   NID_LAUNCH_CHECK(c, "k_assemble");
-  if (want_jac) {
-    const int items = NID_NCLS * (c->bins - 3);
-    k_qtable<<<dim3((items + 255) / 256, c->ncell, n_jobs), 256, qtable_smem(c), c->stream>>>(p);
-    NID_LAUNCH_CHECK(c, "k_qtable");
-  }
   ktime_mark(c, 2);
   if (want_jac) {
     if (pts) launch_jac_w<true>(c, p, ns, n_jobs); else launch_jac_w<false>(c, p, ns, n_jobs);
@@ -821,6 +847,7 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
 
 int sorted_init(nid_ctx* c) {
   cudaError_t e;
+  if (c->bins > NID_SORTED_MAX_BINS) return NID_OK;  // natural-order kernels only
 #define NID_SMEM_ATTR(k, bytes)                                                                     \
   e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));            \
   if (e != cudaSuccess) return check_cuda(e, "smem attr " #k);
@@ -835,7 +862,6 @@ int sorted_init(nid_ctx* c) {
   NID_SMEM_ATTR((k_jac_sell<true, 2>), jac_sell_smem(c));
   NID_SMEM_ATTR((k_jac_sell<false, 2>), jac_sell_smem(c));
   NID_SMEM_ATTR(k_assemble, assemble_smem(c));
-  NID_SMEM_ATTR(k_qtable, qtable_smem(c));
 #undef NID_SMEM_ATTR
   return NID_OK;
 }

@@ -10,6 +10,6 @@ tail -1 gpurun_out/${tag}_bench.json
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/${tag}_bench_ref.json 2>&1; tail -1 gpurun_out/${tag}_bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 3 --warmup 3 --cpu-budget 0.2 > gpurun_out/${tag}_ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_hist_sell|k_jac_sell|k_assemble|k_qtable' -s 8 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_hist_sell|k_jac_sell|k_assemble|k_class_sum' -s 8 -c 4 \
   -o gpurun_out/${tag}_prof -f python bench.py --steps 3 --warmup 3 --cpu-budget 0.2 > gpurun_out/${tag}_ncu_full.log 2>&1
 ls -la gpurun_out
