@@ -65,14 +65,15 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start; p.cell_slice_start = c->cell_slice_start;
   p.cls_task_start = c->cls_task_start; p.span_start = c->span_start; p.hvs = c->hvs; p.wv = c->wv;
   p.max_tasks = c->max_tasks; p.g_stride = (int)c->g_stride;
-  p.G = c->G; p.tex = c->d_tex; p.tex2 = c->d_tex2;
+  p.G = c->G; p.fp1 = c->fp1; p.tex2 = c->d_tex2;
   return p;
 }
 
 // The sorted path pays a fixed cost per (cell, class) segment; below ~12 pixels per segment on average
 // (e.g. the reference's default 16x16 cells at 640x480) the natural-order kernels are used instead.
 bool use_sorted(const nid_ctx* c) {
-  if (c->bins > NID_SORTED_MAX_BINS) return false;  // the assembly tables would not fit in shared memory
+  // the assembly tables must fit in shared memory; below 8 bins every span is an end span
+  if (c->bins > NID_SORTED_MAX_BINS || c->bins < 8) return false;
   if (c->opt_path == 1) return false;
   if (c->opt_path == 2) return true;
   return (double)c->N / ((double)c->ncell * NID_NCLS) >= 12.0;
@@ -142,8 +143,7 @@ int ensure_job_buffers(nid_ctx* c) {
 }
 
 static int update_texture(nid_ctx* c, int pair) {
-  CU(cudaMemcpy2DToArrayAsync(c->tex_arrays[pair], 0, 0, c->im1 + (size_t)pair * c->N, c->cols, c->cols, c->rows,
-                              cudaMemcpyDeviceToDevice, c->stream), "im1 -> texture array");
+  OKR(launch_pack_fp(c, pair));
   OKR(launch_pack_tex(c, pair, c->d_pack));
   CU(cudaMemcpy2DToArrayAsync(c->tex2_arrays[pair], 0, 0, c->d_pack, sizeof(unsigned) * c->cols, sizeof(unsigned) * c->cols,
                               c->rows, cudaMemcpyDeviceToDevice, c->stream), "packed im1 -> texture array");
@@ -254,33 +254,9 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
     CU(cudaMemcpy(c->span_start, ss.data(), sizeof(int) * ss.size(), cudaMemcpyHostToDevice), "H2D span_start");
   }
   c->h_ntasks.assign(P, 0);
-  // target images as gather-able textures (tex2Dgather needs a CUDA array created with cudaArrayTextureGather)
+  // packed target images as gather-able textures (tex2Dgather needs a CUDA array created with cudaArrayTextureGather)
   {
-    c->tex_arrays.assign(P, nullptr);
-    c->h_tex.assign(P, 0);
-    cudaChannelFormatDesc cd = cudaCreateChannelDesc<unsigned char>();
     bool ok = true;
-    for (size_t i = 0; i < P && ok; i++) {
-      if (cudaMallocArray(&c->tex_arrays[i], &cd, cols, rows, cudaArrayTextureGather) != cudaSuccess) { ok = false; break; }
-      cudaResourceDesc rd;
-      memset(&rd, 0, sizeof(rd));
-      rd.resType = cudaResourceTypeArray;
-      rd.res.array.array = c->tex_arrays[i];
-      cudaTextureDesc td;
-      memset(&td, 0, sizeof(td));
-      td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-      td.filterMode = cudaFilterModePoint;
-      td.readMode = cudaReadModeElementType;
-      td.normalizedCoords = 0;
-      if (cudaCreateTextureObject(&c->h_tex[i], &rd, &td, nullptr) != cudaSuccess) ok = false;
-    }
-    if (!ok) {
-      cudaGetLastError();
-      set_error("could not create gather textures for the target images");
-      return NID_ERR_CUDA;
-    }
-    OKR(dalloc(&c->d_tex, P, "d_tex"));
-    CU(cudaMemcpy(c->d_tex, c->h_tex.data(), sizeof(cudaTextureObject_t) * P, cudaMemcpyHostToDevice), "H2D tex handles");
     // packed I | Gx | Gy texels, 32 bit
     c->tex2_arrays.assign(P, nullptr);
     c->h_tex2.assign(P, 0);
@@ -307,6 +283,9 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
     OKR(dalloc(&c->d_tex2, P, "d_tex2"));
     CU(cudaMemcpy(c->d_tex2, c->h_tex2.data(), sizeof(cudaTextureObject_t) * P, cudaMemcpyHostToDevice), "H2D tex2 handles");
     OKR(dalloc(&c->d_pack, N, "d_pack"));
+    OKR(dalloc(&c->fp1, P * N, "fp1"));
+    c->h_Twc0.assign(P * 16, 0.0);
+    c->h_cam.assign(P * 4, 1.0);
   }
   OKR(dalloc(&c->d_depth, N, "d_depth")); OKR(dalloc(&c->d_img64, N, "d_img64")); OKR(dalloc(&c->d_flag, 1, "d_flag"));
   OKR(dalloc(&c->lut_w, 256 * 4, "lut_w")); OKR(dalloc(&c->lut_k, 256, "lut_k"));
@@ -342,10 +321,8 @@ int nid_destroy(nid_ctx* c) {
                   c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
                   c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
                   c->bs_coef, c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->nslices, c->task_pos,
-                  c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->d_tex, c->cls_task_start, c->span_start, c->hvs, c->wv};
-  for (auto t : c->h_tex) if (t) cudaDestroyTextureObject(t);
+                  c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->fp1, c->cls_task_start, c->span_start, c->hvs, c->wv};
   for (auto t : c->h_tex2) if (t) cudaDestroyTextureObject(t);
-  for (auto arr : c->tex_arrays) if (arr) cudaFreeArray(arr);
   for (auto arr : c->tex2_arrays) if (arr) cudaFreeArray(arr);
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->h_poses) cudaFreeHost(c->h_poses);
@@ -370,6 +347,8 @@ static int set_pair_common(nid_ctx* c, int pair, const double* depth, const doub
   CU(cudaMemcpyAsync(c->depth + (size_t)pair * c->N, depth, sizeof(double) * c->N, cudaMemcpyDefault, c->stream), "H2D depth");
   CU(cudaMemcpyAsync(c->Twc0 + 16 * pair, T_wc0, sizeof(double) * 16, cudaMemcpyDefault, c->stream), "H2D Twc0");
   CU(cudaMemcpyAsync(c->cam + 4 * pair, intr, sizeof(double) * 4, cudaMemcpyDefault, c->stream), "H2D intr");
+  memcpy(c->h_Twc0.data() + 16 * (size_t)pair, T_wc0, sizeof(double) * 16);
+  memcpy(c->h_cam.data() + 4 * (size_t)pair, intr, sizeof(double) * 4);
   OKR(launch_points(c, pair));
   c->pair_prepared[pair] = 0;
   return NID_OK;
@@ -430,6 +409,7 @@ int nid_set_pair_points(nid_ctx* c, int pair, const double* points_3d, const dou
     if (!c->d_pix) OKR(dalloc(&c->d_pix, (size_t)8 * c->N, "d_pix"));
     CU(cudaMemcpyAsync(c->d_pix, points_3d, sizeof(double) * 3 * c->N, cudaMemcpyDefault, c->stream), "H2D points3d");
     CU(cudaMemcpyAsync(c->cam + 4 * pair, intr, sizeof(double) * 4, cudaMemcpyDefault, c->stream), "H2D intr");
+    memcpy(c->h_cam.data() + 4 * (size_t)pair, intr, sizeof(double) * 4);
     OKR(launch_points_soa(c, pair, c->d_pix));
     c->pair_prepared[pair] = 0;
     if (!c->sell_points) {
@@ -891,7 +871,7 @@ int nid_set_option(nid_ctx* c, const char* key, int value) {
   if (!strcmp(key, "force_strips")) { c->opt_force_strips = value; return NID_OK; }
   if (!strcmp(key, "path")) {
     if (value < 0 || value > 2) { set_error("path must be 0 (auto), 1 (natural) or 2 (sorted)"); return NID_ERR_ARG; }
-    if (value == 2 && c->bins > NID_SORTED_MAX_BINS) { set_error("the sorted path supports at most 40 bins"); return NID_ERR_UNSUPPORTED; }
+    if (value == 2 && (c->bins > NID_SORTED_MAX_BINS || c->bins < 8)) { set_error("the sorted path supports 8 to 40 bins"); return NID_ERR_UNSUPPORTED; }
     c->opt_path = value;
     return NID_OK;
   }

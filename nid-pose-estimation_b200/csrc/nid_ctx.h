@@ -69,7 +69,7 @@ struct EvalParams {
   int max_tasks;        // task-table stride per pair
   int g_stride;         // partial-buffer stride per job (tasks)
   double* G;            // [jobs][g_stride][bins]
-  const cudaTextureObject_t* tex;   // [n_pairs] target image as a gather-able 8-bit 2D texture
+  const unsigned* fp1;              // [n_pairs][N] footprint-packed target image (pass 1), see k_pack_fp
   const cudaTextureObject_t* tex2;  // [n_pairs] packed I | Gx | Gy 32-bit texture (k_pack_tex)
 };
 
@@ -117,9 +117,11 @@ struct nid_ctx {
   int max_ntasks_prepared = 0;
   // sorted path, per job (grown on demand)
   double *G = nullptr, *jpart_s = nullptr;
-  std::vector<cudaArray_t> tex_arrays, tex2_arrays;
-  std::vector<cudaTextureObject_t> h_tex, h_tex2;
-  cudaTextureObject_t *d_tex = nullptr, *d_tex2 = nullptr;
+  std::vector<cudaArray_t> tex2_arrays;
+  std::vector<cudaTextureObject_t> h_tex2;
+  cudaTextureObject_t* d_tex2 = nullptr;
+  unsigned* fp1 = nullptr;     // [n_pairs][N]
+  std::vector<double> h_Twc0, h_cam;  // host copies per pair (geometry tables are built on the host)
   unsigned* d_pack = nullptr;  // [N] scratch for the packed texture
   size_t g_stride = 0;
   int opt_path = 0;            // 0 auto, 1 natural-order atomics (v1), 2 sorted
@@ -187,6 +189,7 @@ int sorted_init(nid_ctx* c);
 int launch_count_classes(nid_ctx* c, int pair);
 int launch_scatter(nid_ctx* c, int pair);
 int launch_pack_tex(nid_ctx* c, int pair, unsigned* d_out);
+int launch_pack_fp(nid_ctx* c, int pair);
 int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int want_jac);
 int launch_href(nid_ctx* c, int pair);
 

@@ -132,48 +132,41 @@ __global__ void k_pack_tex(int rows, int cols, const uint8_t* __restrict__ im, u
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Per-job geometry, built once per CTA in shared memory.
-struct Geo {
-  double M[12];   // fast path: T_cw1 * T_wc0 (depth form) or T_cw1 (point form), 3x4, M[3*c + r]
-  double T1[12];  // T_cw1, 3x4 (exact path)
-  double T0[16];  // T_wc0 column-major (exact path, depth form)
-  double fx, fy, cx, cy, ifx, ify, ncx, ncy;  // ncx = -cx/fx
-};
-
-template <bool PTS>
-__device__ __forceinline__ void build_geo(const EvalParams& p, int job, int pair, Geo* g) {
-  if (threadIdx.x < 12) {
-    const int c = threadIdx.x / 3, r = threadIdx.x % 3;
-    const double* T1 = p.poses + 16 * job;
-    const double* T0 = p.Twc0 + 16 * pair;
-    g->T1[threadIdx.x] = T1[4 * c + r];
-    double m;
-    if (PTS) m = T1[4 * c + r];
-    else {
-      m = T1[r] * T0[4 * c] + T1[4 + r] * T0[4 * c + 1] + T1[8 + r] * T0[4 * c + 2];
-      if (c == 3) m += T1[12 + r];
-    }
-    g->M[threadIdx.x] = m;
-  } else if (threadIdx.x < 28) {
-    g->T0[threadIdx.x - 12] = p.Twc0[16 * pair + threadIdx.x - 12];
-  } else if (threadIdx.x == 28) {
-    const double* cp = p.cam + 4 * pair;
-    g->fx = cp[0]; g->fy = cp[1]; g->cx = cp[2]; g->cy = cp[3];
-    g->ifx = 1.0 / cp[0]; g->ify = 1.0 / cp[1];
-    g->ncx = -cp[2] / cp[0]; g->ncy = -cp[3] / cp[1];
+// Footprint-packed target image for pass 1: out[y*cols + x] = I(x,y) | I(x+1,y)<<8 | I(x,y+1)<<16 | I(x+1,y+1)<<24
+// (neighbours clamped at the border; in-bounds samples never reach it): one aligned 32-bit load per sample.
+__global__ void k_pack_fp(int rows, int cols, const uint8_t* __restrict__ im, unsigned* __restrict__ out) {
+  const int N = rows * cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const int y = i / cols, x = i % cols;
+    const int xp = min(x + 1, cols - 1), yp = min(y + 1, rows - 1);
+    out[i] = (unsigned)im[y * cols + x] | ((unsigned)im[y * cols + xp] << 8) | ((unsigned)im[yp * cols + x] << 16) |
+             ((unsigned)im[yp * cols + xp] << 24);
   }
 }
 
-// The reference's exact sequence for one pixel: CudaPoints3d.cu:20-28 then computeH.cu:152-158.
+// ------------------------------------------------------------------------------------------------
+// Per-job geometry of the fast path. Built on the host from the staged poses and handed to the pixel
+// kernels BY VALUE: the kernel parameter space is a constant bank, so the entries are read with uniform
+// constant loads instead of occupying ~40 registers of matrix entries per thread.
+//   [0..11] M[3c + r]: T_cw1 * T_wc0 (depth form) or T_cw1 (point form), 3x4; pass 1 gets rows 0 and 1
+//           pre-multiplied by fx and fy (it only needs u and v)
+//   [12] 1/fx  [13] -cx/fx  [14] 1/fy  [15] -cy/fy  [16] fx  [17] fy  [18] cx  [19] cy
+#define NID_GEO_STRIDE 20
+template <int NG>
+struct GeoTable {
+  double g[NG][NID_GEO_STRIDE];
+};
+
+// The reference's exact sequence for one pixel: CudaPoints3d.cu:20-28 then computeH.cu:152-158, from the
+// job's T_cw1, the pair's T_wc0 and intrinsics in global memory (rare path).
 template <bool PTS>
-__device__ __noinline__ void exact_uv(const Geo* g, double a0, double a1, double a2, unsigned id, double* out5) {
-  const Cam cam{g->fx, g->fy, g->cx, g->cy};
+__device__ __noinline__ void exact_uv(const double* __restrict__ T1g, const double* __restrict__ T0g,
+                                      const double* __restrict__ camg, double a0, double a1, double a2, unsigned id,
+                                      double* out5) {
+  const Cam cam{camg[0], camg[1], camg[2], camg[3]};
   double xw = a0, yw = a1, zw = a2;
-  if (!PTS) backproject(g->T0, cam, a0, (int)(id >> 16), (int)(id & 0xffffu), xw, yw, zw);
-  Pose P;
-#pragma unroll
-  for (int i = 0; i < 12; i++) P.m[i] = g->T1[i];
+  if (!PTS) backproject(T0g, cam, a0, (int)(id >> 16), (int)(id & 0xffffu), xw, yw, zw);
+  const Pose P = load_pose(T1g);
   double x1, y1, z1, u, v;
   warp_project(P, cam, xw, yw, zw, x1, y1, z1, u, v);
   out5[0] = x1; out5[1] = y1; out5[2] = z1; out5[3] = u; out5[4] = v;
@@ -181,10 +174,11 @@ __device__ __noinline__ void exact_uv(const Geo* g, double a0, double a1, double
 
 // Result of the shared front end of both passes.
 struct Px {
-  double x, y, z, rz;  // camera-frame point and 1/z
+  double xn, yn, rz;   // normalised camera-frame coordinates x/z, y/z and 1/z (pass 2)
   double dx, dy;       // fractional parts of (u, v)
   int ix, iy;
-  bool cost, jac;      // in-bounds for the cost (u+3<=cols) / for the Jacobian (u+3<=cols-1)
+  bool ok;             // in bounds for the cost: u>=0 && u+3<=cols && v>=0 && v+3<=rows
+  bool jac;            // ... and for the Jacobian (u+3<=cols-1)
   bool exact;          // (u, v) came from the reference's exact sequence
   bool fix;            // fast path could not decide: (u, v) within 2^-24 of an integer
 };
@@ -195,12 +189,13 @@ __device__ __forceinline__ bool frac_is_safe(double d) {
 }
 
 __device__ __forceinline__ void px_from_exact(const double* e, int rows, int cols, Px& r) {
-  r.x = e[0]; r.y = e[1]; r.z = e[2]; r.rz = 1.0 / e[2];  // types_six_dof_expmap.cpp:437
+  r.rz = 1.0 / e[2];  // types_six_dof_expmap.cpp:437
+  r.xn = e[0] * r.rz; r.yn = e[1] * r.rz;
   const double u = e[3], v = e[4];
-  r.cost = inb_cost(u, v, rows, cols);
+  r.ok = inb_cost(u, v, rows, cols);
   r.jac = inb_jac(u, v, rows, cols);
   r.ix = 0; r.iy = 0; r.dx = 0.0; r.dy = 0.0;
-  if (r.cost) {
+  if (r.ok) {
     r.ix = (int)u; r.iy = (int)v;
     r.dx = u - (double)r.ix; r.dy = v - (double)r.iy;
   }
@@ -208,24 +203,25 @@ __device__ __forceinline__ void px_from_exact(const double* e, int rows, int col
   r.fix = false;
 }
 
-// Branch-free fast path (so that the pixels of a group interleave). `valid` = not a padding slot.
-template <bool PTS>
-__device__ __forceinline__ void front(const Geo* g, int rows, int cols, double a0, double a1, double a2, unsigned id,
-                                      bool valid, Px& r) {
+// Branch-free fast path (so that the pixels of a batch interleave). g: the job's geometry entries.
+// P1: pass 1 (rows 0/1 of M pre-scaled, only u, v wanted); else pass 2 (xn, yn, 1/z kept).
+template <bool PTS, bool P1>
+__device__ __forceinline__ void front(const double* __restrict__ g, int rows, int cols, double a0, double a1, double a2,
+                                      unsigned id, Px& r) {
   double x1, y1, z1;
   if (PTS) {
-    x1 = fma(g->M[0], a0, fma(g->M[3], a1, fma(g->M[6], a2, g->M[9])));
-    y1 = fma(g->M[1], a0, fma(g->M[4], a1, fma(g->M[7], a2, g->M[10])));
-    z1 = fma(g->M[2], a0, fma(g->M[5], a1, fma(g->M[8], a2, g->M[11])));
+    x1 = fma(g[0], a0, fma(g[3], a1, fma(g[6], a2, g[9])));
+    y1 = fma(g[1], a0, fma(g[4], a1, fma(g[7], a2, g[10])));
+    z1 = fma(g[2], a0, fma(g[5], a1, fma(g[8], a2, g[11])));
   } else {
-    const double cxn = fma(u2d(id & 0xffffu), g->ifx, g->ncx);
-    const double cyn = fma(u2d(id >> 16), g->ify, g->ncy);
-    const double d0 = fma(g->M[0], cxn, fma(g->M[3], cyn, g->M[6]));
-    const double d1 = fma(g->M[1], cxn, fma(g->M[4], cyn, g->M[7]));
-    const double d2 = fma(g->M[2], cxn, fma(g->M[5], cyn, g->M[8]));
-    x1 = fma(a0, d0, g->M[9]);
-    y1 = fma(a0, d1, g->M[10]);
-    z1 = fma(a0, d2, g->M[11]);
+    const double cxn = fma(u2d(id & 0xffffu), g[12], g[13]);
+    const double cyn = fma(u2d(id >> 16), g[14], g[15]);
+    const double d0 = fma(g[0], cxn, fma(g[3], cyn, g[6]));
+    const double d1 = fma(g[1], cxn, fma(g[4], cyn, g[7]));
+    const double d2 = fma(g[2], cxn, fma(g[5], cyn, g[8]));
+    x1 = fma(a0, d0, g[9]);
+    y1 = fma(a0, d1, g[10]);
+    z1 = fma(a0, d2, g[11]);
   }
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z1));
@@ -233,35 +229,33 @@ __device__ __forceinline__ void front(const Geo* g, int rows, int cols, double a
   y = fma(y, e, y);
   e = fma(-z1, y, 1.0);
   y = fma(y, e, y);
-  const double u = fma(g->fx * x1, y, g->cx);
-  const double v = fma(g->fy * y1, y, g->cy);
-  r.x = x1; r.y = y1; r.z = z1; r.rz = y;
+  double u, v;
+  if (P1) {
+    u = fma(x1, y, g[18]);
+    v = fma(y1, y, g[19]);
+  } else {
+    r.xn = x1 * y; r.yn = y1 * y; r.rz = y;
+    u = fma(g[16], r.xn, g[18]);
+    v = fma(g[17], r.yn, g[19]);
+  }
   r.exact = false;
   const int ix = __double2int_rz(u), iy = __double2int_rz(v);  // NaN -> 0, saturating
-  // u <= -1 or u >= cols+1 (same for v) is out of bounds whatever the last bits are
-  const bool inr = valid && (unsigned)ix <= (unsigned)cols && (unsigned)iy <= (unsigned)rows;
   const double dx = u - u2d((unsigned)ix), dy = v - u2d((unsigned)iy);
+  // u <= -1 or u >= cols-2 (same for v) is out of bounds whatever the last bits are; padding slots never count
+  const bool inr = id != NID_PAD_ID && (unsigned)ix <= (unsigned)(cols - 3) && (unsigned)iy <= (unsigned)(rows - 3);
   const bool safe = frac_is_safe(dx) && frac_is_safe(dy);
   // with u, v not within 2^-24 of an integer the integer comparisons decide exactly like
   // `u>=0 && u+3<=cols && v>=0 && v+3<=rows` (types_six_dof_expmap.cpp:565; :433 with cols-1)
-  r.cost = inr && safe && ix <= cols - 4 && iy <= rows - 4;
-  r.jac = inr && safe && ix <= cols - 5 && iy <= rows - 4;
+  r.ok = inr && safe && ix <= cols - 4 && iy <= rows - 4;
+  r.jac = r.ok && ix <= cols - 5;
   r.fix = inr && !safe;
-  r.ix = r.cost ? ix : 0; r.iy = r.cost ? iy : 0;
+  const bool keep = P1 ? r.ok : r.jac;
+  r.ix = keep ? ix : 0; r.iy = keep ? iy : 0;
   r.dx = dx; r.dy = dy;
 }
 
-// saturated plateau: the clamp `>= 255 -> 254.999` (types_six_dof_expmap.cpp:572) depends on the last bit
-// of the bilinear weights, so the fractions must be the reference's own
-template <bool PTS>
-__device__ __forceinline__ void make_exact(const Geo* g, int rows, int cols, double a0, double a1, double a2, unsigned id,
-                                           Px& r) {
-  double ex[5];
-  exact_uv<PTS>(g, a0, a1, a2, id, ex);
-  px_from_exact(ex, rows, cols, r);
-}
-
-// types_six_dof_expmap.h:321-326 in the reference's term order, without contraction
+// types_six_dof_expmap.h:321-326 in the reference's term order, without contraction (exact-path pixels:
+// on a saturated plateau the `>= 255` clamp that follows sees the last bit of this sum)
 __device__ __forceinline__ double bilinear_ref(double dx, double dy, unsigned p00, unsigned p01, unsigned p10, unsigned p11) {
   const double dxdy = __dmul_rn(dx, dy);
   const double w00 = __dadd_rn(__dsub_rn(__dsub_rn(1.0, dx), dy), dxdy);
@@ -271,13 +265,19 @@ __device__ __forceinline__ double bilinear_ref(double dx, double dy, unsigned p0
   return __dadd_rn(a, __dmul_rn(w00, u2d(p00)));
 }
 
-// gather component order for the footprint with top-left texel (ix, iy):
-//   .w = (ix, iy)  .z = (ix+1, iy)  .x = (ix, iy+1)  .y = (ix+1, iy+1)
-__device__ __forceinline__ uchar4 gather_u8(cudaTextureObject_t tex, int ix, int iy) {
-  return tex2Dgather<uchar4>(tex, (float)ix + 1.0f, (float)iy + 1.0f, 0);
+// Same interpolant for fast-path pixels, as p00 + dx d0 + dy ((p10 + dx d1) - (p00 + dx d0)): 4 fp64 operations.
+// It differs from bilinear_ref by rounding only, which no decision of a fast-path pixel depends on: the spline
+// weights are continuous across span boundaries, an all-zero footprint gives exactly 0 in both forms, and
+// saturated footprints take the exact path.
+__device__ __forceinline__ double bilinear_fast(double dx, double dy, double p00, double d0, double p10, double d1) {
+  const double a = fma(dx, d0, p00), b = fma(dx, d1, p10);
+  return fma(dy, b - a, a);
 }
+
+// pass-2 gather: component order for the footprint with top-left texel (ix, iy):
+//   .w = (ix, iy)  .z = (ix+1, iy)  .x = (ix, iy+1)  .y = (ix+1, iy+1)
 __device__ __forceinline__ uint4 gather_u32(cudaTextureObject_t tex, int ix, int iy) {
-  return tex2Dgather<uint4>(tex, (float)ix + 1.0f, (float)iy + 1.0f, 0);
+  return tex2Dgather<uint4>(tex, (float)(ix + 1), (float)(iy + 1), 0);
 }
 
 // Cubic B-spline basis on span k, f = ub - k. Interior spans of the clamped uniform knot vector
@@ -323,36 +323,69 @@ struct Group {
   }
 };
 
-// Pass 1 on W pixels of a group at once: projection (branch-free), W gathers in flight, spline weights,
-// then the accumulations in pixel order into the lane's private row h[b * 256].
+// what the rare exact paths need from global memory
+struct ExactSrc {
+  const double* T1;   // the job's T_cw1, column-major 4x4
+  const double* T0;   // the pair's T_wc0
+  const double* cam;  // fx fy cx cy
+};
+
+template <bool PTS>
+__device__ __forceinline__ void make_exact(const ExactSrc& xs, int rows, int cols, double a0, double a1, double a2, unsigned id,
+                                           Px& r) {
+  double ex[5];
+  exact_uv<PTS>(xs.T1, xs.T0, xs.cam, a0, a1, a2, id, ex);
+  px_from_exact(ex, rows, cols, r);
+}
+
+// Pass 1 on W pixels of a group at once: projection (branch-free), W footprint loads in flight, spline
+// weights, then the accumulations in pixel order into the lane's private row h[b * 256].
+// fp: the pair's footprint-packed target image, fp[y*cols + x] = I(x,y) | I(x+1,y)<<8 | I(x,y+1)<<16 | I(x+1,y+1)<<24.
 template <bool PTS, int W>
-__device__ __forceinline__ void hist_pixels(const EvalParams& p, const Geo* g, const Group<PTS>& G, int j0,
-                                            cudaTextureObject_t tex, const double* __restrict__ coef, double s, int NS,
-                                            double* __restrict__ h) {
+__device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const ExactSrc& xs, int rows, int cols,
+                                            const Group<PTS>& G, int j0, const unsigned* __restrict__ fp,
+                                            const double* __restrict__ coef, double s, int NS, double* __restrict__ h) {
   Px r[W];
-  bool anyfix = false;
+  bool anyexact = false;
 #pragma unroll
   for (int j = 0; j < W; j++) {
-    front<PTS>(g, p.rows, p.cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], G.id[j0 + j] != NID_PAD_ID, r[j]);
-    anyfix |= r[j].fix;
+    front<PTS, true>(g, rows, cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
+    anyexact |= r[j].fix;
   }
-  if (anyfix) {
+  if (anyexact) {
 #pragma unroll
     for (int j = 0; j < W; j++)
-      if (r[j].fix) make_exact<PTS>(g, p.rows, p.cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
+      if (r[j].fix) make_exact<PTS>(xs, rows, cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
   }
-  uchar4 t[W];
+  unsigned t[W];
 #pragma unroll
-  for (int j = 0; j < W; j++) t[j] = gather_u8(tex, r[j].ix, r[j].iy);
+  for (int j = 0; j < W; j++) t[j] = __ldg(fp + r[j].iy * cols + r[j].ix);
   bool sat = false;
 #pragma unroll
-  for (int j = 0; j < W; j++) sat |= r[j].cost && !r[j].exact && (t[j].x & t[j].y & t[j].z & t[j].w) == 255;
+  for (int j = 0; j < W; j++) sat |= r[j].ok && !r[j].exact && t[j] == 0xffffffffu;
   if (sat) {
+    // saturated plateau: the clamp `>= 255 -> 254.999` (types_six_dof_expmap.cpp:572) depends on the last bit
+    // of the bilinear weights, so the fractions must be the reference's own
+    anyexact = true;
 #pragma unroll
     for (int j = 0; j < W; j++)
-      if (r[j].cost && !r[j].exact && (t[j].x & t[j].y & t[j].z & t[j].w) == 255) {
-        make_exact<PTS>(g, p.rows, p.cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
-        t[j] = gather_u8(tex, r[j].ix, r[j].iy);
+      if (r[j].ok && !r[j].exact && t[j] == 0xffffffffu) {
+        make_exact<PTS>(xs, rows, cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
+        t[j] = __ldg(fp + r[j].iy * cols + r[j].ix);
+      }
+  }
+  double ic[W];
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    const int p00 = t[j] & 0xffu, p01 = (t[j] >> 8) & 0xffu, p10 = (t[j] >> 16) & 0xffu, p11 = t[j] >> 24;
+    ic[j] = bilinear_fast(r[j].dx, r[j].dy, u2d(p00), i2d_small(p01 - p00), u2d(p10), i2d_small(p11 - p10));
+  }
+  if (anyexact) {
+#pragma unroll
+    for (int j = 0; j < W; j++)
+      if (r[j].exact) {
+        const unsigned p00 = t[j] & 0xffu, p01 = (t[j] >> 8) & 0xffu, p10 = (t[j] >> 16) & 0xffu, p11 = t[j] >> 24;
+        ic[j] = clamp_intensity(bilinear_ref(r[j].dx, r[j].dy, p00, p01, p10, p11));
       }
   }
   double wt[W][4], fr[W];
@@ -360,21 +393,20 @@ __device__ __forceinline__ void hist_pixels(const EvalParams& p, const Geo* g, c
   bool edge = false;
 #pragma unroll
   for (int j = 0; j < W; j++) {
-    const double ic = clamp_intensity(bilinear_ref(r[j].dx, r[j].dy, t[j].w, t[j].z, t[j].x, t[j].y));
-    const double ub = ic * s;
-    kt[j] = r[j].cost ? (int)ub : 0;  // 0 <= ub < NS
+    const double ub = ic[j] * s;
+    kt[j] = r[j].ok ? min((int)ub, NS - 1) : 0;  // 0 <= ub <= NS (== NS only by rounding)
     fr[j] = ub - u2d((unsigned)kt[j]);
     bspline4_uniform(fr[j], wt[j]);
-    edge |= r[j].cost && !span_is_uniform(kt[j], NS);
+    edge |= r[j].ok && !span_is_uniform(kt[j], NS);
   }
   if (edge) {
 #pragma unroll
     for (int j = 0; j < W; j++)
-      if (r[j].cost && !span_is_uniform(kt[j], NS)) bspline4_edge(coef, kt[j], fr[j], wt[j]);
+      if (r[j].ok && !span_is_uniform(kt[j], NS)) bspline4_edge(coef, kt[j], fr[j], wt[j]);
   }
 #pragma unroll
   for (int j = 0; j < W; j++) {
-    if (!r[j].cost) continue;
+    if (!r[j].ok) continue;
     double* hk = h + kt[j] * 256;
 #pragma unroll
     for (int n = 0; n < 4; n++) hk[n * 256] += wt[j][n];
@@ -382,20 +414,21 @@ __device__ __forceinline__ void hist_pixels(const EvalParams& p, const Geo* g, c
 }
 
 // Pass 1: per task the un-weighted target soft histogram h[B] of its pixels.
-// grid (jobs, ceil(max_slices/8)), 256 threads; shared: rows [B][256] + spline table + geometry. The job
+// grid (jobs of this launch, ceil(max_slices/8)), 256 threads; shared: rows [B][256] + spline table. The job
 // index is the fast grid dimension and slices are ordered longest first, so the long CTAs of every job
-// start first and the short ones fill the tail.
-template <bool PTS, int W>
-__global__ void __launch_bounds__(256, W == 1 ? 4 : (W == 2 ? 3 : 2)) k_hist_sell(EvalParams p) {
+// start first and the short ones fill the tail. The next group's pixels are loaded before the current
+// group is processed.
+template <bool PTS, int W, int NG>
+__global__ void __launch_bounds__(256, W == 1 ? 4 : (W == 2 ? 3 : 2))
+k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
   extern __shared__ double sm[];
-  __shared__ Geo geo;
   const int B = p.bins, NS = B - 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int job = blockIdx.x + p.job0;
   const int pair = p.job_pair[job];
+  const double* g = gt.g[blockIdx.x];
   double* coef = sm + (size_t)B * 256;
   for (int i = threadIdx.x; i < NS * 16; i += blockDim.x) coef[i] = p.bs_coef[i];
-  build_geo<PTS>(p, job, pair, &geo);
   __syncthreads();
   const int slice = blockIdx.y * 8 + warp;
   if (slice >= p.nslices[pair]) return;
@@ -409,13 +442,17 @@ __global__ void __launch_bounds__(256, W == 1 ? 4 : (W == 2 ? 3 : 2)) k_hist_sel
   const double* q1 = PTS ? p.sd1 + sbase : nullptr;
   const double* q2 = PTS ? p.sd2 + sbase : nullptr;
   const unsigned* qi = p.sid + sbase;
-  const cudaTextureObject_t tex = p.tex[pair];
+  const unsigned* fp = p.fp1 + (size_t)pair * p.N;
+  const ExactSrc xs{p.poses + 16 * job, p.Twc0 + 16 * pair, p.cam + 4 * pair};
   const double s = (double)NS / 255.0;
+  Group<PTS> G;
+  G.load(q0, q1, q2, qi, 0);
   for (int gi = 0; gi < ngroups; gi++) {
-    Group<PTS> G;
-    G.load(q0, q1, q2, qi, (size_t)gi * 128);
+    Group<PTS> Gn = G;
+    if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
 #pragma unroll
-    for (int j0 = 0; j0 < 4; j0 += W) hist_pixels<PTS, W>(p, &geo, G, j0, tex, coef, s, NS, h);
+    for (int j0 = 0; j0 < 4; j0 += W) hist_pixels<PTS, W>(g, xs, p.rows, p.cols, G, j0, fp, coef, s, NS, h);
+    G = Gn;
   }
   if (task >= 0) {
     double* out = p.G + ((size_t)job * p.g_stride + task) * B;
@@ -546,66 +583,67 @@ __device__ __forceinline__ double biased9_to_double(unsigned v) {  // v in [0, 5
 // (types_six_dof_expmap.cpp:562-575), the second projection fx*(x/z)+cx for the Jacobian bounds test and the
 // four gradient samples (:407-435). Taken when (u, v) is within 2^-24 of an integer, on saturated plateaus,
 // and in the first image row / column, where (int)(u-1) truncates towards zero so that the five bilinear
-// samples do not share their fractions. out: {x, y, z, 1/z, ic, 2 gx, 2 gy}; returns the Jacobian validity.
+// samples do not share their fractions. out: {x/z, y/z, 1/z, clamped ic, 2 gx, 2 gy}; returns the Jacobian validity.
 template <bool PTS>
-__device__ __noinline__ bool jac_pixel_literal(const Geo* g, int rows, int cols, const uint8_t* __restrict__ im,
-                                               double a0, double a1, double a2, unsigned id, double* out7) {
+__device__ __noinline__ bool jac_pixel_literal(const double* __restrict__ T1g, const double* __restrict__ T0g,
+                                               const double* __restrict__ camg, int rows, int cols,
+                                               const uint8_t* __restrict__ im, double a0, double a1, double a2, unsigned id,
+                                               double* out6) {
   double e[5];
-  exact_uv<PTS>(g, a0, a1, a2, id, e);
-  const Cam cam{g->fx, g->fy, g->cx, g->cy};
+  exact_uv<PTS>(T1g, T0g, camg, a0, a1, a2, id, e);
+  const Cam cam{camg[0], camg[1], camg[2], camg[3]};
   const double u = e[3], v = e[4];
   double u2, v2;
   project_jac(cam, e[0], e[1], e[2], u2, v2);
   if (!inb_cost(u, v, rows, cols) || !inb_jac(u2, v2, rows, cols)) return false;
-  out7[0] = e[0]; out7[1] = e[1]; out7[2] = e[2]; out7[3] = 1.0 / e[2];
-  out7[4] = interp_u8(im, cols, u, v);
-  out7[5] = interp_u8(im, cols, u2 + 1.0, v2) - interp_u8(im, cols, u2 - 1.0, v2);
-  out7[6] = interp_u8(im, cols, u2, v2 + 1.0) - interp_u8(im, cols, u2, v2 - 1.0);
+  const double iz = 1.0 / e[2];
+  out6[0] = e[0] * iz; out6[1] = e[1] * iz; out6[2] = iz;
+  out6[3] = clamp_intensity(interp_u8(im, cols, u, v));
+  out6[4] = interp_u8(im, cols, u2 + 1.0, v2) - interp_u8(im, cols, u2 - 1.0, v2);
+  out6[5] = interp_u8(im, cols, u2, v2 + 1.0) - interp_u8(im, cols, u2, v2 - 1.0);
   return true;
 }
 
 // Pass 2 on W pixels of a group at once; acc[6] are the lane's Jacobian partial sums.
 template <bool PTS, int W>
-__device__ __forceinline__ void jac_pixels(const EvalParams& p, const Geo* g, const Group<PTS>& G, int j0,
-                                           cudaTextureObject_t tex2, const uint8_t* __restrict__ im1, double s, double hfx,
-                                           double hfy, const double* __restrict__ wq, double acc[6]) {
+__device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const ExactSrc& xs, int rows, int cols,
+                                           const Group<PTS>& G, int j0, cudaTextureObject_t tex2,
+                                           const uint8_t* __restrict__ im1, double s, int NS, double hfx, double hfy,
+                                           const double* __restrict__ wq, double acc[6]) {
   Px r[W];
 #pragma unroll
-  for (int j = 0; j < W; j++)
-    front<PTS>(g, p.rows, p.cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], G.id[j0 + j] != NID_PAD_ID, r[j]);
+  for (int j = 0; j < W; j++) front<PTS, false>(g, rows, cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
   uint4 t[W];
 #pragma unroll
-  for (int j = 0; j < W; j++) t[j] = gather_u32(tex2, r[j].jac ? r[j].ix : 0, r[j].jac ? r[j].iy : 0);
+  for (int j = 0; j < W; j++) t[j] = gather_u32(tex2, r[j].ix, r[j].iy);
 #pragma unroll
   for (int j = 0; j < W; j++) {
-    double ic = bilinear_ref(r[j].dx, r[j].dy, t[j].w & 0xffu, t[j].z & 0xffu, t[j].x & 0xffu, t[j].y & 0xffu);
-    const double w11 = r[j].dx * r[j].dy, w10 = r[j].dy - w11, w01 = r[j].dx - w11, w00 = 1.0 - r[j].dx - r[j].dy + w11;
-    double gx2 = fma(w11, biased9_to_double((t[j].y >> 8) & 0x1ffu),
-                     fma(w10, biased9_to_double((t[j].x >> 8) & 0x1ffu),
-                         fma(w01, biased9_to_double((t[j].z >> 8) & 0x1ffu), w00 * biased9_to_double((t[j].w >> 8) & 0x1ffu))));
-    double gy2 = fma(w11, biased9_to_double(t[j].y >> 17),
-                     fma(w10, biased9_to_double(t[j].x >> 17),
-                         fma(w01, biased9_to_double(t[j].z >> 17), w00 * biased9_to_double(t[j].w >> 17))));
+    // texel = I | (Gx+256) << 8 | (Gy+256) << 17; the biases cancel in the differences
+    const int i00 = t[j].w & 0xffu, i01 = t[j].z & 0xffu, i10 = t[j].x & 0xffu, i11 = t[j].y & 0xffu;
+    const int x00 = (t[j].w >> 8) & 0x1ffu, x01 = (t[j].z >> 8) & 0x1ffu, x10 = (t[j].x >> 8) & 0x1ffu, x11 = (t[j].y >> 8) & 0x1ffu;
+    const int y00 = t[j].w >> 17, y01 = t[j].z >> 17, y10 = t[j].x >> 17, y11 = t[j].y >> 17;
+    double ic = bilinear_fast(r[j].dx, r[j].dy, u2d(i00), i2d_small(i01 - i00), u2d(i10), i2d_small(i11 - i10));
+    double gx2 = bilinear_fast(r[j].dx, r[j].dy, biased9_to_double(x00), i2d_small(x01 - x00), biased9_to_double(x10), i2d_small(x11 - x10));
+    double gy2 = bilinear_fast(r[j].dx, r[j].dy, biased9_to_double(y00), i2d_small(y01 - y00), biased9_to_double(y10), i2d_small(y11 - y10));
     // rare: undecided by the fast path, saturated plateau, or first image row / column
-    const bool sat = (t[j].x & t[j].y & t[j].z & t[j].w & 0xffu) == 0xffu;
+    const bool sat = (i00 & i01 & i10 & i11) == 0xff;
     if (r[j].fix || (r[j].jac && (sat || r[j].ix < 1 || r[j].iy < 1))) {
-      double o7[7];
-      r[j].jac = jac_pixel_literal<PTS>(g, p.rows, p.cols, im1, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], o7);
+      double o6[6];
+      r[j].jac = jac_pixel_literal<PTS>(xs.T1, xs.T0, xs.cam, rows, cols, im1, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], o6);
       if (r[j].jac) {
-        r[j].x = o7[0]; r[j].y = o7[1]; r[j].z = o7[2]; r[j].rz = o7[3];
-        ic = o7[4]; gx2 = o7[5]; gy2 = o7[6];
+        r[j].xn = o6[0]; r[j].yn = o6[1]; r[j].rz = o6[2];
+        ic = o6[3]; gx2 = o6[4]; gy2 = o6[5];
       }
     }
-    ic = clamp_intensity(ic);
     const double ub = r[j].jac ? ic * s : 0.0;
-    const int k = (int)ub;
+    const int k = min((int)ub, NS - 1);  // 0 <= ub <= NS (== NS only by rounding)
     const double f = ub - u2d((unsigned)k);
     const double* q = wq + 3 * k * 128;
     double ci = fma(f, fma(f, q[256], q[128]), q[0]);
     if (ub == 0.0) ci = 0.0;  // the reference's BsplineDer quirk
     if (!r[j].jac) continue;  // (a padding slot may carry z = 0 and non-finite coordinates)
     // d(u,v)/d(xi), types_six_dof_expmap.cpp:438-450, in normalised coordinates xn = x/z, yn = y/z
-    const double iz = r[j].rz, xn = r[j].x * iz, yn = r[j].y * iz;
+    const double iz = r[j].rz, xn = r[j].xn, yn = r[j].yn;
     const double a = ci * gx2 * hfx, b = ci * gy2 * hfy;
     const double xy = xn * yn;
     acc[0] = fma(-b, fma(yn, yn, 1.0), fma(-a, xy, acc[0]));
@@ -619,15 +657,15 @@ __device__ __forceinline__ void jac_pixels(const EvalParams& p, const Geo* g, co
 }
 
 // grid (jobs, ceil(max_slices/4)), 128 threads; shared: the lanes' quadratic rows [3*NS][128].
-template <bool PTS, int W>
-__global__ void __launch_bounds__(128, W == 1 ? 5 : 4) k_jac_sell(EvalParams p) {
+template <bool PTS, int W, int NG>
+__global__ void __launch_bounds__(128, W == 1 ? 5 : 4)
+k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
   extern __shared__ double sm[];
-  __shared__ Geo geo;
   const int B = p.bins, NS = B - 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int job = blockIdx.x + p.job0;
   const int pair = p.job_pair[job];
-  build_geo<PTS>(p, job, pair, &geo);
+  const double* g = gt.g[blockIdx.x];
   {
     // derivative of the per-span basis polynomials: dco[k][j][m] = (j+1) * coef[k][m][j+1]
     double* dco = sm + 3 * NS * 128 + 4 * (B * (B + 1) + B);
@@ -695,14 +733,18 @@ __global__ void __launch_bounds__(128, W == 1 ? 5 : 4) k_jac_sell(EvalParams p) 
   const unsigned* qi = p.sid + sbase;
   const cudaTextureObject_t tex2 = p.tex2[pair];
   const uint8_t* im1 = p.im1 + (size_t)pair * p.N;
+  const ExactSrc xs{p.poses + 16 * job, p.Twc0 + 16 * pair, p.cam + 4 * pair};
   const double s = (double)NS / 255.0;
-  const double hfx = 0.5 * geo.fx, hfy = 0.5 * geo.fy;  // the /2 of the central differences folded in
+  const double hfx = 0.5 * g[16], hfy = 0.5 * g[17];  // the /2 of the central differences folded in
   double acc[6] = {0, 0, 0, 0, 0, 0};
+  Group<PTS> G;
+  G.load(q0, q1, q2, qi, 0);
   for (int gi = 0; gi < ngroups; gi++) {
-    Group<PTS> G;
-    G.load(q0, q1, q2, qi, (size_t)gi * 128);
+    Group<PTS> Gn = G;
+    if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
 #pragma unroll
-    for (int j0 = 0; j0 < 4; j0 += W) jac_pixels<PTS, W>(p, &geo, G, j0, tex2, im1, s, hfx, hfy, wq, acc);
+    for (int j0 = 0; j0 < 4; j0 += W) jac_pixels<PTS, W>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, acc);
+    G = Gn;
   }
   // one partial per slice: fixed-order butterfly over the 32 lanes (lanes without a task hold zeros)
 #pragma unroll
@@ -779,6 +821,14 @@ int launch_scatter(nid_ctx* c, int pair) {
   return NID_OK;
 }
 
+int launch_pack_fp(nid_ctx* c, int pair) {
+  int g = (c->N + 255) / 256;
+  if (g > c->sm_count * 8) g = c->sm_count * 8;
+  k_pack_fp<<<g, 256, 0, c->stream>>>(c->rows, c->cols, c->im1 + (size_t)pair * c->N, c->fp1 + (size_t)pair * c->N);
+  NID_LAUNCH_CHECK(c, "k_pack_fp");
+  return NID_OK;
+}
+
 int launch_pack_tex(nid_ctx* c, int pair, unsigned* d_out) {
   int g = (c->N + 255) / 256;
   if (g > c->sm_count * 8) g = c->sm_count * 8;
@@ -794,23 +844,80 @@ size_t jac_sell_smem(const nid_ctx* c) {
 }
 size_t assemble_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)5 * c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins + 1024); }
 
-template <bool PTS>
-static void launch_hist_w(nid_ctx* c, const EvalParams& p, int ns, int n_jobs) {
-  const dim3 grid(n_jobs, (ns + 7) / 8);
-  const size_t sm = hist_sell_smem(c);
-  switch (c->opt_ilp_hist) {
-    case 1: k_hist_sell<PTS, 1><<<grid, 256, sm, c->stream>>>(p); break;
-    case 2: k_hist_sell<PTS, 2><<<grid, 256, sm, c->stream>>>(p); break;
-    default: k_hist_sell<PTS, 4><<<grid, 256, sm, c->stream>>>(p); break;
+// Host side of the geometry table: job (first + i) -> gt.g[i] from the staged poses (pinned mirror), the pair's
+// T_wc0 and intrinsics. pass1: rows 0 and 1 of M pre-multiplied by fx, fy.
+template <int NG>
+static void fill_geo(const nid_ctx* c, GeoTable<NG>& gt, int first, int n, bool pass1) {
+  for (int i = 0; i < n; i++) {
+    const double* T1 = c->h_poses + 16 * (size_t)(first + i);
+    const int pair = c->h_job_pair[first + i];
+    const double* T0 = c->h_Twc0.data() + 16 * (size_t)pair;
+    const double* cam = c->h_cam.data() + 4 * (size_t)pair;
+    double* g = gt.g[i];
+    for (int col = 0; col < 4; col++)
+      for (int r = 0; r < 3; r++) {
+        double m;
+        if (c->sell_points) m = T1[4 * col + r];
+        else {
+          m = T1[r] * T0[4 * col] + T1[4 + r] * T0[4 * col + 1] + T1[8 + r] * T0[4 * col + 2];
+          if (col == 3) m += T1[12 + r];
+        }
+        if (pass1 && r < 2) m *= cam[r];
+        g[3 * col + r] = m;
+      }
+    g[12] = 1.0 / cam[0]; g[13] = -cam[2] / cam[0]; g[14] = 1.0 / cam[1]; g[15] = -cam[3] / cam[1];
+    g[16] = cam[0]; g[17] = cam[1]; g[18] = cam[2]; g[19] = cam[3];
   }
 }
-template <bool PTS>
-static void launch_jac_w(nid_ctx* c, const EvalParams& p, int ns, int n_jobs) {
-  const dim3 grid(n_jobs, (ns + 3) / 4);
+
+template <bool PTS, int NG>
+static void launch_hist_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
+  const size_t sm = hist_sell_smem(c);
+  for (int s0 = 0; s0 < n_jobs; s0 += NG) {
+    const int n = std::min(NG, n_jobs - s0);
+    GeoTable<NG> gt;
+    fill_geo(c, gt, job0 + s0, n, true);
+    EvalParams q = p;
+    q.job0 = job0 + s0;
+    const dim3 grid(n, (ns + 7) / 8);
+    if (c->opt_ilp_hist <= 2) k_hist_sell<PTS, 2, NG><<<grid, 256, sm, c->stream>>>(q, gt);
+    else k_hist_sell<PTS, 4, NG><<<grid, 256, sm, c->stream>>>(q, gt);
+    c->launches++;
+  }
+}
+template <bool PTS, int NG>
+static void launch_jac_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
   const size_t sm = jac_sell_smem(c);
-  switch (c->opt_ilp_jac) {
-    case 1: k_jac_sell<PTS, 1><<<grid, 128, sm, c->stream>>>(p); break;
-    default: k_jac_sell<PTS, 2><<<grid, 128, sm, c->stream>>>(p); break;
+  for (int s0 = 0; s0 < n_jobs; s0 += NG) {
+    const int n = std::min(NG, n_jobs - s0);
+    GeoTable<NG> gt;
+    fill_geo(c, gt, job0 + s0, n, false);
+    EvalParams q = p;
+    q.job0 = job0 + s0;
+    const dim3 grid(n, (ns + 3) / 4);
+    if (c->opt_ilp_jac <= 1) k_jac_sell<PTS, 1, NG><<<grid, 128, sm, c->stream>>>(q, gt);
+    else k_jac_sell<PTS, 2, NG><<<grid, 128, sm, c->stream>>>(q, gt);
+    c->launches++;
+  }
+}
+#define NID_GEO_SMALL 8
+#define NID_GEO_LARGE 96
+static void launch_hist_w(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
+  if (c->sell_points) {
+    if (n_jobs <= NID_GEO_SMALL) launch_hist_chunks<true, NID_GEO_SMALL>(c, p, ns, job0, n_jobs);
+    else launch_hist_chunks<true, NID_GEO_LARGE>(c, p, ns, job0, n_jobs);
+  } else {
+    if (n_jobs <= NID_GEO_SMALL) launch_hist_chunks<false, NID_GEO_SMALL>(c, p, ns, job0, n_jobs);
+    else launch_hist_chunks<false, NID_GEO_LARGE>(c, p, ns, job0, n_jobs);
+  }
+}
+static void launch_jac_w(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
+  if (c->sell_points) {
+    if (n_jobs <= NID_GEO_SMALL) launch_jac_chunks<true, NID_GEO_SMALL>(c, p, ns, job0, n_jobs);
+    else launch_jac_chunks<true, NID_GEO_LARGE>(c, p, ns, job0, n_jobs);
+  } else {
+    if (n_jobs <= NID_GEO_SMALL) launch_jac_chunks<false, NID_GEO_SMALL>(c, p, ns, job0, n_jobs);
+    else launch_jac_chunks<false, NID_GEO_LARGE>(c, p, ns, job0, n_jobs);
   }
 }
 
@@ -818,9 +925,9 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
   EvalParams p = make_params(c, n_jobs_total);
   p.job0 = job0;
   const int ns = c->max_nslices_prepared;
-  const bool pts = c->sell_points;
   ktime_mark(c, 0);
-  if (pts) launch_hist_w<true>(c, p, ns, n_jobs); else launch_hist_w<false>(c, p, ns, n_jobs);
+  launch_hist_w(c, p, ns, job0, n_jobs);
+  c->launches--;
   NID_LAUNCH_CHECK(c, "k_hist_sell");
   ktime_mark(c, 1);
   k_class_sum<<<dim3((NID_NCLS * c->bins + 255) / 256, c->ncell, n_jobs), 256, 0, c->stream>>>(p);
@@ -829,7 +936,8 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
   NID_LAUNCH_CHECK(c, "k_assemble");
   ktime_mark(c, 2);
   if (want_jac) {
-    if (pts) launch_jac_w<true>(c, p, ns, n_jobs); else launch_jac_w<false>(c, p, ns, n_jobs);
+    launch_jac_w(c, p, ns, job0, n_jobs);
+    c->launches--;
     NID_LAUNCH_CHECK(c, "k_jac_sell");
     ktime_mark(c, 3);
     const int warps = n_jobs * c->ncell;
@@ -847,20 +955,20 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
 
 int sorted_init(nid_ctx* c) {
   cudaError_t e;
-  if (c->bins > NID_SORTED_MAX_BINS) return NID_OK;  // natural-order kernels only
+  if (c->bins > NID_SORTED_MAX_BINS || c->bins < 8) return NID_OK;  // natural-order kernels only
 #define NID_SMEM_ATTR(k, bytes)                                                                     \
   e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));            \
   if (e != cudaSuccess) return check_cuda(e, "smem attr " #k);
-  NID_SMEM_ATTR((k_hist_sell<true, 1>), hist_sell_smem(c));
-  NID_SMEM_ATTR((k_hist_sell<false, 1>), hist_sell_smem(c));
-  NID_SMEM_ATTR((k_hist_sell<true, 2>), hist_sell_smem(c));
-  NID_SMEM_ATTR((k_hist_sell<false, 2>), hist_sell_smem(c));
-  NID_SMEM_ATTR((k_hist_sell<true, 4>), hist_sell_smem(c));
-  NID_SMEM_ATTR((k_hist_sell<false, 4>), hist_sell_smem(c));
-  NID_SMEM_ATTR((k_jac_sell<true, 1>), jac_sell_smem(c));
-  NID_SMEM_ATTR((k_jac_sell<false, 1>), jac_sell_smem(c));
-  NID_SMEM_ATTR((k_jac_sell<true, 2>), jac_sell_smem(c));
-  NID_SMEM_ATTR((k_jac_sell<false, 2>), jac_sell_smem(c));
+#define NID_SMEM_ATTR_PX(PTS, NG)                                        \
+  NID_SMEM_ATTR((k_hist_sell<PTS, 2, NG>), hist_sell_smem(c));           \
+  NID_SMEM_ATTR((k_hist_sell<PTS, 4, NG>), hist_sell_smem(c));           \
+  NID_SMEM_ATTR((k_jac_sell<PTS, 1, NG>), jac_sell_smem(c));             \
+  NID_SMEM_ATTR((k_jac_sell<PTS, 2, NG>), jac_sell_smem(c));
+  NID_SMEM_ATTR_PX(true, NID_GEO_SMALL)
+  NID_SMEM_ATTR_PX(false, NID_GEO_SMALL)
+  NID_SMEM_ATTR_PX(true, NID_GEO_LARGE)
+  NID_SMEM_ATTR_PX(false, NID_GEO_LARGE)
+#undef NID_SMEM_ATTR_PX
   NID_SMEM_ATTR(k_assemble, assemble_smem(c));
 #undef NID_SMEM_ATTR
   return NID_OK;
