@@ -418,8 +418,20 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
 // index is the fast grid dimension and slices are ordered longest first, so the long CTAs of every job
 // start first and the short ones fill the tail. The next group's pixels are loaded before the current
 // group is processed.
+#ifndef NID_HIST_MINB4
+#define NID_HIST_MINB4 2
+#endif
+#ifndef NID_HIST_MINB2
+#define NID_HIST_MINB2 3
+#endif
+#ifndef NID_JAC_MINB2
+#define NID_JAC_MINB2 4
+#endif
+#ifndef NID_JAC_MINB1
+#define NID_JAC_MINB1 5
+#endif
 template <bool PTS, int W, int NG>
-__global__ void __launch_bounds__(256, W == 1 ? 4 : (W == 2 ? 3 : 2))
+__global__ void __launch_bounds__(256, W == 2 ? NID_HIST_MINB2 : NID_HIST_MINB4)
 k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
   extern __shared__ double sm[];
   const int B = p.bins, NS = B - 3;
@@ -658,7 +670,7 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
 
 // grid (jobs, ceil(max_slices/4)), 128 threads; shared: the lanes' quadratic rows [3*NS][128].
 template <bool PTS, int W, int NG>
-__global__ void __launch_bounds__(128, W == 1 ? 5 : 4)
+__global__ void __launch_bounds__(128, W == 1 ? NID_JAC_MINB1 : NID_JAC_MINB2)
 k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
   extern __shared__ double sm[];
   const int B = p.bins, NS = B - 3;
