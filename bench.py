@@ -55,7 +55,7 @@ class ClockSampler:
                 self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -179,7 +179,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=96, help="pair slots per rank (96 x 8.3 MB of inputs >> L2)")
