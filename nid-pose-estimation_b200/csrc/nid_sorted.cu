@@ -430,6 +430,9 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
 #ifndef NID_JAC_MINB1
 #define NID_JAC_MINB1 5
 #endif
+#ifndef NID_JAC_MINB4
+#define NID_JAC_MINB4 3
+#endif
 template <bool PTS, int W, int NG>
 __global__ void __launch_bounds__(256, W == 2 ? NID_HIST_MINB2 : NID_HIST_MINB4)
 k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
@@ -670,7 +673,7 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
 
 // grid (jobs, ceil(max_slices/4)), 128 threads; shared: the lanes' quadratic rows [3*NS][128].
 template <bool PTS, int W, int NG>
-__global__ void __launch_bounds__(128, W == 1 ? NID_JAC_MINB1 : NID_JAC_MINB2)
+__global__ void __launch_bounds__(128, W == 1 ? NID_JAC_MINB1 : (W == 2 ? NID_JAC_MINB2 : NID_JAC_MINB4))
 k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
   extern __shared__ double sm[];
   const int B = p.bins, NS = B - 3;
@@ -908,7 +911,8 @@ static void launch_jac_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0,
     q.job0 = job0 + s0;
     const dim3 grid(n, (ns + 3) / 4);
     if (c->opt_ilp_jac <= 1) k_jac_sell<PTS, 1, NG><<<grid, 128, sm, c->stream>>>(q, gt);
-    else k_jac_sell<PTS, 2, NG><<<grid, 128, sm, c->stream>>>(q, gt);
+    else if (c->opt_ilp_jac == 2) k_jac_sell<PTS, 2, NG><<<grid, 128, sm, c->stream>>>(q, gt);
+    else k_jac_sell<PTS, 4, NG><<<grid, 128, sm, c->stream>>>(q, gt);
     c->launches++;
   }
 }
@@ -975,7 +979,8 @@ int sorted_init(nid_ctx* c) {
   NID_SMEM_ATTR((k_hist_sell<PTS, 2, NG>), hist_sell_smem(c));           \
   NID_SMEM_ATTR((k_hist_sell<PTS, 4, NG>), hist_sell_smem(c));           \
   NID_SMEM_ATTR((k_jac_sell<PTS, 1, NG>), jac_sell_smem(c));             \
-  NID_SMEM_ATTR((k_jac_sell<PTS, 2, NG>), jac_sell_smem(c));
+  NID_SMEM_ATTR((k_jac_sell<PTS, 2, NG>), jac_sell_smem(c));             \
+  NID_SMEM_ATTR((k_jac_sell<PTS, 4, NG>), jac_sell_smem(c));
   NID_SMEM_ATTR_PX(true, NID_GEO_SMALL)
   NID_SMEM_ATTR_PX(false, NID_GEO_SMALL)
   NID_SMEM_ATTR_PX(true, NID_GEO_LARGE)

@@ -364,3 +364,62 @@ def test_task_length_does_not_change_results(nid, orc, make_pair, task_px):
     np.testing.assert_allclose(b[0], a[0], rtol=1e-12)
     np.testing.assert_allclose(b[1], a[1], rtol=1e-12)
     np.testing.assert_allclose(b[2], a[2], rtol=1e-8, atol=1e-11)
+
+
+def test_full_size_c3_1280x960_32_bins_gamma(nid, orc, make_pair):
+    """BASELINE config 3 at its full size: 1280x960, 4x4 cells, 32-bin histograms, strong gamma change."""
+    p = make_pair(1000, 960, 1280, gamma=0.45)
+    P = orc.Problem(p.im0, p.depth0, p.im1, p.T_wc0, p.intr, 4, 32, threads=8)
+    P.set_quirks(0, 1)
+    pose0 = orc.reference_perturbation(p.T_wc1)
+    ctx = nid.Context(960, 1280, 4, 32)
+    ctx.set_pair(0, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+    nc, href = ctx.prepare(0, orc.se3_to_mat16(pose0))
+    nco, hrefo = P.prepare(pose0)
+    assert np.array_equal(nc, nco)
+    np.testing.assert_allclose(href, hrefo, rtol=1e-10)
+    xi = np.array([0.002, -0.001, 0.0015, 0.004, -0.003, 0.002])
+    pose = orc.se3_mul(orc.se3_exp(xi), pose0)
+    Ht, Hj, J = ctx.eval(0, orc.se3_to_mat16(pose), True)
+    Hto, Hjo, erro, Jo = P.eval(pose, True)
+    np.testing.assert_allclose(Ht, Hto, rtol=1e-10)
+    np.testing.assert_allclose(Hj, Hjo, rtol=1e-10)
+    assert _jrel(J, Jo) < 1e-5  # north_star's bar, stated; measured orders of magnitude below
+    assert _jrel(J, Jo) < 1e-8
+
+
+def test_full_size_c2_batch_properties(nid, orc, make_pair):
+    """BASELINE config 4 shape (a batch of C2 pairs) through size-independent properties: every job of a batch equals
+    the same evaluation submitted alone, bit for bit, whatever the batch composition; identical poses on
+    identical pairs give identical results; the cost-only call returns the entropies of the cost+Jacobian call."""
+    pairs = [make_pair(1000 + i, 480, 640) for i in range(2)]
+    n_slots, n_jobs = 6, 40
+    ctx = nid.Context(480, 640, 4, 16, n_pairs=n_slots, max_jobs=n_jobs)
+    pose0 = [orc.reference_perturbation(p.T_wc1) for p in pairs]
+    for s in range(n_slots):
+        p = pairs[s % 2]
+        ctx.set_pair(s, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+        ctx.prepare(s, orc.se3_to_mat16(pose0[s % 2]))
+    rng = np.random.default_rng(9)
+    job_pair = rng.integers(0, n_slots, size=n_jobs).astype(np.int32)
+    xis = rng.uniform(-1, 1, size=(n_jobs, 6)) * 3e-3
+    poses = np.stack([orc.se3_to_mat16(orc.se3_mul(orc.se3_exp(xis[j]), pose0[job_pair[j] % 2])) for j in range(n_jobs)])
+    Ht, Hj, J = ctx.eval_jobs(poses, job_pair, True)
+    Ht2, Hj2, _ = ctx.eval_jobs(poses, job_pair, False)
+    assert np.array_equal(Ht, Ht2) and np.array_equal(Hj, Hj2)
+    for j in (0, 7, 23, 39):
+        a, b, c = ctx.eval(int(job_pair[j]), poses[j], True)
+        assert np.array_equal(a, Ht[j]) and np.array_equal(b, Hj[j]) and np.array_equal(c, J[j])
+    # slots s and s+2 hold the same pair: same pose => same bits
+    same = np.stack([poses[0]] * 3)
+    Ha, Hb, Jc = ctx.eval_jobs(same, np.array([job_pair[0] % 2, job_pair[0] % 2 + 2, job_pair[0] % 2 + 4], dtype=np.int32), True)
+    assert np.array_equal(Ha[0], Ha[1]) and np.array_equal(Ha[0], Ha[2]) and np.array_equal(Jc[0], Jc[2])
+    # and one job against the oracle at full size
+    P = orc.Problem(pairs[0].im0, pairs[0].depth0, pairs[0].im1, pairs[0].T_wc0, pairs[0].intr, 4, 16, threads=8)
+    P.set_quirks(0, 1)
+    P.prepare(pose0[0])
+    j = int(np.where(job_pair % 2 == 0)[0][0])
+    Hto, Hjo, _, Jo = P.eval(orc.se3_mul(orc.se3_exp(xis[j]), pose0[0]), True)
+    np.testing.assert_allclose(Ht[j], Hto, rtol=1e-10)
+    np.testing.assert_allclose(Hj[j], Hjo, rtol=1e-10)
+    assert _jrel(J[j], Jo) < 1e-8
