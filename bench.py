@@ -117,6 +117,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(kernel, n_evals):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    names = {"k_hist": "k_hist_sell", "k_jac": "k_jac_sell"}
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return d["dram_bytes_per_eval"][names[kernel]] * n_evals, d["source"]
+    except Exception:
+        return None, None
+
+
 def cpu_layout(cores):
     """Use every host core: `workers` independent evaluations in flight, each an OpenMP team of `team` threads over
     the 16 cells (team divides 16 so that cells split evenly)."""
@@ -323,6 +333,7 @@ def main():
         share = {n: kt[n][0] for n in kt}
         tot = sum(share.values()) or 1.0
         achieved = ALGO_BYTES_PER_EVAL * n_slots / (dom_ms * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(dom, n_slots)
         cpu_v, cpu_n, cpu_el = cpu_eval_rate(orc, synth, 1, 1, args.cpu_budget / 2)
         workers, team = cpu_layout(os.cpu_count() or 1)
         cores = workers * team
@@ -340,7 +351,8 @@ def main():
                     "call": "nid_eval_jobs (host poses in, host Htarget/Hjoint/der out, blocking)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "note": "fp64 path: the binding roofs are fp64 issue and latency, not HBM (DESIGN.md 4)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_EVAL * n_slots,
                          "kernel_ms_per_launch": dom_ms,
                          "kernel_share_of_step": {n: share[n] / tot for n in share}},
