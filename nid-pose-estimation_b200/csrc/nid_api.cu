@@ -69,14 +69,15 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   return p;
 }
 
-// The sorted path pays a fixed cost per (cell, class) segment; below ~12 pixels per segment on average
-// (e.g. the reference's default 16x16 cells at 640x480) the natural-order kernels are used instead.
+// Path selection. The sorted path (no floating-point atomics) wins wherever it is available: measured on B200 at
+// 640x480, cost+Jacobian: 4x4 cells/16 bins 77k vs 9k evals/s, the reference's default 16x16 cells/10 bins 29k vs 9k
+// (tools/time_config.py). The natural-order kernels remain for bin counts outside [8, 40] and as a second,
+// independently written implementation the parity tests hold to the same bar.
 bool use_sorted(const nid_ctx* c) {
   // the assembly tables must fit in shared memory; below 8 bins every span is an end span
   if (c->bins > NID_SORTED_MAX_BINS || c->bins < 8) return false;
   if (c->opt_path == 1) return false;
-  if (c->opt_path == 2) return true;
-  return (double)c->N / ((double)c->ncell * NID_NCLS) >= 12.0;
+  return true;
 }
 
 // Per-span polynomial form of the clamped cubic B-spline basis: for span k (k <= ub < k+1) and m = 0..3,

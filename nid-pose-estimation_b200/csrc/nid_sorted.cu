@@ -624,7 +624,7 @@ template <bool PTS, int W>
 __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const ExactSrc& xs, int rows, int cols,
                                            const Group<PTS>& G, int j0, cudaTextureObject_t tex2,
                                            const uint8_t* __restrict__ im1, double s, int NS, double hfx, double hfy,
-                                           const double* __restrict__ wq, double acc[6]) {
+                                           const double* __restrict__ wq, const double* __restrict__ dco, double acc[6]) {
   Px r[W];
 #pragma unroll
   for (int j = 0; j < W; j++) front<PTS, false>(g, rows, cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
@@ -653,8 +653,20 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
     const double ub = r[j].jac ? ic * s : 0.0;
     const int k = min((int)ub, NS - 1);  // 0 <= ub <= NS (== NS only by rounding)
     const double f = ub - u2d((unsigned)k);
-    const double* q = wq + 3 * k * 128;
-    double ci = fma(f, fma(f, q[256], q[128]), q[0]);
+    // c_i = sum_m N'_{k+m}(k + f) * Wv[k + m] with the lane's class table Wv (prologue of k_jac_sell)
+    double dw[4];
+    if (span_is_uniform(k, NS)) {
+      dw[0] = fma(f, fma(f, -0.5, 1.0), -0.5);
+      dw[1] = f * fma(f, 1.5, -2.0);
+      dw[2] = fma(f, fma(f, -1.5, 1.0), 0.5);
+      dw[3] = 0.5 * f * f;
+    } else {
+      const double* cf = dco + k * 12;
+#pragma unroll
+      for (int m = 0; m < 4; m++) dw[m] = fma(f, fma(f, cf[8 + m], cf[4 + m]), cf[m]);
+    }
+    const double* q = wq + k * 128;
+    double ci = fma(dw[3], q[384], fma(dw[2], q[256], fma(dw[1], q[128], dw[0] * q[0])));
     if (ub == 0.0) ci = 0.0;  // the reference's BsplineDer quirk
     if (!r[j].jac) continue;  // (a padding slot may carry z = 0 and non-finite coordinates)
     // d(u,v)/d(xi), types_six_dof_expmap.cpp:438-450, in normalised coordinates xn = x/z, yn = y/z
@@ -681,9 +693,11 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   const int job = blockIdx.x + p.job0;
   const int pair = p.job_pair[job];
   const double* g = gt.g[blockIdx.x];
+  // shared: the lanes' class tables Wv [B][128] | derivative coefficients of the end spans [NS][3][4] |
+  // per-warp log tables W|V (prologue only)
+  double* dco = sm + B * 128;
   {
     // derivative of the per-span basis polynomials: dco[k][j][m] = (j+1) * coef[k][m][j+1]
-    double* dco = sm + 3 * NS * 128 + 4 * (B * (B + 1) + B);
     for (int i = threadIdx.x; i < NS * 12; i += blockDim.x) {
       const int k = i / 12, j = (i % 12) / 4, m = i % 4;
       dco[i] = (double)(j + 1) * p.bs_coef[(k * 4 + m) * 4 + j + 1];
@@ -695,16 +709,15 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
   const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
-  double* wq = sm + threadIdx.x;  // wq[i * 128]
-  // ---- per-class / per-span quadratic of the lane's task (class v, cell of the slice):
-  //   c(f) = q0 + q1 f + q2 f^2 = sum_m N'_{k+m}(k+f) * Wv[k+m],
+  double* wq = sm + threadIdx.x;  // wq[t * 128]
+  // ---- class table of the lane's task (class v, cell of the slice):
   //   Wv[t] = V[t] + sum_kk w_ref,v[kk] W[k_r(v)+kk][t]     (class 256: V only)
-  // from the cell's scaled log tables W|V (k_assemble), staged per warp with rows padded to B+1.
+  // from the cell's scaled log tables W|V (k_assemble), staged per warp with rows padded to B+1. Pass 2 then needs
+  //   c_i = sum_m N'_{k+m}(u_i) * Wv[k+m]   per pixel (types_six_dof_expmap.cpp:467-528 re-associated).
   {
     const int BP = B + 1;
-    double* Ww = sm + 3 * NS * 128 + warp * (B * BP + B);
+    double* Ww = dco + NS * 12 + warp * (B * BP + B);
     double* Vw = Ww + B * BP;
-    const double* dco = sm + 3 * NS * 128 + 4 * (B * BP + B);  // [NS][3][4] derivative coefficients
     const int desc = task >= 0 ? p.tasks[(size_t)pair * p.max_tasks + task].y : 0;
     const int cell = __shfl_sync(0xffffffffu, (desc >> 18) & 0x3fff, 0);  // lane 0 always owns a task
     const double* wvg = p.wv + ((size_t)job * p.ncell + cell) * (size_t)(B * B + B);
@@ -721,23 +734,11 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
         for (int kk = 0; kk < 4; kk++) wr[kk] = p.lut_w[4 * cls + kk];
       }
       const double* Wr = Ww + kr * BP;
-      auto wv_at = [&](int t) {
+      for (int t = 0; t < B; t++) {
         double a = Vw[t];
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) a += wr[kk] * Wr[kk * BP + t];
-        return a;
-      };
-      double w0 = wv_at(0), w1 = wv_at(1), w2 = wv_at(2), w3;
-      for (int k = 0; k < NS; k++) {
-        w3 = wv_at(k + 3);
-        const double* cf = dco + k * 12;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-        a0 += cf[0] * w0; a1 += cf[4] * w0; a2 += cf[8] * w0;
-        a0 += cf[1] * w1; a1 += cf[5] * w1; a2 += cf[9] * w1;
-        a0 += cf[2] * w2; a1 += cf[6] * w2; a2 += cf[10] * w2;
-        a0 += cf[3] * w3; a1 += cf[7] * w3; a2 += cf[11] * w3;
-        wq[(3 * k) * 128] = a0; wq[(3 * k + 1) * 128] = a1; wq[(3 * k + 2) * 128] = a2;
-        w0 = w1; w1 = w2; w2 = w3;
+        wq[t * 128] = a;
       }
     }
   }
@@ -758,7 +759,7 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
     Group<PTS> Gn = G;
     if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
 #pragma unroll
-    for (int j0 = 0; j0 < 4; j0 += W) jac_pixels<PTS, W>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, acc);
+    for (int j0 = 0; j0 < 4; j0 += W) jac_pixels<PTS, W>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, dco, acc);
     G = Gn;
   }
   // one partial per slice: fixed-order butterfly over the 32 lanes (lanes without a task hold zeros)
@@ -855,7 +856,7 @@ int launch_pack_tex(nid_ctx* c, int pair, unsigned* d_out) {
 size_t hist_sell_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)c->bins * 256 + (size_t)(c->bins - 3) * 16); }
 size_t jac_sell_smem(const nid_ctx* c) {
   const size_t B = c->bins, NS = B - 3;
-  return sizeof(double) * (NS * 3 * 128 + 4 * (B * (B + 1) + B) + NS * 12);
+  return sizeof(double) * (B * 128 + NS * 12 + 4 * (B * (B + 1) + B));
 }
 size_t assemble_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)5 * c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins + 1024); }
 
