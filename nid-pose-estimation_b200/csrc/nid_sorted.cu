@@ -339,12 +339,13 @@ __device__ __forceinline__ void make_exact(const ExactSrc& xs, int rows, int col
 }
 
 // Pass 1 on W pixels of a group at once: projection (branch-free), W footprint loads in flight, spline
-// weights, then the accumulations in pixel order into the lane's private row h[b * 256].
+// weights, then the accumulations in pixel order into the lane's private row h[b * T] (T = threads per CTA).
 // fp: the pair's footprint-packed target image, fp[y*cols + x] = I(x,y) | I(x+1,y)<<8 | I(x,y+1)<<16 | I(x+1,y+1)<<24.
 template <bool PTS, int W>
 __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const ExactSrc& xs, int rows, int cols,
                                             const Group<PTS>& G, int j0, const unsigned* __restrict__ fp,
-                                            const double* __restrict__ coef, double s, int NS, double* __restrict__ h) {
+                                            const double* __restrict__ coef, double s, int NS, double* __restrict__ h,
+                                            int T) {
   Px r[W];
   bool anyexact = false;
 #pragma unroll
@@ -407,14 +408,15 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
 #pragma unroll
   for (int j = 0; j < W; j++) {
     if (!r[j].ok) continue;
-    double* hk = h + kt[j] * 256;
+    double* hk = h + kt[j] * T;
 #pragma unroll
-    for (int n = 0; n < 4; n++) hk[n * 256] += wt[j][n];
+    for (int n = 0; n < 4; n++) hk[n * T] += wt[j][n];
   }
 }
 
 // Pass 1: per task the un-weighted target soft histogram h[B] of its pixels.
-// grid (jobs of this launch, ceil(max_slices/8)), 256 threads; shared: rows [B][256] + spline table. The job
+// grid (jobs of this launch, ceil(max_slices/(T/32))), T = 32..256 threads (fewer when few jobs are in flight, so
+// that every SM gets work); shared: rows [B][T] + spline table. The job
 // index is the fast grid dimension and slices are ordered longest first, so the long CTAs of every job
 // start first and the short ones fill the tail. The next group's pixels are loaded before the current
 // group is processed.
@@ -442,16 +444,17 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
   const int job = blockIdx.x + p.job0;
   const int pair = p.job_pair[job];
   const double* g = gt.g[blockIdx.x];
-  double* coef = sm + (size_t)B * 256;
+  const int T = blockDim.x;
+  double* coef = sm + (size_t)B * T;
   for (int i = threadIdx.x; i < NS * 16; i += blockDim.x) coef[i] = p.bs_coef[i];
   __syncthreads();
-  const int slice = blockIdx.y * 8 + warp;
+  const int slice = blockIdx.y * (T >> 5) + warp;
   if (slice >= p.nslices[pair]) return;
   const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
   const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
-  double* h = sm + threadIdx.x;  // h[b * 256]
-  for (int b = 0; b < B; b++) h[b * 256] = 0.0;
+  double* h = sm + threadIdx.x;  // h[b * T]
+  for (int b = 0; b < B; b++) h[b * T] = 0.0;
   const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
   const double* q0 = p.sd0 + sbase;
   const double* q1 = PTS ? p.sd1 + sbase : nullptr;
@@ -466,12 +469,12 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
     Group<PTS> Gn = G;
     if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
 #pragma unroll
-    for (int j0 = 0; j0 < 4; j0 += W) hist_pixels<PTS, W>(g, xs, p.rows, p.cols, G, j0, fp, coef, s, NS, h);
+    for (int j0 = 0; j0 < 4; j0 += W) hist_pixels<PTS, W>(g, xs, p.rows, p.cols, G, j0, fp, coef, s, NS, h, T);
     G = Gn;
   }
   if (task >= 0) {
     double* out = p.G + ((size_t)job * p.g_stride + task) * B;
-    for (int b = 0; b < B; b++) out[b] = h[b * 256];
+    for (int b = 0; b < B; b++) out[b] = h[b * T];
   }
 }
 
@@ -589,7 +592,6 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, 2) k_assemble(EvalParams p, i
 // ------------------------------------------------------------------------------------------------
 // Pass 2: per task the partial of  J[a] = sum_i g_i[a] * c_i,  c_i = q0 + f_i (q1 + f_i q2) with the
 // quadratic of the pixel's (class, span); c_i = 0 at ub == 0 exactly (the reference's BsplineDer quirk).
-// grid (ceil(max_slices/4), jobs), 128 threads; shared: the lanes' quadratic rows [3*NS][128].
 __device__ __forceinline__ double biased9_to_double(unsigned v) {  // v in [0, 511] -> (double)(v - 256), exact
   return __hiloint2double(0x43300000, (int)v) - (4503599627370496.0 + 256.0);
 }
@@ -624,7 +626,8 @@ template <bool PTS, int W>
 __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const ExactSrc& xs, int rows, int cols,
                                            const Group<PTS>& G, int j0, cudaTextureObject_t tex2,
                                            const uint8_t* __restrict__ im1, double s, int NS, double hfx, double hfy,
-                                           const double* __restrict__ wq, const double* __restrict__ dco, double acc[6]) {
+                                           const double* __restrict__ wq, const double* __restrict__ dco, int T,
+                                           double acc[6]) {
   Px r[W];
 #pragma unroll
   for (int j = 0; j < W; j++) front<PTS, false>(g, rows, cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
@@ -665,8 +668,8 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
 #pragma unroll
       for (int m = 0; m < 4; m++) dw[m] = fma(f, fma(f, cf[8 + m], cf[4 + m]), cf[m]);
     }
-    const double* q = wq + k * 128;
-    double ci = fma(dw[3], q[384], fma(dw[2], q[256], fma(dw[1], q[128], dw[0] * q[0])));
+    const double* q = wq + k * T;
+    double ci = fma(dw[3], q[3 * T], fma(dw[2], q[2 * T], fma(dw[1], q[T], dw[0] * q[0])));
     if (ub == 0.0) ci = 0.0;  // the reference's BsplineDer quirk
     if (!r[j].jac) continue;  // (a padding slot may carry z = 0 and non-finite coordinates)
     // d(u,v)/d(xi), types_six_dof_expmap.cpp:438-450, in normalised coordinates xn = x/z, yn = y/z
@@ -683,7 +686,7 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
   }
 }
 
-// grid (jobs, ceil(max_slices/4)), 128 threads; shared: the lanes' quadratic rows [3*NS][128].
+// grid (jobs of this launch, ceil(max_slices/(T/32))), T = 32..128 threads.
 template <bool PTS, int W, int NG>
 __global__ void __launch_bounds__(128, W == 1 ? NID_JAC_MINB1 : (W == 2 ? NID_JAC_MINB2 : NID_JAC_MINB4))
 k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
@@ -693,9 +696,10 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   const int job = blockIdx.x + p.job0;
   const int pair = p.job_pair[job];
   const double* g = gt.g[blockIdx.x];
-  // shared: the lanes' class tables Wv [B][128] | derivative coefficients of the end spans [NS][3][4] |
+  // shared: the lanes' class tables Wv [B][T] | derivative coefficients of the end spans [NS][3][4] |
   // per-warp log tables W|V (prologue only)
-  double* dco = sm + B * 128;
+  const int T = blockDim.x;
+  double* dco = sm + B * T;
   {
     // derivative of the per-span basis polynomials: dco[k][j][m] = (j+1) * coef[k][m][j+1]
     for (int i = threadIdx.x; i < NS * 12; i += blockDim.x) {
@@ -704,12 +708,12 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
     }
   }
   __syncthreads();
-  const int slice = blockIdx.y * 4 + warp;
+  const int slice = blockIdx.y * (T >> 5) + warp;
   if (slice >= p.nslices[pair]) return;
   const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
   const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
-  double* wq = sm + threadIdx.x;  // wq[t * 128]
+  double* wq = sm + threadIdx.x;  // wq[t * T]
   // ---- class table of the lane's task (class v, cell of the slice):
   //   Wv[t] = V[t] + sum_kk w_ref,v[kk] W[k_r(v)+kk][t]     (class 256: V only)
   // from the cell's scaled log tables W|V (k_assemble), staged per warp with rows padded to B+1. Pass 2 then needs
@@ -738,7 +742,7 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
         double a = Vw[t];
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) a += wr[kk] * Wr[kk * BP + t];
-        wq[t * 128] = a;
+        wq[t * T] = a;
       }
     }
   }
@@ -759,7 +763,7 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
     Group<PTS> Gn = G;
     if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
 #pragma unroll
-    for (int j0 = 0; j0 < 4; j0 += W) jac_pixels<PTS, W>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, dco, acc);
+    for (int j0 = 0; j0 < 4; j0 += W) jac_pixels<PTS, W>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, dco, T, acc);
     G = Gn;
   }
   // one partial per slice: fixed-order butterfly over the 32 lanes (lanes without a task hold zeros)
@@ -853,10 +857,18 @@ int launch_pack_tex(nid_ctx* c, int pair, unsigned* d_out) {
   return NID_OK;
 }
 
-size_t hist_sell_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)c->bins * 256 + (size_t)(c->bins - 3) * 16); }
-size_t jac_sell_smem(const nid_ctx* c) {
+size_t hist_sell_smem(const nid_ctx* c, int T = 256) { return sizeof(double) * ((size_t)c->bins * T + (size_t)(c->bins - 3) * 16); }
+size_t jac_sell_smem(const nid_ctx* c, int T = 128) {
   const size_t B = c->bins, NS = B - 3;
-  return sizeof(double) * (B * 128 + NS * 12 + 4 * (B * (B + 1) + B));
+  return sizeof(double) * (B * T + NS * 12 + (size_t)(T / 32) * (B * (B + 1) + B));
+}
+
+// Threads per CTA of the pixel kernels: the largest of 32..tmax that still gives every SM about two CTAs; a
+// handful of jobs (a single LM solve) then spreads its slices over the whole GPU instead of a few dozen SMs.
+static int pick_block(const nid_ctx* c, int ns, int n_jobs, int tmax) {
+  for (int T = tmax; T > 32; T >>= 1)
+    if ((long long)n_jobs * ((ns + T / 32 - 1) / (T / 32)) >= 2LL * c->sm_count) return T;
+  return 32;
 }
 size_t assemble_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)5 * c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins + 1024); }
 
@@ -888,32 +900,34 @@ static void fill_geo(const nid_ctx* c, GeoTable<NG>& gt, int first, int n, bool 
 
 template <bool PTS, int NG>
 static void launch_hist_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
-  const size_t sm = hist_sell_smem(c);
+  const int T = pick_block(c, ns, n_jobs, 256);
+  const size_t sm = hist_sell_smem(c, T);
   for (int s0 = 0; s0 < n_jobs; s0 += NG) {
     const int n = std::min(NG, n_jobs - s0);
     GeoTable<NG> gt;
     fill_geo(c, gt, job0 + s0, n, true);
     EvalParams q = p;
     q.job0 = job0 + s0;
-    const dim3 grid(n, (ns + 7) / 8);
-    if (c->opt_ilp_hist <= 2) k_hist_sell<PTS, 2, NG><<<grid, 256, sm, c->stream>>>(q, gt);
-    else k_hist_sell<PTS, 4, NG><<<grid, 256, sm, c->stream>>>(q, gt);
+    const dim3 grid(n, (ns + T / 32 - 1) / (T / 32));
+    if (c->opt_ilp_hist <= 2) k_hist_sell<PTS, 2, NG><<<grid, T, sm, c->stream>>>(q, gt);
+    else k_hist_sell<PTS, 4, NG><<<grid, T, sm, c->stream>>>(q, gt);
     c->launches++;
   }
 }
 template <bool PTS, int NG>
 static void launch_jac_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
-  const size_t sm = jac_sell_smem(c);
+  const int T = pick_block(c, ns, n_jobs, 128);
+  const size_t sm = jac_sell_smem(c, T);
   for (int s0 = 0; s0 < n_jobs; s0 += NG) {
     const int n = std::min(NG, n_jobs - s0);
     GeoTable<NG> gt;
     fill_geo(c, gt, job0 + s0, n, false);
     EvalParams q = p;
     q.job0 = job0 + s0;
-    const dim3 grid(n, (ns + 3) / 4);
-    if (c->opt_ilp_jac <= 1) k_jac_sell<PTS, 1, NG><<<grid, 128, sm, c->stream>>>(q, gt);
-    else if (c->opt_ilp_jac == 2) k_jac_sell<PTS, 2, NG><<<grid, 128, sm, c->stream>>>(q, gt);
-    else k_jac_sell<PTS, 4, NG><<<grid, 128, sm, c->stream>>>(q, gt);
+    const dim3 grid(n, (ns + T / 32 - 1) / (T / 32));
+    if (c->opt_ilp_jac <= 1) k_jac_sell<PTS, 1, NG><<<grid, T, sm, c->stream>>>(q, gt);
+    else if (c->opt_ilp_jac == 2) k_jac_sell<PTS, 2, NG><<<grid, T, sm, c->stream>>>(q, gt);
+    else k_jac_sell<PTS, 4, NG><<<grid, T, sm, c->stream>>>(q, gt);
     c->launches++;
   }
 }
