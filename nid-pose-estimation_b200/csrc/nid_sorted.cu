@@ -472,9 +472,38 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
     for (int j0 = 0; j0 < 4; j0 += W) hist_pixels<PTS, W>(g, xs, p.rows, p.cols, G, j0, fp, coef, s, NS, h, T);
     G = Gn;
   }
-  if (task >= 0) {
-    double* out = p.G + ((size_t)job * p.g_stride + task) * B;
-    for (int b = 0; b < B; b++) out[b] = h[b * T];
+  // Epilogue: the warp's 32 rows go out as whole 8 B x B lines. Lane l first rotates its row inside the warp's own
+  // columns of the shared array -- value (l, b) to column (l + b) mod 32 of plane b -- so that the lanes which then
+  // write one task's row read B different banks; each store instruction covers 32/B' complete rows (B' = B rounded up
+  // to a power of two) instead of 32 partial sectors of 32 different rows.
+  {
+    double* hw = sm + (threadIdx.x & ~31);  // plane b of this warp: hw[b * T + 0..31]
+    for (int b0 = 0; b0 < B; b0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = (b0 + i < B) ? hw[(b0 + i) * T + lane] : 0.0;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (b0 + i < B) hw[(b0 + i) * T + ((lane + b0 + i) & 31)] = v[i];
+    }
+    __syncwarp();
+    const int BP2 = B <= 8 ? 8 : (B <= 16 ? 16 : 32);  // lanes per row
+    const int rpi = 32 / BP2;                          // rows per store instruction
+    const int b = lane & (BP2 - 1), sub = lane / BP2;
+    double* Gj = p.G + (size_t)job * p.g_stride * B;
+    for (int t0 = 0; t0 < 32; t0 += rpi) {
+      const int tl = t0 + sub;
+      const int tk = __shfl_sync(0xffffffffu, task, tl);
+      if (b < B && tk >= 0) Gj[(size_t)tk * B + b] = hw[b * T + ((tl + b) & 31)];
+    }
+    for (int b1 = BP2; b1 < B; b1 += BP2) {  // B > 32: remaining columns
+      for (int t0 = 0; t0 < 32; t0 += rpi) {
+        const int tl = t0 + sub, bb = b1 + b;
+        const int tk = __shfl_sync(0xffffffffu, task, tl);
+        if (bb < B && tk >= 0) Gj[(size_t)tk * B + bb] = hw[bb * T + ((tl + bb) & 31)];
+      }
+    }
   }
 }
 
