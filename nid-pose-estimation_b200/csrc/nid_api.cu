@@ -877,8 +877,6 @@ int nid_set_option(nid_ctx* c, const char* key, int value) {
     return NID_OK;
   }
   if (!strcmp(key, "keep_hist")) { c->opt_keep_hist = value; return NID_OK; }
-  if (!strcmp(key, "ilp_hist")) { c->opt_ilp_hist = value; return NID_OK; }
-  if (!strcmp(key, "ilp_jac")) { c->opt_ilp_jac = value; return NID_OK; }
   if (!strcmp(key, "task_px")) {
     if (value < 16 || value > NID_TASK_PX_MAX || (value & 3)) { set_error("task_px must be a multiple of 4 in [16, 256]"); return NID_ERR_ARG; }
     if (value != c->task_px) {

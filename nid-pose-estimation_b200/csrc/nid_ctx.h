@@ -102,7 +102,6 @@ struct nid_ctx {
   std::vector<int> h_nslices;
   int max_nslices_prepared = 0;
   int task_px = 32;            // L: pixels per task
-  int opt_ilp_hist = 4, opt_ilp_jac = 2;  // pixels a lane processes together in pass 1 / pass 2
   bool sell_points = false;    // pairs carry caller-supplied world points (nid_set_pair_points)
   int2* tasks = nullptr;
   int* ntasks = nullptr;

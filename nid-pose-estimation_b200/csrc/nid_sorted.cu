@@ -280,9 +280,19 @@ __device__ __forceinline__ uint4 gather_u32(cudaTextureObject_t tex, int ix, int
   return tex2Dgather<uint4>(tex, (float)(ix + 1), (float)(iy + 1), 0);
 }
 
-// Cubic B-spline basis on span k, f = ub - k. Interior spans of the clamped uniform knot vector
-// (2 <= k <= NS-3) share the uniform cubic basis; the two spans at either end take the per-span
-// polynomial table (nid_api.cu: build_bspline_table).
+// Cubic B-spline weights without end-span cases. The reference's basis N_j lives on the clamped knot vector
+// t_i = clamp(i-3, 0, B-3) (types_six_dof_expmap.cpp:738-764); on [0, B-3] it spans the same space as the B shifted
+// copies U_j of the uniform cubic B-spline, and the change of basis is the identity except for a 3x3 block at
+// either end (exact rationals, the same for every B >= 6):
+//     N_0 = 6 U_0                N_{B-1} = 6 U_{B-1}
+//     N_1 = -6 U_0 + 3/2 U_1     N_{B-2} = 3/2 U_{B-2} - 6 U_{B-1}
+//     N_2 = U_0 - 1/2 U_1 + U_2  N_{B-3} = U_{B-3} - 1/2 U_{B-2} + U_{B-1}
+// Histograms are sums of basis values, so pass 1 accumulates the *uniform* weights of every pixel (one branch-free
+// formula, no coefficient table) and applies the block once per task row (fold_row); pass 2 uses the transposed
+// block on its class table (fold_table) and the uniform derivative per pixel. The one place where this is not
+// a rounding-level identity is a bin whose clamped sum is exactly zero in the reference while U-sums cancel only
+// to rounding: that happens iff every contributing pixel sits at u == 0 exactly (N_1(0) = N_2(0) = 0), so pixels
+// with u == 0 are counted apart and enter bin 0 with weight exactly 1.
 __device__ __forceinline__ void bspline4_uniform(double f, double w[4]) {
   const double s6 = 1.0 / 6.0;
   w[0] = fma(f, fma(f, fma(f, -s6, 0.5), -0.5), s6);
@@ -290,14 +300,25 @@ __device__ __forceinline__ void bspline4_uniform(double f, double w[4]) {
   w[2] = fma(f, fma(f, fma(f, -0.5, 0.5), 0.5), s6);
   w[3] = f * f * f * s6;
 }
-__device__ __forceinline__ bool span_is_uniform(int k, int NS) { return (unsigned)(k - 2) <= (unsigned)(NS - 5); }
-__device__ __forceinline__ void bspline4_edge(const double* __restrict__ coef, int k, double f, double w[4]) {
-  const double2* c2 = reinterpret_cast<const double2*>(coef + (size_t)k * 16);
-#pragma unroll
-  for (int m = 0; m < 4; m++) {
-    const double2 a = c2[2 * m], b = c2[2 * m + 1];
-    w[m] = fma(f, fma(f, fma(f, b.y, b.x), a.y), a.x);
-  }
+// h: one lane's row of uniform sums, element b at h[b * stride]; n0: its pixels with u == 0
+__device__ __forceinline__ void fold_row(double* h, int stride, int B, double n0) {
+  const double u0 = h[0], u1 = h[stride], u2 = h[2 * stride];
+  h[0] = fma(6.0, u0, n0);
+  h[stride] = fma(1.5, u1, -6.0 * u0);
+  h[2 * stride] = (u0 - 0.5 * u1) + u2;
+  const double t1 = h[(B - 1) * stride], t2 = h[(B - 2) * stride], t3 = h[(B - 3) * stride];
+  h[(B - 1) * stride] = 6.0 * t1;
+  h[(B - 2) * stride] = fma(1.5, t2, -6.0 * t1);
+  h[(B - 3) * stride] = (t1 - 0.5 * t2) + t3;
+}
+// transposed block: sum_j N'_j W_j = sum_j U'_j W^_j
+__device__ __forceinline__ void fold_table(double* w, int stride, int B) {
+  const double w0 = w[0], w1 = w[stride], w2 = w[2 * stride];
+  w[0] = fma(6.0, w0 - w1, w2);
+  w[stride] = fma(1.5, w1, -0.5 * w2);
+  const double v1 = w[(B - 1) * stride], v2 = w[(B - 2) * stride], v3 = w[(B - 3) * stride];
+  w[(B - 1) * stride] = fma(6.0, v1 - v2, v3);
+  w[(B - 2) * stride] = fma(1.5, v2, -0.5 * v3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,14 +359,14 @@ __device__ __forceinline__ void make_exact(const ExactSrc& xs, int rows, int col
   px_from_exact(ex, rows, cols, r);
 }
 
-// Pass 1 on W pixels of a group at once: projection (branch-free), W footprint loads in flight, spline
+// Pass 1 on W pixels of a group at once: projection (branch-free), W footprint loads in flight, uniform spline
 // weights, then the accumulations in pixel order into the lane's private row h[b * T] (T = threads per CTA).
 // fp: the pair's footprint-packed target image, fp[y*cols + x] = I(x,y) | I(x+1,y)<<8 | I(x,y+1)<<16 | I(x+1,y+1)<<24.
-template <bool PTS, int W>
+// n0 counts the lane's pixels with u == 0 exactly (see bspline4_uniform).
+template <bool PTS, int W, int T>
 __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const ExactSrc& xs, int rows, int cols,
-                                            const Group<PTS>& G, int j0, const unsigned* __restrict__ fp,
-                                            const double* __restrict__ coef, double s, int NS, double* __restrict__ h,
-                                            int T) {
+                                            const Group<PTS>& G, int j0, const unsigned* __restrict__ fp, double s, int NS,
+                                            double* __restrict__ h, int& n0) {
   Px r[W];
   bool anyexact = false;
 #pragma unroll
@@ -360,7 +381,7 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
   }
   unsigned t[W];
 #pragma unroll
-  for (int j = 0; j < W; j++) t[j] = __ldg(fp + r[j].iy * cols + r[j].ix);
+  for (int j = 0; j < W; j++) t[j] = __ldg(fp + (unsigned)(r[j].iy * cols + r[j].ix));
   bool sat = false;
 #pragma unroll
   for (int j = 0; j < W; j++) sat |= r[j].ok && !r[j].exact && t[j] == 0xffffffffu;
@@ -372,14 +393,18 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
     for (int j = 0; j < W; j++)
       if (r[j].ok && !r[j].exact && t[j] == 0xffffffffu) {
         make_exact<PTS>(xs, rows, cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
-        t[j] = __ldg(fp + r[j].iy * cols + r[j].ix);
+        t[j] = __ldg(fp + (unsigned)(r[j].iy * cols + r[j].ix));
       }
   }
   double ic[W];
 #pragma unroll
   for (int j = 0; j < W; j++) {
-    const int p00 = t[j] & 0xffu, p01 = (t[j] >> 8) & 0xffu, p10 = (t[j] >> 16) & 0xffu, p11 = t[j] >> 24;
-    ic[j] = bilinear_fast(r[j].dx, r[j].dy, u2d(p00), i2d_small(p01 - p00), u2d(p10), i2d_small(p11 - p10));
+    // 2^52 + tap as a double (byte extract straight into the low word); differences of two such are exact
+    const double e00 = __hiloint2double(0x43300000, (int)__byte_perm(t[j], 0, 0x4440));
+    const double e01 = __hiloint2double(0x43300000, (int)__byte_perm(t[j], 0, 0x4441));
+    const double e10 = __hiloint2double(0x43300000, (int)__byte_perm(t[j], 0, 0x4442));
+    const double e11 = __hiloint2double(0x43300000, (int)__byte_perm(t[j], 0, 0x4443));
+    ic[j] = bilinear_fast(r[j].dx, r[j].dy, e00 - 4503599627370496.0, e01 - e00, e10 - 4503599627370496.0, e11 - e10);
   }
   if (anyexact) {
 #pragma unroll
@@ -389,25 +414,21 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
         ic[j] = clamp_intensity(bilinear_ref(r[j].dx, r[j].dy, p00, p01, p10, p11));
       }
   }
-  double wt[W][4], fr[W];
+  double wt[W][4];
   int kt[W];
-  bool edge = false;
+  bool acc[W];
 #pragma unroll
   for (int j = 0; j < W; j++) {
     const double ub = ic[j] * s;
     kt[j] = r[j].ok ? min((int)ub, NS - 1) : 0;  // 0 <= ub <= NS (== NS only by rounding)
-    fr[j] = ub - u2d((unsigned)kt[j]);
-    bspline4_uniform(fr[j], wt[j]);
-    edge |= r[j].ok && !span_is_uniform(kt[j], NS);
-  }
-  if (edge) {
-#pragma unroll
-    for (int j = 0; j < W; j++)
-      if (r[j].ok && !span_is_uniform(kt[j], NS)) bspline4_edge(coef, kt[j], fr[j], wt[j]);
+    bspline4_uniform(ub - u2d((unsigned)kt[j]), wt[j]);
+    const bool zero = ub == 0.0;
+    acc[j] = r[j].ok && !zero;
+    n0 += (r[j].ok && zero) ? 1 : 0;
   }
 #pragma unroll
   for (int j = 0; j < W; j++) {
-    if (!r[j].ok) continue;
+    if (!acc[j]) continue;
     double* hk = h + kt[j] * T;
 #pragma unroll
     for (int n = 0; n < 4; n++) hk[n * T] += wt[j][n];
@@ -416,27 +437,19 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
 
 // Pass 1: per task the un-weighted target soft histogram h[B] of its pixels.
 // grid (jobs of this launch, ceil(max_slices/(T/32))), T = 32..256 threads (fewer when few jobs are in flight, so
-// that every SM gets work); shared: rows [B][T] + spline table. The job
-// index is the fast grid dimension and slices are ordered longest first, so the long CTAs of every job
-// start first and the short ones fill the tail. The next group's pixels are loaded before the current
-// group is processed.
-#ifndef NID_HIST_MINB4
-#define NID_HIST_MINB4 2
+// that every SM gets work); shared: rows [B][T]. The job index is the fast grid dimension and slices are ordered
+// longest first, so the long CTAs of every job start first and the short ones fill the tail. The next group's
+// pixels are loaded before the current group is processed. NID_HIST_W pixels of a lane are in flight together.
+#define NID_HIST_W 4
+#define NID_JAC_W 2
+#ifndef NID_HIST_MINB
+#define NID_HIST_MINB 2  // CTAs of 256 threads per SM (128 registers)
 #endif
-#ifndef NID_HIST_MINB2
-#define NID_HIST_MINB2 3
+#ifndef NID_JAC_MINB
+#define NID_JAC_MINB 4  // CTAs of 128 threads per SM (128 registers)
 #endif
-#ifndef NID_JAC_MINB2
-#define NID_JAC_MINB2 4
-#endif
-#ifndef NID_JAC_MINB1
-#define NID_JAC_MINB1 5
-#endif
-#ifndef NID_JAC_MINB4
-#define NID_JAC_MINB4 3
-#endif
-template <bool PTS, int W, int NG>
-__global__ void __launch_bounds__(256, W == 2 ? NID_HIST_MINB2 : NID_HIST_MINB4)
+template <bool PTS, int NG, int T>
+__global__ void __launch_bounds__(T, NID_HIST_MINB * 256 / T)
 k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
   extern __shared__ double sm[];
   const int B = p.bins, NS = B - 3;
@@ -444,12 +457,8 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
   const int job = blockIdx.x + p.job0;
   const int pair = p.job_pair[job];
   const double* g = gt.g[blockIdx.x];
-  const int T = blockDim.x;
-  double* coef = sm + (size_t)B * T;
-  for (int i = threadIdx.x; i < NS * 16; i += blockDim.x) coef[i] = p.bs_coef[i];
-  __syncthreads();
   const int slice = blockIdx.y * (T >> 5) + warp;
-  if (slice >= p.nslices[pair]) return;
+  if (slice >= p.nslices[pair]) return;  // (no block-wide barrier below)
   const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
   const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
@@ -463,15 +472,18 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
   const unsigned* fp = p.fp1 + (size_t)pair * p.N;
   const ExactSrc xs{p.poses + 16 * job, p.Twc0 + 16 * pair, p.cam + 4 * pair};
   const double s = (double)NS / 255.0;
+  int n0 = 0;
   Group<PTS> G;
   G.load(q0, q1, q2, qi, 0);
   for (int gi = 0; gi < ngroups; gi++) {
     Group<PTS> Gn = G;
     if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
 #pragma unroll
-    for (int j0 = 0; j0 < 4; j0 += W) hist_pixels<PTS, W>(g, xs, p.rows, p.cols, G, j0, fp, coef, s, NS, h, T);
+    for (int j0 = 0; j0 < 4; j0 += NID_HIST_W) hist_pixels<PTS, NID_HIST_W, T>(g, xs, p.rows, p.cols, G, j0, fp, s, NS, h, n0);
     G = Gn;
   }
+  fold_row(h, T, B, (double)n0);  // uniform sums -> sums of the reference's clamped basis
+  __syncwarp();
   // Epilogue: the warp's 32 rows go out as whole 8 B x B lines. Lane l first rotates its row inside the warp's own
   // columns of the shared array -- value (l, b) to column (l + b) mod 32 of plane b -- so that the lanes which then
   // write one task's row read B different banks; each store instruction covers 32/B' complete rows (B' = B rounded up
@@ -621,10 +633,6 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, 2) k_assemble(EvalParams p, i
 // ------------------------------------------------------------------------------------------------
 // Pass 2: per task the partial of  J[a] = sum_i g_i[a] * c_i,  c_i = q0 + f_i (q1 + f_i q2) with the
 // quadratic of the pixel's (class, span); c_i = 0 at ub == 0 exactly (the reference's BsplineDer quirk).
-__device__ __forceinline__ double biased9_to_double(unsigned v) {  // v in [0, 511] -> (double)(v - 256), exact
-  return __hiloint2double(0x43300000, (int)v) - (4503599627370496.0 + 256.0);
-}
-
 // Pass-2 pixel by the reference's literal sequence: exact (u, v) for the cached intensity
 // (types_six_dof_expmap.cpp:562-575), the second projection fx*(x/z)+cx for the Jacobian bounds test and the
 // four gradient samples (:407-435). Taken when (u, v) is within 2^-24 of an integer, on saturated plateaus,
@@ -650,13 +658,16 @@ __device__ __noinline__ bool jac_pixel_literal(const double* __restrict__ T1g, c
   return true;
 }
 
+// 2^52 + v as a double (v < 2^32): differences of two such values are exact small integers
+__device__ __forceinline__ double tapd(unsigned v) { return __hiloint2double(0x43300000, (int)v); }
+
 // Pass 2 on W pixels of a group at once; acc[6] are the lane's Jacobian partial sums.
-template <bool PTS, int W>
+// wq: the lane's folded class table (fold_table), element t at wq[t * T].
+template <bool PTS, int W, int T>
 __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const ExactSrc& xs, int rows, int cols,
                                            const Group<PTS>& G, int j0, cudaTextureObject_t tex2,
                                            const uint8_t* __restrict__ im1, double s, int NS, double hfx, double hfy,
-                                           const double* __restrict__ wq, const double* __restrict__ dco, int T,
-                                           double acc[6]) {
+                                           const double* __restrict__ wq, double acc[6]) {
   Px r[W];
 #pragma unroll
   for (int j = 0; j < W; j++) front<PTS, false>(g, rows, cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
@@ -666,14 +677,16 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
 #pragma unroll
   for (int j = 0; j < W; j++) {
     // texel = I | (Gx+256) << 8 | (Gy+256) << 17; the biases cancel in the differences
-    const int i00 = t[j].w & 0xffu, i01 = t[j].z & 0xffu, i10 = t[j].x & 0xffu, i11 = t[j].y & 0xffu;
-    const int x00 = (t[j].w >> 8) & 0x1ffu, x01 = (t[j].z >> 8) & 0x1ffu, x10 = (t[j].x >> 8) & 0x1ffu, x11 = (t[j].y >> 8) & 0x1ffu;
-    const int y00 = t[j].w >> 17, y01 = t[j].z >> 17, y10 = t[j].x >> 17, y11 = t[j].y >> 17;
-    double ic = bilinear_fast(r[j].dx, r[j].dy, u2d(i00), i2d_small(i01 - i00), u2d(i10), i2d_small(i11 - i10));
-    double gx2 = bilinear_fast(r[j].dx, r[j].dy, biased9_to_double(x00), i2d_small(x01 - x00), biased9_to_double(x10), i2d_small(x11 - x10));
-    double gy2 = bilinear_fast(r[j].dx, r[j].dy, biased9_to_double(y00), i2d_small(y01 - y00), biased9_to_double(y10), i2d_small(y11 - y10));
+    const double two52 = 4503599627370496.0;
+    const double i00 = tapd(t[j].w & 0xffu), i01 = tapd(t[j].z & 0xffu), i10 = tapd(t[j].x & 0xffu), i11 = tapd(t[j].y & 0xffu);
+    const double x00 = tapd((t[j].w >> 8) & 0x1ffu), x01 = tapd((t[j].z >> 8) & 0x1ffu);
+    const double x10 = tapd((t[j].x >> 8) & 0x1ffu), x11 = tapd((t[j].y >> 8) & 0x1ffu);
+    const double y00 = tapd(t[j].w >> 17), y01 = tapd(t[j].z >> 17), y10 = tapd(t[j].x >> 17), y11 = tapd(t[j].y >> 17);
+    double ic = bilinear_fast(r[j].dx, r[j].dy, i00 - two52, i01 - i00, i10 - two52, i11 - i10);
+    double gx2 = bilinear_fast(r[j].dx, r[j].dy, x00 - (two52 + 256.0), x01 - x00, x10 - (two52 + 256.0), x11 - x10);
+    double gy2 = bilinear_fast(r[j].dx, r[j].dy, y00 - (two52 + 256.0), y01 - y00, y10 - (two52 + 256.0), y11 - y10);
     // rare: undecided by the fast path, saturated plateau, or first image row / column
-    const bool sat = (i00 & i01 & i10 & i11) == 0xff;
+    const bool sat = (t[j].w & t[j].z & t[j].x & t[j].y & 0xffu) == 0xffu;
     if (r[j].fix || (r[j].jac && (sat || r[j].ix < 1 || r[j].iy < 1))) {
       double o6[6];
       r[j].jac = jac_pixel_literal<PTS>(xs.T1, xs.T0, xs.cam, rows, cols, im1, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], o6);
@@ -685,20 +698,13 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
     const double ub = r[j].jac ? ic * s : 0.0;
     const int k = min((int)ub, NS - 1);  // 0 <= ub <= NS (== NS only by rounding)
     const double f = ub - u2d((unsigned)k);
-    // c_i = sum_m N'_{k+m}(k + f) * Wv[k + m] with the lane's class table Wv (prologue of k_jac_sell)
-    double dw[4];
-    if (span_is_uniform(k, NS)) {
-      dw[0] = fma(f, fma(f, -0.5, 1.0), -0.5);
-      dw[1] = f * fma(f, 1.5, -2.0);
-      dw[2] = fma(f, fma(f, -1.5, 1.0), 0.5);
-      dw[3] = 0.5 * f * f;
-    } else {
-      const double* cf = dco + k * 12;
-#pragma unroll
-      for (int m = 0; m < 4; m++) dw[m] = fma(f, fma(f, cf[8 + m], cf[4 + m]), cf[m]);
-    }
+    // c_i = sum_m N'_{k+m}(u_i) Wv[k+m] = sum_m U'_m(f) W^v[k+m]: uniform cubic derivative, folded class table
+    const double dw0 = fma(f, fma(f, -0.5, 1.0), -0.5);
+    const double dw1 = f * fma(f, 1.5, -2.0);
+    const double dw2 = fma(f, fma(f, -1.5, 1.0), 0.5);
+    const double dw3 = 0.5 * f * f;
     const double* q = wq + k * T;
-    double ci = fma(dw[3], q[3 * T], fma(dw[2], q[2 * T], fma(dw[1], q[T], dw[0] * q[0])));
+    double ci = fma(dw3, q[3 * T], fma(dw2, q[2 * T], fma(dw1, q[T], dw0 * q[0])));
     if (ub == 0.0) ci = 0.0;  // the reference's BsplineDer quirk
     if (!r[j].jac) continue;  // (a padding slot may carry z = 0 and non-finite coordinates)
     // d(u,v)/d(xi), types_six_dof_expmap.cpp:438-450, in normalised coordinates xn = x/z, yn = y/z
@@ -716,8 +722,8 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
 }
 
 // grid (jobs of this launch, ceil(max_slices/(T/32))), T = 32..128 threads.
-template <bool PTS, int W, int NG>
-__global__ void __launch_bounds__(128, W == 1 ? NID_JAC_MINB1 : (W == 2 ? NID_JAC_MINB2 : NID_JAC_MINB4))
+template <bool PTS, int NG, int T>
+__global__ void __launch_bounds__(T, NID_JAC_MINB * 128 / T)
 k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
   extern __shared__ double sm[];
   const int B = p.bins, NS = B - 3;
@@ -725,31 +731,21 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   const int job = blockIdx.x + p.job0;
   const int pair = p.job_pair[job];
   const double* g = gt.g[blockIdx.x];
-  // shared: the lanes' class tables Wv [B][T] | derivative coefficients of the end spans [NS][3][4] |
-  // per-warp log tables W|V (prologue only)
-  const int T = blockDim.x;
-  double* dco = sm + B * T;
-  {
-    // derivative of the per-span basis polynomials: dco[k][j][m] = (j+1) * coef[k][m][j+1]
-    for (int i = threadIdx.x; i < NS * 12; i += blockDim.x) {
-      const int k = i / 12, j = (i % 12) / 4, m = i % 4;
-      dco[i] = (double)(j + 1) * p.bs_coef[(k * 4 + m) * 4 + j + 1];
-    }
-  }
-  __syncthreads();
+  // shared: the lanes' class tables W^v [B][T] | per-warp log tables W|V (prologue only)
   const int slice = blockIdx.y * (T >> 5) + warp;
-  if (slice >= p.nslices[pair]) return;
+  if (slice >= p.nslices[pair]) return;  // (no block-wide barrier below)
   const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
   const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
   double* wq = sm + threadIdx.x;  // wq[t * T]
   // ---- class table of the lane's task (class v, cell of the slice):
   //   Wv[t] = V[t] + sum_kk w_ref,v[kk] W[k_r(v)+kk][t]     (class 256: V only)
-  // from the cell's scaled log tables W|V (k_assemble), staged per warp with rows padded to B+1. Pass 2 then needs
-  //   c_i = sum_m N'_{k+m}(u_i) * Wv[k+m]   per pixel (types_six_dof_expmap.cpp:467-528 re-associated).
+  // from the cell's scaled log tables W|V (k_assemble), staged per warp with rows padded to B+1, then folded onto
+  // the uniform basis (fold_table). Pass 2 then needs  c_i = sum_m U'_m(f_i) * W^v[k_i+m]  per pixel
+  // (types_six_dof_expmap.cpp:467-528 re-associated).
   {
     const int BP = B + 1;
-    double* Ww = dco + NS * 12 + warp * (B * BP + B);
+    double* Ww = sm + B * T + warp * (B * BP + B);
     double* Vw = Ww + B * BP;
     const int desc = task >= 0 ? p.tasks[(size_t)pair * p.max_tasks + task].y : 0;
     const int cell = __shfl_sync(0xffffffffu, (desc >> 18) & 0x3fff, 0);  // lane 0 always owns a task
@@ -773,6 +769,7 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
         for (int kk = 0; kk < 4; kk++) a += wr[kk] * Wr[kk * BP + t];
         wq[t * T] = a;
       }
+      fold_table(wq, T, B);
     }
   }
   const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
@@ -792,7 +789,7 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
     Group<PTS> Gn = G;
     if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
 #pragma unroll
-    for (int j0 = 0; j0 < 4; j0 += W) jac_pixels<PTS, W>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, dco, T, acc);
+    for (int j0 = 0; j0 < 4; j0 += NID_JAC_W) jac_pixels<PTS, NID_JAC_W, T>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, acc);
     G = Gn;
   }
   // one partial per slice: fixed-order butterfly over the 32 lanes (lanes without a task hold zeros)
@@ -886,10 +883,10 @@ int launch_pack_tex(nid_ctx* c, int pair, unsigned* d_out) {
   return NID_OK;
 }
 
-size_t hist_sell_smem(const nid_ctx* c, int T = 256) { return sizeof(double) * ((size_t)c->bins * T + (size_t)(c->bins - 3) * 16); }
+size_t hist_sell_smem(const nid_ctx* c, int T = 256) { return sizeof(double) * ((size_t)c->bins * T); }
 size_t jac_sell_smem(const nid_ctx* c, int T = 128) {
-  const size_t B = c->bins, NS = B - 3;
-  return sizeof(double) * (B * T + NS * 12 + (size_t)(T / 32) * (B * (B + 1) + B));
+  const size_t B = c->bins;
+  return sizeof(double) * (B * T + (size_t)(T / 32) * (B * (B + 1) + B));
 }
 
 // Threads per CTA of the pixel kernels: the largest of 32..tmax that still gives every SM about two CTAs; a
@@ -938,8 +935,12 @@ static void launch_hist_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0
     EvalParams q = p;
     q.job0 = job0 + s0;
     const dim3 grid(n, (ns + T / 32 - 1) / (T / 32));
-    if (c->opt_ilp_hist <= 2) k_hist_sell<PTS, 2, NG><<<grid, T, sm, c->stream>>>(q, gt);
-    else k_hist_sell<PTS, 4, NG><<<grid, T, sm, c->stream>>>(q, gt);
+    switch (T) {
+      case 256: k_hist_sell<PTS, NG, 256><<<grid, 256, sm, c->stream>>>(q, gt); break;
+      case 128: k_hist_sell<PTS, NG, 128><<<grid, 128, sm, c->stream>>>(q, gt); break;
+      case 64: k_hist_sell<PTS, NG, 64><<<grid, 64, sm, c->stream>>>(q, gt); break;
+      default: k_hist_sell<PTS, NG, 32><<<grid, 32, sm, c->stream>>>(q, gt); break;
+    }
     c->launches++;
   }
 }
@@ -954,9 +955,11 @@ static void launch_jac_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0,
     EvalParams q = p;
     q.job0 = job0 + s0;
     const dim3 grid(n, (ns + T / 32 - 1) / (T / 32));
-    if (c->opt_ilp_jac <= 1) k_jac_sell<PTS, 1, NG><<<grid, T, sm, c->stream>>>(q, gt);
-    else if (c->opt_ilp_jac == 2) k_jac_sell<PTS, 2, NG><<<grid, T, sm, c->stream>>>(q, gt);
-    else k_jac_sell<PTS, 4, NG><<<grid, T, sm, c->stream>>>(q, gt);
+    switch (T) {
+      case 128: k_jac_sell<PTS, NG, 128><<<grid, 128, sm, c->stream>>>(q, gt); break;
+      case 64: k_jac_sell<PTS, NG, 64><<<grid, 64, sm, c->stream>>>(q, gt); break;
+      default: k_jac_sell<PTS, NG, 32><<<grid, 32, sm, c->stream>>>(q, gt); break;
+    }
     c->launches++;
   }
 }
@@ -1019,12 +1022,14 @@ int sorted_init(nid_ctx* c) {
 #define NID_SMEM_ATTR(k, bytes)                                                                     \
   e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));            \
   if (e != cudaSuccess) return check_cuda(e, "smem attr " #k);
-#define NID_SMEM_ATTR_PX(PTS, NG)                                        \
-  NID_SMEM_ATTR((k_hist_sell<PTS, 2, NG>), hist_sell_smem(c));           \
-  NID_SMEM_ATTR((k_hist_sell<PTS, 4, NG>), hist_sell_smem(c));           \
-  NID_SMEM_ATTR((k_jac_sell<PTS, 1, NG>), jac_sell_smem(c));             \
-  NID_SMEM_ATTR((k_jac_sell<PTS, 2, NG>), jac_sell_smem(c));             \
-  NID_SMEM_ATTR((k_jac_sell<PTS, 4, NG>), jac_sell_smem(c));
+#define NID_SMEM_ATTR_PX(PTS, NG)                                           \
+  NID_SMEM_ATTR((k_hist_sell<PTS, NG, 256>), hist_sell_smem(c, 256));       \
+  NID_SMEM_ATTR((k_hist_sell<PTS, NG, 128>), hist_sell_smem(c, 128));       \
+  NID_SMEM_ATTR((k_hist_sell<PTS, NG, 64>), hist_sell_smem(c, 64));         \
+  NID_SMEM_ATTR((k_hist_sell<PTS, NG, 32>), hist_sell_smem(c, 32));         \
+  NID_SMEM_ATTR((k_jac_sell<PTS, NG, 128>), jac_sell_smem(c, 128));         \
+  NID_SMEM_ATTR((k_jac_sell<PTS, NG, 64>), jac_sell_smem(c, 64));           \
+  NID_SMEM_ATTR((k_jac_sell<PTS, NG, 32>), jac_sell_smem(c, 32));
   NID_SMEM_ATTR_PX(true, NID_GEO_SMALL)
   NID_SMEM_ATTR_PX(false, NID_GEO_SMALL)
   NID_SMEM_ATTR_PX(true, NID_GEO_LARGE)
