@@ -351,10 +351,18 @@ struct ExactSrc {
   const double* cam;  // fx fy cx cy
 };
 
+// where the current group of the lane lives in the pixel store: the rare paths re-read a pixel from there, so that
+// the group's registers are free once the fast front end has consumed them
+struct GroupAddr {
+  const double *q0, *q1, *q2;
+  const unsigned* qi;
+};
+
 template <bool PTS>
-__device__ __forceinline__ void make_exact(const ExactSrc& xs, int rows, int cols, double a0, double a1, double a2, unsigned id,
-                                           Px& r) {
+__device__ __forceinline__ void make_exact(const ExactSrc& xs, int rows, int cols, const GroupAddr& ga, int j, Px& r) {
   double ex[5];
+  const double a0 = ga.q0[j], a1 = PTS ? ga.q1[j] : 0.0, a2 = PTS ? ga.q2[j] : 0.0;
+  const unsigned id = ga.qi[j];
   exact_uv<PTS>(xs.T1, xs.T0, xs.cam, a0, a1, a2, id, ex);
   px_from_exact(ex, rows, cols, r);
 }
@@ -365,8 +373,9 @@ __device__ __forceinline__ void make_exact(const ExactSrc& xs, int rows, int col
 // n0 counts the lane's pixels with u == 0 exactly (see bspline4_uniform).
 template <bool PTS, int W, int T>
 __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const ExactSrc& xs, int rows, int cols,
-                                            const Group<PTS>& G, int j0, const unsigned* __restrict__ fp, double s, int NS,
-                                            double* __restrict__ h, int& n0) {
+                                            const Group<PTS>& G, int j0, const GroupAddr& ga,
+                                            const unsigned* __restrict__ fp, double s, int NS, double* __restrict__ h,
+                                            int& n0) {
   Px r[W];
   bool anyexact = false;
 #pragma unroll
@@ -377,7 +386,7 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
   if (anyexact) {
 #pragma unroll
     for (int j = 0; j < W; j++)
-      if (r[j].fix) make_exact<PTS>(xs, rows, cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
+      if (r[j].fix) make_exact<PTS>(xs, rows, cols, ga, j0 + j, r[j]);
   }
   unsigned t[W];
 #pragma unroll
@@ -392,19 +401,15 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
 #pragma unroll
     for (int j = 0; j < W; j++)
       if (r[j].ok && !r[j].exact && t[j] == 0xffffffffu) {
-        make_exact<PTS>(xs, rows, cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
+        make_exact<PTS>(xs, rows, cols, ga, j0 + j, r[j]);
         t[j] = __ldg(fp + (unsigned)(r[j].iy * cols + r[j].ix));
       }
   }
   double ic[W];
 #pragma unroll
   for (int j = 0; j < W; j++) {
-    // 2^52 + tap as a double (byte extract straight into the low word); differences of two such are exact
-    const double e00 = __hiloint2double(0x43300000, (int)__byte_perm(t[j], 0, 0x4440));
-    const double e01 = __hiloint2double(0x43300000, (int)__byte_perm(t[j], 0, 0x4441));
-    const double e10 = __hiloint2double(0x43300000, (int)__byte_perm(t[j], 0, 0x4442));
-    const double e11 = __hiloint2double(0x43300000, (int)__byte_perm(t[j], 0, 0x4443));
-    ic[j] = bilinear_fast(r[j].dx, r[j].dy, e00 - 4503599627370496.0, e01 - e00, e10 - 4503599627370496.0, e11 - e10);
+    const int p00 = t[j] & 0xffu, p01 = (t[j] >> 8) & 0xffu, p10 = (t[j] >> 16) & 0xffu, p11 = t[j] >> 24;
+    ic[j] = bilinear_fast(r[j].dx, r[j].dy, u2d(p00), i2d_small(p01 - p00), u2d(p10), i2d_small(p11 - p10));
   }
   if (anyexact) {
 #pragma unroll
@@ -440,8 +445,15 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
 // that every SM gets work); shared: rows [B][T]. The job index is the fast grid dimension and slices are ordered
 // longest first, so the long CTAs of every job start first and the short ones fill the tail. The next group's
 // pixels are loaded before the current group is processed. NID_HIST_W pixels of a lane are in flight together.
+#ifndef NID_HIST_W
 #define NID_HIST_W 4
+#endif
+#ifndef NID_JAC_W
 #define NID_JAC_W 2
+#endif
+#ifndef NID_JAC_INTTAP
+#define NID_JAC_INTTAP 0
+#endif
 #ifndef NID_HIST_MINB
 #define NID_HIST_MINB 2  // CTAs of 256 threads per SM (128 registers)
 #endif
@@ -478,8 +490,10 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
   for (int gi = 0; gi < ngroups; gi++) {
     Group<PTS> Gn = G;
     if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
+    const size_t go = (size_t)gi * 128;
+    const GroupAddr ga{q0 + go, PTS ? q1 + go : nullptr, PTS ? q2 + go : nullptr, qi + go};
 #pragma unroll
-    for (int j0 = 0; j0 < 4; j0 += NID_HIST_W) hist_pixels<PTS, NID_HIST_W, T>(g, xs, p.rows, p.cols, G, j0, fp, s, NS, h, n0);
+    for (int j0 = 0; j0 < 4; j0 += NID_HIST_W) hist_pixels<PTS, NID_HIST_W, T>(g, xs, p.rows, p.cols, G, j0, ga, fp, s, NS, h, n0);
     G = Gn;
   }
   fold_row(h, T, B, (double)n0);  // uniform sums -> sums of the reference's clamped basis
@@ -677,6 +691,14 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
 #pragma unroll
   for (int j = 0; j < W; j++) {
     // texel = I | (Gx+256) << 8 | (Gy+256) << 17; the biases cancel in the differences
+#if NID_JAC_INTTAP
+    const int i00 = t[j].w & 0xffu, i01 = t[j].z & 0xffu, i10 = t[j].x & 0xffu, i11 = t[j].y & 0xffu;
+    const int x00 = (t[j].w >> 8) & 0x1ffu, x01 = (t[j].z >> 8) & 0x1ffu, x10 = (t[j].x >> 8) & 0x1ffu, x11 = (t[j].y >> 8) & 0x1ffu;
+    const int y00 = t[j].w >> 17, y01 = t[j].z >> 17, y10 = t[j].x >> 17, y11 = t[j].y >> 17;
+    double ic = bilinear_fast(r[j].dx, r[j].dy, u2d(i00), i2d_small(i01 - i00), u2d(i10), i2d_small(i11 - i10));
+    double gx2 = bilinear_fast(r[j].dx, r[j].dy, i2d_small(x00 - 256), i2d_small(x01 - x00), i2d_small(x10 - 256), i2d_small(x11 - x10));
+    double gy2 = bilinear_fast(r[j].dx, r[j].dy, i2d_small(y00 - 256), i2d_small(y01 - y00), i2d_small(y10 - 256), i2d_small(y11 - y10));
+#else
     const double two52 = 4503599627370496.0;
     const double i00 = tapd(t[j].w & 0xffu), i01 = tapd(t[j].z & 0xffu), i10 = tapd(t[j].x & 0xffu), i11 = tapd(t[j].y & 0xffu);
     const double x00 = tapd((t[j].w >> 8) & 0x1ffu), x01 = tapd((t[j].z >> 8) & 0x1ffu);
@@ -685,6 +707,7 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
     double ic = bilinear_fast(r[j].dx, r[j].dy, i00 - two52, i01 - i00, i10 - two52, i11 - i10);
     double gx2 = bilinear_fast(r[j].dx, r[j].dy, x00 - (two52 + 256.0), x01 - x00, x10 - (two52 + 256.0), x11 - x10);
     double gy2 = bilinear_fast(r[j].dx, r[j].dy, y00 - (two52 + 256.0), y01 - y00, y10 - (two52 + 256.0), y11 - y10);
+#endif
     // rare: undecided by the fast path, saturated plateau, or first image row / column
     const bool sat = (t[j].w & t[j].z & t[j].x & t[j].y & 0xffu) == 0xffu;
     if (r[j].fix || (r[j].jac && (sat || r[j].ix < 1 || r[j].iy < 1))) {
