@@ -63,7 +63,7 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.sl_off = c->sl_off; p.sl_task = c->sl_task; p.nslices = c->nslices;
   p.sell_cap = c->sell_cap; p.max_slices = c->max_slices; p.Twc0 = c->Twc0;
   p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start; p.cell_slice_start = c->cell_slice_start;
-  p.cls_task_start = c->cls_task_start; p.span_start = c->span_start; p.hvs = c->hvs; p.wv = c->wv;
+  p.cls_task_start = c->cls_task_start; p.span_start = c->span_start; p.wv = c->wv;
   p.max_tasks = c->max_tasks; p.g_stride = (int)c->g_stride;
   p.G = c->G; p.fp1 = c->fp1; p.tex2 = c->d_tex2;
   return p;
@@ -134,7 +134,6 @@ int ensure_job_buffers(nid_ctx* c) {
     }
     if (!c->jpart_s) OKR(dalloc(&c->jpart_s, J * (size_t)c->max_slices * 6, "jpart_s"));  // one partial per slice
     if (!c->wv) OKR(dalloc(&c->wv, J * NC * hs, "wv"));
-    if (!c->hvs) OKR(dalloc(&c->hvs, J * NC * NID_NCLS * (size_t)c->bins, "hvs"));
   } else if (!c->part) {
     c->part_slots = J + 2 * (size_t)c->sm_count + 64;
     OKR(dalloc(&c->part, c->part_slots * NC * hs, "part"));
@@ -322,7 +321,7 @@ int nid_destroy(nid_ctx* c) {
                   c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
                   c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
                   c->bs_coef, c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->nslices, c->task_pos,
-                  c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->fp1, c->cls_task_start, c->span_start, c->hvs, c->wv};
+                  c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->fp1, c->cls_task_start, c->span_start, c->wv};
   for (auto t : c->h_tex2) if (t) cudaDestroyTextureObject(t);
   for (auto arr : c->tex2_arrays) if (arr) cudaFreeArray(arr);
   for (void* p : ptrs) if (p) cudaFree(p);

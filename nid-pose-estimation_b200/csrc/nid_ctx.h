@@ -64,7 +64,6 @@ struct EvalParams {
   const int* cell_slice_start; // [n_pairs][ncell+1] first slice of every cell (slices never mix cells)
   const int* cls_task_start;   // [n_pairs][ncell][NID_NCLS+1] first task of every class
   const int* span_start;       // [bins-2] first class whose k_r is >= k (classes of span k: [k], [k+1])
-  double* hvs;                 // [jobs][ncell][NID_NCLS][bins] per-class soft histograms (class_sum -> assemble)
   double* wv;                  // [jobs][ncell][bins*bins+bins] scaled log tables (assemble -> pass 2)
   int max_tasks;        // task-table stride per pair
   int g_stride;         // partial-buffer stride per job (tasks)
@@ -109,7 +108,6 @@ struct nid_ctx {
   int* cell_slice_start = nullptr;
   int* cls_task_start = nullptr;
   int* span_start = nullptr;
-  double* hvs = nullptr;
   double* wv = nullptr;
   int max_tasks = 0;
   std::vector<int> h_ntasks;

@@ -534,24 +534,6 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-class soft histograms: hvs[job][cell][v][t] = sum over the tasks of class v (task order) of G[task][t].
-// One thread per output, grid (ceil(257*B/256), ncell, jobs): ~1.6 M independent short sums, full occupancy.
-__global__ void __launch_bounds__(256) k_class_sum(EvalParams p) {
-  const int B = p.bins;
-  const int c = blockIdx.y, job = blockIdx.z + p.job0;
-  const int pair = p.job_pair[job];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= NID_NCLS * B) return;
-  if (p.n_c[pair * p.ncell + c] < NID_MIN_CELL_POINTS) return;
-  const int v = i / B, tt = i % B;
-  const int* cts = p.cls_task_start + ((size_t)pair * p.ncell + c) * (NID_NCLS + 1);
-  const int t0 = cts[v], t1 = cts[v + 1];
-  const double* G = p.G + (size_t)job * p.g_stride * B + tt;
-  double hv = 0.0;
-  for (int t = t0; t < t1; t++) hv += G[(size_t)t * B];
-  p.hvs[((size_t)job * p.ncell + c) * (NID_NCLS * B) + i] = hv;
-}
-
 // Assembly (a7 + table half of a8): one CTA per (cell, job). From the per-class soft histograms h_v,
 //     P_j[r][t] = sum_kk sum_{v: k_r(v) = r-kk} w_ref,v[kk] * h_v[t]     (kk = 0..3, classes in order)
 //     P_t[t]    = sum_v h_v[t]
@@ -564,6 +546,8 @@ __global__ void __launch_bounds__(256) k_class_sum(EvalParams p) {
 __global__ void __launch_bounds__(NID_ASM_THREADS, 2) k_assemble(EvalParams p, int want_jac) {
   extern __shared__ double sm[];
   __shared__ double scratch[NID_ASM_THREADS / 32];
+  __shared__ int s_cts[NID_NCLS + 1];
+  __shared__ int s_bnd[NID_ASM_THREADS / 8 + 2];
   const int B = p.bins, BB = B * B, NS = B - 3;
   double* Pall = sm;                    // [BB + B]
   double* red = sm + BB + B;            // [NID_ASM_THREADS] partial sums of P_t
@@ -578,10 +562,52 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, 2) k_assemble(EvalParams p, i
     if (threadIdx.x == 0) { p.ht[o] = nan(""); p.hj[o] = nan(""); p.err[o] = nan(""); }
     return;
   }
+  // ---- per-class soft histograms h_v[t] = sum over the tasks of class v (task order) of G[task][t], straight from
+  // pass 1's task rows. The cell's tasks are one contiguous range ordered by class; the 257 classes are cut into
+  // NID_ASM_THREADS/B runs of about equal task count, and thread (run, t) streams through its run with eight
+  // independent row loads in flight, closing a class whenever the task index passes the class's end.
   {
-    const double* src = p.hvs + o * (size_t)(NID_NCLS * B);
-    for (int i = threadIdx.x; i < NID_NCLS * B; i += blockDim.x) hvs[i] = src[i];
+    const int* cts = p.cls_task_start + ((size_t)pair * p.ncell + c) * (NID_NCLS + 1);
+    for (int i = threadIdx.x; i <= NID_NCLS; i += blockDim.x) s_cts[i] = cts[i];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) wl[i] = p.lut_w[i];
+    __syncthreads();
+    const int ng = NID_ASM_THREADS / B;
+    const int tfirst = s_cts[0], ntask = s_cts[NID_NCLS] - tfirst;
+    if ((int)threadIdx.x <= ng) {
+      const int target = tfirst + (int)(((long long)threadIdx.x * ntask) / ng);
+      int lo = 0, hi = NID_NCLS;  // smallest v with s_cts[v] >= target
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_cts[mid] >= target) hi = mid; else lo = mid + 1;
+      }
+      s_bnd[threadIdx.x] = (int)threadIdx.x == ng ? NID_NCLS : lo;
+    }
+    __syncthreads();
+    const int g = threadIdx.x / B, tt = threadIdx.x % B;
+    if (g < ng) {
+      int v = s_bnd[g];
+      const int vend = s_bnd[g + 1];
+      if (v < vend) {
+        int t = s_cts[v], nxt = s_cts[v + 1];
+        const int tend = s_cts[vend];
+        const double* Gp = p.G + (size_t)job * p.g_stride * B + tt;
+        double acc = 0.0;
+        while (t < tend) {
+          double x[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) x[i] = (t + i < tend) ? Gp[(size_t)(t + i) * B] : 0.0;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            if (t + i < tend) {
+              while (t + i >= nxt) { hvs[v * B + tt] = acc; acc = 0.0; v++; nxt = s_cts[v + 1]; }
+              acc += x[i];
+            }
+          }
+          t += 8;
+        }
+        for (; v < vend; v++) { hvs[v * B + tt] = acc; acc = 0.0; }
+      }
+    }
   }
   __syncthreads();
   // ---- P_j: item (kk, r, t) sums the classes of span r-kk
@@ -1016,8 +1042,6 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
   c->launches--;
   NID_LAUNCH_CHECK(c, "k_hist_sell");
   ktime_mark(c, 1);
-  k_class_sum<<<dim3((NID_NCLS * c->bins + 255) / 256, c->ncell, n_jobs), 256, 0, c->stream>>>(p);
-  NID_LAUNCH_CHECK(c, "k_class_sum");
   k_assemble<<<dim3(c->ncell, n_jobs), NID_ASM_THREADS, assemble_smem(c), c->stream>>>(p, want_jac);
   NID_LAUNCH_CHECK(c, "k_assemble");
   ktime_mark(c, 2);

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 go, pr = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-EVAL = ("k_hist_sell", "k_class_sum", "k_assemble", "k_jac_sell", "k_jac_final_sorted")
+EVAL = ("k_hist_sell", "k_assemble", "k_jac_sell", "k_jac_final_sorted")
 
 
 def short(name):
@@ -56,7 +56,7 @@ keys = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'smsp__pcsamp_warps_issue_stalled_barrier', 'smsp__pcsamp_warps_issue_stalled_branch_resolving']
 traffic = {}
 with open(os.path.join(pr, f"{tag}_ncu_full.txt"), "w") as f:
-    f.write(f"ncu --set full --clock-control none --import-source on -k regex:'k_hist_sell|k_jac_sell|k_assemble|k_class_sum|k_jac_final' -s 10 -c 5 python bench.py --pairs {pairs} --steps 3 --warmup 3\n")
+    f.write(f"ncu --set full --clock-control none --import-source on -k regex:'k_hist_sell|k_jac_sell|k_assemble|k_jac_final' -s 8 -c 4 python bench.py --pairs {pairs} --steps 3 --warmup 3\n")
     f.write(f"one launch = {pairs} cost+Jacobian evaluations of 640x480 pairs (4x4 cells, 16 bins)\n")
     for r in rr[2:]:
         name = short(r[hdr.index('Kernel Name')])
