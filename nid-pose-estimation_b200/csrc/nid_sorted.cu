@@ -542,8 +542,13 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
 //   W[r][t] = coefJ * (1 + log2 P_j[r][t]),  V[t] = coefT * (1 + log2 P_t[t])   (0 where P < 1e-30),
 //   coefJ = -(s/(n_c Hj^2)) (Ht + Href), coefT = (s/(n_c Hj^2)) Hj  (types_six_dof_expmap.cpp:486-528).
 // k_r(v) is monotone in v, so the classes of a span are a contiguous range (span_start).
-#define NID_ASM_THREADS 512
-__global__ void __launch_bounds__(NID_ASM_THREADS, 2) k_assemble(EvalParams p, int want_jac) {
+#ifndef NID_ASM_THREADS
+#define NID_ASM_THREADS 256
+#endif
+#ifndef NID_ASM_MINB
+#define NID_ASM_MINB 4
+#endif
+__global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(EvalParams p, int want_jac) {
   extern __shared__ double sm[];
   __shared__ double scratch[NID_ASM_THREADS / 32];
   __shared__ int s_cts[NID_NCLS + 1];
@@ -590,20 +595,22 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, 2) k_assemble(EvalParams p, i
       if (v < vend) {
         int t = s_cts[v], nxt = s_cts[v + 1];
         const int tend = s_cts[vend];
-        const double* Gp = p.G + (size_t)job * p.g_stride * B + tt;
+        const double* gp = p.G + ((size_t)job * p.g_stride + t) * B + tt;
         double acc = 0.0;
         while (t < tend) {
+          const int rem = tend - t;
           double x[8];
 #pragma unroll
-          for (int i = 0; i < 8; i++) x[i] = (t + i < tend) ? Gp[(size_t)(t + i) * B] : 0.0;
+          for (int i = 0; i < 8; i++) x[i] = (i < rem) ? gp[i * B] : 0.0;
 #pragma unroll
           for (int i = 0; i < 8; i++) {
-            if (t + i < tend) {
+            if (i < rem) {
               while (t + i >= nxt) { hvs[v * B + tt] = acc; acc = 0.0; v++; nxt = s_cts[v + 1]; }
               acc += x[i];
             }
           }
           t += 8;
+          gp += 8 * B;
         }
         for (; v < vend; v++) { hvs[v * B + tt] = acc; acc = 0.0; }
       }
@@ -637,7 +644,9 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, 2) k_assemble(EvalParams p, i
     const double a = ((part[idx] + part[BB + idx]) + part[2 * BB + idx]) + part[3 * BB + idx];
     const double q = a / (double)nc;
     Pall[idx] = q;
-    ej -= (q < kSigma) ? 0.0 : q * log2(q);
+    const double lg = (q < kSigma) ? 0.0 : log2(q);
+    ej -= q * lg;
+    part[idx] = (q < kSigma) ? 0.0 : 1.0 + lg;  // this thread's own slot: 1 + log2 P_j for the tables below
   }
   if ((int)threadIdx.x >= NID_ASM_THREADS - B) {  // the last B threads (idle in the loop above for B <= 22)
     const int tt = threadIdx.x - (NID_ASM_THREADS - B);
@@ -646,7 +655,9 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, 2) k_assemble(EvalParams p, i
     for (int g = 0; g < ng; g++) a += red[g * B + tt];
     const double q = a / (double)nc;
     Pall[BB + tt] = q;
-    et -= (q < kSigma) ? 0.0 : q * log2(q);
+    const double lg = (q < kSigma) ? 0.0 : log2(q);
+    et -= q * lg;
+    red[tt] = (q < kSigma) ? 0.0 : 1.0 + lg;  // (column tt of red belongs to this thread)
   }
   const double Hj = block_sum(ej, scratch);
   const double Ht = block_sum(et, scratch);
@@ -662,11 +673,8 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, 2) k_assemble(EvalParams p, i
     const double coefJ = -s_over * (Ht + Href);
     const double coefT = s_over * Hj;
     double* wv = p.wv + o * (size_t)(BB + B);
-    for (int i = threadIdx.x; i < BB + B; i += blockDim.x) {
-      const double q = Pall[i];
-      const double L = (q < kSigma) ? 0.0 : (1.0 + log2(q));
-      wv[i] = L * (i < BB ? coefJ : coefT);
-    }
+    for (int i = threadIdx.x; i < BB; i += blockDim.x) wv[i] = part[i] * coefJ;
+    if ((int)threadIdx.x < B) wv[BB + threadIdx.x] = red[threadIdx.x] * coefT;
   }
 }
 
