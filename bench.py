@@ -119,10 +119,9 @@ def peaks():
 
 def measured_traffic(kernel, n_evals):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None."""
-    names = {"k_hist": "k_hist_sell", "k_jac": "k_jac_sell"}
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return d["dram_bytes_per_eval"][names[kernel]] * n_evals, d["source"]
+        return d["dram_bytes_per_eval"][kernel] * n_evals, d["source"]
     except Exception:
         return None, None
 
@@ -305,6 +304,25 @@ def main():
     kt = ctx.kernel_times()
     ctx.set_option("time_kernels", 0)
 
+    # ---------------- kernel 1 on its own (warp + sample, north_star kernel (1)): HBM roofline probe
+    probe = None
+    try:
+        for k in range(min(args.warmup, 3)):
+            ctx.warp_sample_jobs(poses[k], job_pair, fetch=False)
+        ctx.event_record(0)
+        for k in range(args.warmup, total_steps):
+            ctx.warp_sample_jobs(poses[k], job_pair, fetch=False)
+        ctx.event_record(1)
+        probe_ms = ctx.event_elapsed_ms() / args.steps
+        probe = {"kernel": "k_warp_sample_jobs", "ms_per_launch": probe_ms,
+                 "algorithmic_bytes_per_launch": ROWS * COLS * 24 * n_slots,
+                 "moved_bytes_per_launch": ROWS * COLS * (8 + 4 + 16) * n_slots,
+                 "note": "one launch = kernel 1 for every pair slot: fp64 depth in, packed 2x2 gather, float4 {I_c, g_x, g_y, "
+                         "valid} out; algorithmic bytes = SURVEY 8(d) 24 B/px; the evaluation path fuses this front end "
+                         "into both passes instead of storing its output"}
+    except Exception as e:  # noqa: BLE001 - the probe must not take the bench line down
+        probe = {"kernel": "k_warp_sample_jobs", "error": str(e)}
+
     # ---------------- complete LM pose solves (optimize(10), reference perturbation), all slots in lockstep
     solve_s, solve_stats = 0.0, None
     if args.solves:
@@ -328,7 +346,7 @@ def main():
         value = evals / (ms * 1e-3)
         e2e_value = evals / (e2e_ms * 1e-3)
         peak, peak_src = peaks()
-        dom = max(("k_hist", "k_jac"), key=lambda n: kt[n][0])
+        dom = max(("k_hist_sell", "k_jac_sell"), key=lambda n: kt[n][0])
         dom_ms = kt[dom][0] / max(kt[dom][1], 1)
         share = {n: kt[n][0] for n in kt}
         tot = sum(share.values()) or 1.0
@@ -364,6 +382,14 @@ def main():
                                        "absent here)"},
             "clocks": clk.summary(),
         }
+        if probe and "ms_per_launch" in probe:
+            probe["achieved"] = probe["algorithmic_bytes_per_launch"] / (probe["ms_per_launch"] * 1e-3) / 1e9
+            probe["moved"] = probe["moved_bytes_per_launch"] / (probe["ms_per_launch"] * 1e-3) / 1e9
+            probe["unit"] = "GB/s"
+            probe["peak"] = peak
+            probe["frac"] = probe["achieved"] / peak
+            probe["frac_moved"] = probe["moved"] / peak
+        line["roofline"]["warp_sample_probe"] = probe
         if args.solves and solve_ms > 0:
             line["pose_solves"] = {"value": n_slots * world / (solve_ms * 1e-3), "unit": "solves/s",
                                    "solves": n_slots * world, "ms": solve_ms,

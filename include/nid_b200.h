@@ -132,6 +132,10 @@ int nid_hard_eval_jobs(nid_ctx* ctx, int n_jobs, const int* job_pair, const doub
  * (valid: 0 invalid, 1 cost only, 3 cost+Jacobian). out: host buffer of 4*rows*cols floats, or NULL
  * to leave the result on the device (timing). */
 int nid_warp_sample(nid_ctx* ctx, int pair, const double T_cw1[16], float* out);
+/* The same kernel-1 record for n_jobs (pair, pose) jobs in one launch, from the pairs' depth planes (fast composed
+ * warp with the exact fallbacks of the evaluation path). out: host buffer of n_jobs*4*rows*cols floats, or NULL to
+ * leave the result on the device (bench.py's HBM-roofline probe). Depth pairs only (nid_set_pair). */
+int nid_warp_sample_jobs(nid_ctx* ctx, int n_jobs, const int* job_pair, const double* poses, float* out);
 /* fp64 per-pixel record for strict parity: out[8*N] = {u,v,I_c,g_x,g_y,valid_cost,valid_jac,p_z} */
 int nid_warp_sample_f64(nid_ctx* ctx, int pair, const double T_cw1[16], double* out);
 

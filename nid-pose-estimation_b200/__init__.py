@@ -68,6 +68,7 @@ def lib():
         L.nid_hard_eval_jobs.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp]
         L.nid_warp_sample.argtypes = [C.c_void_p, C.c_int, _dp, _fp]
         L.nid_warp_sample_f64.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.nid_warp_sample_jobs.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _fp]
         L.nid_debug_hist.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
         L.nid_launch_count.restype = C.c_longlong
         L.nid_launch_count.argtypes = [C.c_void_p]
@@ -235,6 +236,16 @@ class Context:
         _chk(lib().nid_warp_sample(self._h, pair, _d(_f64(T_cw1, 16)), out.ctypes.data_as(_fp) if fetch else None))
         return out
 
+    def warp_sample_jobs(self, poses, job_pair, fetch=True):
+        """Kernel-1 record {I_c, g_x, g_y, valid} of every (pair, pose) job in one launch -> [n_jobs, N, 4] float32."""
+        poses = _f64(poses).reshape(-1, 16)
+        n = poses.shape[0]
+        jp = np.ascontiguousarray(job_pair, dtype=np.int32)
+        out = np.empty((n, self.rows * self.cols, 4), dtype=np.float32) if fetch else None
+        _chk(lib().nid_warp_sample_jobs(self._h, n, jp.ctypes.data_as(_ip), _d(poses),
+                                        out.ctypes.data_as(_fp) if fetch else None))
+        return out
+
     def warp_sample_f64(self, pair, T_cw1):
         out = np.zeros((self.n, 8))
         _chk(lib().nid_warp_sample_f64(self._h, pair, _d(_f64(T_cw1, 16)), _d(out)))
@@ -258,7 +269,7 @@ class Context:
         ms = np.zeros(4)
         calls = np.zeros(4, dtype=np.int64)
         _chk(lib().nid_kernel_times(self._h, _d(ms), calls.ctypes.data_as(C.POINTER(C.c_longlong))))
-        return dict(zip(("k_hist", "k_jac", "k_jac_final", "k_entropy"), zip(ms.tolist(), calls.tolist())))
+        return dict(zip(("k_hist_sell", "k_jac_sell", "k_jac_final_sorted", "k_assemble"), zip(ms.tolist(), calls.tolist())))
 
     def launch_count(self) -> int:
         return int(lib().nid_launch_count(self._h))

@@ -318,7 +318,7 @@ int nid_destroy(nid_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->pwx, c->pwy, c->pwz, c->im0, c->im1, c->inb0, c->n_c, c->href, c->cam, c->Twc0, c->cnt, c->d_depth,
-                  c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
+                  c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_pix4_jobs, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
                   c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
                   c->bs_coef, c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->nslices, c->task_pos,
                   c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->fp1, c->cls_task_start, c->span_start, c->wv};
@@ -821,6 +821,27 @@ int nid_warp_sample(nid_ctx* c, int pair, const double T_cw1[16], float* out) {
   OKR(warp_sample_common(c, pair, T_cw1, 0));
   if (out) CU(cudaMemcpyAsync(out, c->d_pix4, sizeof(float) * 4 * c->N, cudaMemcpyDefault, c->stream), "D2H pix4");
   CU(cudaStreamSynchronize(c->stream), "sync warp_sample");
+  return NID_OK;
+}
+
+int nid_warp_sample_jobs(nid_ctx* c, int n_jobs, const int* job_pair, const double* poses, float* out) {
+  if (!c || !poses) { set_error("bad argument"); return NID_ERR_ARG; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
+  if (n_jobs < 1 || n_jobs > c->max_jobs) { set_error("n_jobs out of range"); return NID_ERR_ARG; }
+  if (c->sell_points) { set_error("nid_warp_sample_jobs needs depth pairs (nid_set_pair), not caller-supplied points"); return NID_ERR_UNSUPPORTED; }
+  if (!c->d_tex2) { set_error("nid_warp_sample_jobs needs the packed target textures (8 to 40 bins)"); return NID_ERR_UNSUPPORTED; }
+  for (int j = 0; j < n_jobs; j++) {
+    const int pr = job_pair ? job_pair[j] : 0;
+    if (pr < 0 || pr >= c->n_pairs || !c->pair_set[pr]) { set_error("job_pair invalid or pair not set"); return NID_ERR_ARG; }
+    c->h_job_pair[j] = pr;
+  }
+  if (!c->d_pix4_jobs) OKR(dalloc(&c->d_pix4_jobs, (size_t)4 * c->N * c->max_jobs, "d_pix4_jobs"));
+  memcpy(c->h_poses, poses, sizeof(double) * 16 * n_jobs);
+  CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16 * n_jobs, cudaMemcpyHostToDevice, c->stream), "H2D poses");
+  CU(cudaMemcpyAsync(c->job_pair, c->h_job_pair, sizeof(int) * n_jobs, cudaMemcpyHostToDevice, c->stream), "H2D job_pair");
+  OKR(launch_warp_sample_jobs(c, n_jobs, (float4*)c->d_pix4_jobs));
+  if (out) CU(cudaMemcpyAsync(out, c->d_pix4_jobs, sizeof(float) * 4 * c->N * (size_t)n_jobs, cudaMemcpyDefault, c->stream), "D2H pix4 jobs");
+  CU(cudaStreamSynchronize(c->stream), "sync warp_sample_jobs");
   return NID_OK;
 }
 

@@ -130,6 +130,7 @@ struct nid_ctx {
   int* d_flag = nullptr;
   double* d_pix = nullptr;     // [8N] scratch for nid_warp_sample_f64
   float* d_pix4 = nullptr;     // [4N] scratch for nid_warp_sample
+  float* d_pix4_jobs = nullptr;  // [max_jobs][4N] output of nid_warp_sample_jobs (allocated on first use)
   double* d_bsv = nullptr;     // [4N] scratch for nid_get_ref_weights
   int* d_bsi = nullptr;        // [N]
   // luts
@@ -201,6 +202,7 @@ int launch_eval_natural(nid_ctx* c, int n_jobs, int want_jac);
 int launch_gn(nid_ctx* c, int n_jobs, double delta);
 int launch_hard(nid_ctx* c, int n_jobs);
 int launch_warp_sample(nid_ctx* c, int pair, const double* d_pose16, int f64);
+int launch_warp_sample_jobs(nid_ctx* c, int n_jobs, float4* d_out);
 int launch_check_integral(nid_ctx* c, const double* d_src, uint8_t* d_dst, int is_ref);
 int launch_chi2(nid_ctx* c, int n_jobs, double delta);
 int launch_eval_mixed(nid_ctx* c, int nj, int nt, double delta);

@@ -298,6 +298,45 @@ def _saturate(p, lo=110, hi=190):
     return dataclasses.replace(p, im0=stretch(p.im0), im1=stretch(p.im1))
 
 
+@pytest.mark.parametrize("kind", ["plain", "saturated", "integer_aligned"])
+def test_warp_sample_jobs_batched_kernel1(nid, orc, make_pair, synth, kind):
+    """The batched kernel-1 launch (fast composed warp + packed gather, bench.py's HBM probe) against the oracle's
+    per-pixel record: validity flags identical, I_c / g_x / g_y to float precision, for several poses of two
+    pairs in one launch; on saturated plateaus and integer-aligned warps the decisions must be the reference's."""
+    import dataclasses
+    pa = make_pair(1003, 120, 160, invalid_depth_frac=0.03)
+    pb = make_pair(1004, 120, 160)
+    if kind == "saturated":
+        pa, pb = _saturate(pa), _saturate(pb)
+    poses = []
+    if kind == "integer_aligned":
+        depth = pb.depth0.copy()
+        depth[0, :] = 0.0
+        depth[:, 0] = 0.0
+        pb = dataclasses.replace(pb, im1=pb.im0.copy(), depth0=depth)
+    ctx = nid.Context(pa.rows, pa.cols, 4, 16, n_pairs=2, max_jobs=4)
+    probs = []
+    for i, p in enumerate((pa, pb)):
+        ctx.set_pair(i, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+        P = orc.Problem(p.im0, p.depth0, p.im1, p.T_wc0, p.intr, 4, 16, threads=4)
+        P.set_quirks(0, 1)
+        probs.append(P)
+    base = [orc.reference_perturbation(pa.T_wc1), orc.reference_perturbation(pb.T_wc1)]
+    if kind == "integer_aligned":
+        base[1] = orc.se3_from_mat16(synth.mat16_inverse(pb.T_wc0))
+    job_pair = [0, 1, 1, 0]
+    xi = np.array([0.002, -0.001, 0.0015, 0.004, -0.003, 0.002])
+    poses = [base[0], base[1], orc.se3_mul(orc.se3_exp(xi), base[1]), orc.se3_mul(orc.se3_exp(-xi), base[0])]
+    got = ctx.warp_sample_jobs(np.stack([orc.se3_to_mat16(q) for q in poses]), job_pair)
+    for j, (pr, pose) in enumerate(zip(job_pair, poses)):
+        exp = probs[pr].pixels(pose)
+        m = ~np.isnan(exp[:, 0])
+        assert np.array_equal(got[j, m, 3], exp[m, 5] + 2 * exp[m, 6])
+        np.testing.assert_allclose(got[j, m, 0], exp[m, 2], rtol=1e-6, atol=1e-5)
+        np.testing.assert_allclose(got[j, m, 1:3], exp[m, 3:5], rtol=1e-6, atol=1e-5)
+        assert np.all(got[j, ~m] == 0)
+
+
 @pytest.mark.parametrize("path", [NATURAL, SORTED])
 def test_saturated_plateaus(nid, orc, make_pair, path):
     """The reference clamps `>= 255 -> 254.999` after the bilinear sample and returns a zero B-spline
