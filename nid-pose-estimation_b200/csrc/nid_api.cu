@@ -331,6 +331,7 @@ int nid_destroy(nid_ctx* c) {
   for (int i = 0; i < 2; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 5; i++) if (c->kev[i]) cudaEventDestroy(c->kev[i]);
   cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   delete c;
   return NID_OK;
 }
@@ -669,6 +670,74 @@ void lm_start_trial(LM& s) {
 }
 }  // namespace
 
+// One LM step of problem s from the 44 doubles {chi2, H[36], b[6], -} of its job
+// (optimization_algorithm_levenberg.cpp:98-141 after a cost+Jacobian job, :173-202 after a trial-pose cost job).
+static void lm_absorb(nid_ctx* c, LM& s, const double* g, int n, int max_iters) {
+  const int maxTrials = 10;
+  const double tau = 1e-5, goodUp = 2. / 3., goodLo = 1. / 3.;
+  if (s.phase == 0) {
+    s.jac_evals++;
+    s.currentChi = g[0];
+    s.iniChi = s.currentChi;
+    memcpy(s.H, g + 1, sizeof(double) * 36);
+    memcpy(s.b, g + 37, sizeof(double) * 6);
+    if (s.it == 0) {
+      double md = 0.;
+      for (int j = 0; j < 6; j++) md = std::max(std::fabs(s.H[7 * j]), md);
+      s.lambda = tau * md;
+      s.ni = 2;
+      s.nBad = 0;
+    }
+    s.rho = 0;
+    s.qmax = 0;
+    lm_start_trial(s);
+    return;
+  }
+  s.cost_evals++;
+  double tempChi = g[0];
+  if (!s.ok2) tempChi = std::numeric_limits<double>::max();
+  double rho = s.currentChi - tempChi;
+  double scale = 0.;
+  for (int j = 0; j < 6; j++) scale += s.x[j] * (s.lambda * s.x[j] + s.b[j]);
+  scale += 1e-3;
+  rho /= scale;
+  if (rho > 0 && std::isfinite(tempChi)) {
+    double alpha = 1. - std::pow((2 * rho - 1), 3);
+    alpha = std::min(alpha, goodUp);
+    double sf = std::max(goodLo, alpha);
+    s.lambda *= sf;
+    s.ni = 2;
+    s.currentChi = tempChi;
+  } else {
+    s.lambda *= s.ni;
+    s.ni *= 2;
+    s.est = s.backup;  // pop
+  }
+  s.rho = rho;
+  s.qmax++;
+  if (rho < 0 && s.qmax < maxTrials) {
+    lm_start_trial(s);
+    return;
+  }
+  bool terminate = (s.qmax == maxTrials || rho == 0);
+  if (!terminate) {
+    if ((s.iniChi - s.currentChi) * 1e3 < s.iniChi) s.nBad++;
+    else s.nBad = 0;
+    if (s.nBad >= 3) terminate = true;
+  }
+  s.it++;
+  s.phase = (!terminate && s.it < max_iters) ? 0 : 2;
+  if (c->lm_trace && n == 1 && s.it <= c->lm_trace_cap) {
+    double* t = c->lm_trace + 10 * (s.it - 1);
+    t[0] = s.currentChi; t[1] = s.lambda; t[2] = s.qmax;
+    memcpy(t + 3, s.est.t, sizeof(double) * 3);
+    memcpy(t + 6, s.est.q, sizeof(double) * 4);
+  }
+}
+
+// Lock-step LM over n problems. The problems are cut into two halves that ping-pong: while the device evaluates the
+// jobs of one half (its own stream and its own range of job slots), the host absorbs the results of the other half,
+// solves the 6x6 systems and stages the next poses. Each problem sees exactly the schedule of a solo solve.
 int nid_solve_jobs(nid_ctx* c, int n, const int* job_pair, double* poses7, int max_iters, double delta, int* stats) {
   if (!c || n < 1 || n > c->max_jobs || !poses7) { set_error("bad argument"); return NID_ERR_ARG; }
   CU(cudaSetDevice(c->device), "cudaSetDevice");
@@ -682,90 +751,57 @@ int nid_solve_jobs(nid_ctx* c, int n, const int* job_pair, double* poses7, int m
     memcpy(s.est.q, poses7 + 7 * j + 3, sizeof(double) * 4);
     s.phase = max_iters > 0 ? 0 : 2;
   }
-  const int maxTrials = 10;
-  const double tau = 1e-5, goodUp = 2. / 3., goodLo = 1. / 3.;
-  std::vector<int> order(n);
-  for (;;) {
-    // jobs: first every problem that needs cost+Jacobian, then every problem with a trial pose
-    int nj = 0, nt = 0;
-    for (int j = 0; j < n; j++) if (st[j].phase == 0) order[nj++] = j;
-    for (int j = 0; j < n; j++) if (st[j].phase == 1) order[nj + nt++] = j;
-    const int na = nj + nt;
-    if (na == 0) break;
-    for (int k = 0; k < na; k++) {
-      nidhost::pose_to_mat16(st[order[k]].est, c->h_poses + 16 * k);
-      c->h_job_pair[k] = st[order[k]].pair;
+  OKR(ensure_job_buffers(c));
+  // (the natural-order kernels size their per-job partial buffers by the job count of a launch: one range there)
+  const int nh = (n >= 8 && use_sorted(c)) ? 2 : 1;
+  if (nh == 2 && !c->stream2) {
+    CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking), "cudaStreamCreate (LM)");
+  }
+  CU(cudaStreamSynchronize(c->stream), "sync before LM");
+  struct Half { int lo, hi, base, na; std::vector<int> order; cudaStream_t stream; };
+  Half H[2];
+  H[0] = {0, nh == 2 ? n / 2 : n, 0, 0, {}, c->stream};
+  H[1] = {n / 2, n, n / 2, 0, {}, c->stream2};
+  cudaStream_t const main_stream = c->stream;
+  int rc = NID_OK;
+  // stage and launch the jobs of half h: first every problem that needs cost+Jacobian, then every trial pose
+  auto issue = [&](Half& h) -> int {
+    h.order.clear();
+    int nj = 0;
+    for (int j = h.lo; j < h.hi; j++) if (st[j].phase == 0) { h.order.push_back(j); nj++; }
+    for (int j = h.lo; j < h.hi; j++) if (st[j].phase == 1) h.order.push_back(j);
+    h.na = (int)h.order.size();
+    if (h.na == 0) return NID_OK;
+    for (int k = 0; k < h.na; k++) {
+      nidhost::pose_to_mat16(st[h.order[k]].est, c->h_poses + 16 * (size_t)(h.base + k));
+      c->h_job_pair[h.base + k] = st[h.order[k]].pair;
     }
-    CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16 * na, cudaMemcpyHostToDevice, c->stream), "H2D poses");
-    CU(cudaMemcpyAsync(c->job_pair, c->h_job_pair, sizeof(int) * na, cudaMemcpyHostToDevice, c->stream), "H2D job_pair");
-    OKR(launch_eval_mixed(c, nj, nt, delta));
-    CU(cudaMemcpyAsync(c->h_out, c->gn, sizeof(double) * 44 * na, cudaMemcpyDeviceToHost, c->stream), "D2H gn");
-    CU(cudaStreamSynchronize(c->stream), "sync lm");
-    for (int k = 0; k < na; k++) {
-      LM& s = st[order[k]];
-      const double* g = c->h_out + 44 * k;
-      if (s.phase == 0) {
-        // optimization_algorithm_levenberg.cpp:98-141
-        s.jac_evals++;
-        s.currentChi = g[0];
-        s.iniChi = s.currentChi;
-        memcpy(s.H, g + 1, sizeof(double) * 36);
-        memcpy(s.b, g + 37, sizeof(double) * 6);
-        if (s.it == 0) {
-          double md = 0.;
-          for (int j = 0; j < 6; j++) md = std::max(std::fabs(s.H[7 * j]), md);
-          s.lambda = tau * md;
-          s.ni = 2;
-          s.nBad = 0;
-        }
-        s.rho = 0;
-        s.qmax = 0;
-        lm_start_trial(s);
-      } else {
-        // :173-202
-        s.cost_evals++;
-        double tempChi = g[0];
-        if (!s.ok2) tempChi = std::numeric_limits<double>::max();
-        double rho = s.currentChi - tempChi;
-        double scale = 0.;
-        for (int j = 0; j < 6; j++) scale += s.x[j] * (s.lambda * s.x[j] + s.b[j]);
-        scale += 1e-3;
-        rho /= scale;
-        if (rho > 0 && std::isfinite(tempChi)) {
-          double alpha = 1. - std::pow((2 * rho - 1), 3);
-          alpha = std::min(alpha, goodUp);
-          double sf = std::max(goodLo, alpha);
-          s.lambda *= sf;
-          s.ni = 2;
-          s.currentChi = tempChi;
-        } else {
-          s.lambda *= s.ni;
-          s.ni *= 2;
-          s.est = s.backup;  // pop
-        }
-        s.rho = rho;
-        s.qmax++;
-        if (rho < 0 && s.qmax < maxTrials) {
-          lm_start_trial(s);
-        } else {
-          bool terminate = (s.qmax == maxTrials || rho == 0);
-          if (!terminate) {
-            if ((s.iniChi - s.currentChi) * 1e3 < s.iniChi) s.nBad++;
-            else s.nBad = 0;
-            if (s.nBad >= 3) terminate = true;
-          }
-          s.it++;
-          s.phase = (!terminate && s.it < max_iters) ? 0 : 2;
-          if (c->lm_trace && n == 1 && s.it <= c->lm_trace_cap) {
-            double* t = c->lm_trace + 10 * (s.it - 1);
-            t[0] = s.currentChi; t[1] = s.lambda; t[2] = s.qmax;
-            memcpy(t + 3, s.est.t, sizeof(double) * 3);
-            memcpy(t + 6, s.est.q, sizeof(double) * 4);
-          }
-        }
-      }
+    CU(cudaMemcpyAsync(c->poses + 16 * (size_t)h.base, c->h_poses + 16 * (size_t)h.base, sizeof(double) * 16 * h.na,
+                       cudaMemcpyHostToDevice, h.stream), "H2D poses");
+    CU(cudaMemcpyAsync(c->job_pair + h.base, c->h_job_pair + h.base, sizeof(int) * h.na, cudaMemcpyHostToDevice, h.stream),
+       "H2D job_pair");
+    c->stream = h.stream;  // the launchers issue on the context's current stream
+    const int r = launch_eval_mixed(c, h.base, nj, h.na - nj, delta);
+    c->stream = main_stream;
+    if (r != NID_OK) return r;
+    CU(cudaMemcpyAsync(c->h_out + 44 * (size_t)h.base, c->gn + 44 * (size_t)h.base, sizeof(double) * 44 * h.na,
+                       cudaMemcpyDeviceToHost, h.stream), "D2H gn");
+    return NID_OK;
+  };
+  for (int i = 0; i < nh && rc == NID_OK; i++) rc = issue(H[i]);
+  while (rc == NID_OK && (H[0].na > 0 || (nh == 2 && H[1].na > 0))) {
+    for (int i = 0; i < nh && rc == NID_OK; i++) {
+      Half& h = H[i];
+      if (h.na == 0) continue;
+      if (cudaStreamSynchronize(h.stream) != cudaSuccess) { rc = check_cuda(cudaGetLastError(), "sync lm"); break; }
+      for (int k = 0; k < h.na; k++) lm_absorb(c, st[h.order[k]], c->h_out + 44 * (size_t)(h.base + k), n, max_iters);
+      rc = issue(h);
     }
   }
+  c->stream = main_stream;
+  if (nh == 2) cudaStreamSynchronize(c->stream2);
+  cudaStreamSynchronize(main_stream);
+  if (rc != NID_OK) return rc;
   for (int j = 0; j < n; j++) {
     memcpy(poses7 + 7 * j, st[j].est.t, sizeof(double) * 3);
     memcpy(poses7 + 7 * j + 3, st[j].est.q, sizeof(double) * 4);

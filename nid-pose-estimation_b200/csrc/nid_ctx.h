@@ -81,6 +81,7 @@ struct nid_ctx {
   int n_pairs = 0, max_jobs = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second stream of the ping-pong LM driver (nid_solve_jobs)
   long long launches = 0;
 
   // per pair
@@ -205,7 +206,7 @@ int launch_warp_sample(nid_ctx* c, int pair, const double* d_pose16, int f64);
 int launch_warp_sample_jobs(nid_ctx* c, int n_jobs, float4* d_out);
 int launch_check_integral(nid_ctx* c, const double* d_src, uint8_t* d_dst, int is_ref);
 int launch_chi2(nid_ctx* c, int n_jobs, double delta);
-int launch_eval_mixed(nid_ctx* c, int nj, int nt, double delta);
+int launch_eval_mixed(nid_ctx* c, int base, int nj, int nt, double delta);
 int launch_points_soa(nid_ctx* c, int pair, const double* d_in);
 int launch_import_flags(nid_ctx* c, int pair, const double* d_bsv);
 }  // namespace nid

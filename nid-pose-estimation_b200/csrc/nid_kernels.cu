@@ -664,19 +664,21 @@ int launch_eval_natural(nid_ctx* c, int n_jobs, int want_jac) {
   return NID_OK;
 }
 
-// LM lockstep round: jobs [0,nj) want cost+Jacobian+GN block, jobs [nj,nj+nt) want the robust cost only
-int launch_eval_mixed(nid_ctx* c, int nj, int nt, double delta) {
+// Jobs [base, base + nj) get cost + Jacobian + the Gauss-Newton block, jobs [base + nj, base + nj + nt) the cost and
+// chi2 only; everything is issued on the context's current stream (the LM driver runs two such ranges on two streams).
+int launch_eval_mixed(nid_ctx* c, int base, int nj, int nt, double delta) {
   const int na = nj + nt;
   int r = ensure_job_buffers(c);
   if (r != NID_OK) return r;
-  EvalParams p = make_params(c, na);
+  EvalParams p = make_params(c, base + na);
   p.huber_delta = delta;
   p.huber_dsqr = (double)(float)(delta * delta);  // `float dsqr`, robust_kernel_impl.h:84
+  p.job0 = base;
   EvalParams q = p;
-  q.job0 = nj;
+  q.job0 = base + nj;
   if (use_sorted(c)) {
-    if (nj > 0) { r = launch_eval_sorted(c, 0, nj, na, 1); if (r != NID_OK) return r; }
-    if (nt > 0) { r = launch_eval_sorted(c, nj, nt, na, 0); if (r != NID_OK) return r; }
+    if (nj > 0) { r = launch_eval_sorted(c, base, nj, base + na, 1); if (r != NID_OK) return r; }
+    if (nt > 0) { r = launch_eval_sorted(c, base + nj, nt, base + na, 0); if (r != NID_OK) return r; }
   } else {
     const size_t smem = sizeof(double) * p.hist_stride;
     k_hist<<<dim3(p.S, p.ncell, na), 256, smem, c->stream>>>(p);

@@ -900,42 +900,62 @@ __global__ void __launch_bounds__(256) k_jac_final_sorted(EvalParams p, int n_jo
 // depth (8 B, coalesced) -> back-projection and SE3 warp with the job's composed matrix -> packed 2x2 gather ->
 // {I_c, g_x, g_y, valid} as one float4 store (valid: 0 invalid, 1 cost only, 3 cost + Jacobian). The decisions
 // (bounds, truncation, saturation clamp) take the same exact fallbacks as pass 2.
+#ifndef NID_WS_ROWS
+#define NID_WS_ROWS 2  // image rows per thread (pixels in flight per lane)
+#endif
+#ifndef NID_WS_MINB
+#define NID_WS_MINB 6
+#endif
 template <int NG>
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(128, NID_WS_MINB)
 k_warp_sample_jobs(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt,
                    const double* __restrict__ depth, float4* __restrict__ out) {
+  constexpr int W = NID_WS_ROWS;
   const int job = blockIdx.x + p.job0;
   const int pair = p.job_pair[job];
   const double* g = gt.g[blockIdx.x];
-  const int bpr = (p.cols + 127) >> 7;  // CTAs per image row
-  const int row = blockIdx.y / bpr, col = (blockIdx.y - row * bpr) * 128 + threadIdx.x;
+  const int bpr = (p.cols + 127) >> 7;  // CTAs per band of W image rows
+  const int band = blockIdx.y / bpr, col = (blockIdx.y - band * bpr) * 128 + threadIdx.x;
   if (col >= p.cols) return;
-  const int i = row * p.cols + col;
-  const double z = depth[(size_t)pair * p.N + i];
-  const unsigned id = ((unsigned)row << 16) | (unsigned)col;
-  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (z >= 0.01 && z <= 100.0) {  // CudaPoints3d.cu:16-19 (NaN point otherwise)
-    Px r;
-    front<false, false>(g, p.rows, p.cols, z, 0.0, 0.0, id, r);
-    const uint4 t = gather_u32(p.tex2[pair], r.ix, r.iy);
+  const int row0 = band * W;
+  const double* dp = depth + (size_t)pair * p.N + col;
+  double z[W];
+#pragma unroll
+  for (int j = 0; j < W; j++) z[j] = (row0 + j < p.rows) ? dp[(size_t)(row0 + j) * p.cols] : 0.0;
+  Px r[W];
+  uint4 t[W];
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    // depth outside [0.01, 100] is a NaN point in the reference (CudaPoints3d.cu:16-19): a padding slot here
+    const bool valid = z[j] >= 0.01 && z[j] <= 100.0;
+    const unsigned id = valid ? (((unsigned)(row0 + j) << 16) | (unsigned)col) : NID_PAD_ID;
+    front<false, false>(g, p.rows, p.cols, valid ? z[j] : 1.0, 0.0, 0.0, id, r[j]);
+    if (!valid) r[j].fix = false;
+  }
+#pragma unroll
+  for (int j = 0; j < W; j++) t[j] = gather_u32(p.tex2[pair], r[j].ix, r[j].iy);
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    if (row0 + j >= p.rows) continue;
     const double two52 = 4503599627370496.0;
-    const double i00 = tapd(t.w & 0xffu), i01 = tapd(t.z & 0xffu), i10 = tapd(t.x & 0xffu), i11 = tapd(t.y & 0xffu);
-    const double x00 = tapd((t.w >> 8) & 0x1ffu), x01 = tapd((t.z >> 8) & 0x1ffu);
-    const double x10 = tapd((t.x >> 8) & 0x1ffu), x11 = tapd((t.y >> 8) & 0x1ffu);
-    const double y00 = tapd(t.w >> 17), y01 = tapd(t.z >> 17), y10 = tapd(t.x >> 17), y11 = tapd(t.y >> 17);
-    double ic = bilinear_fast(r.dx, r.dy, i00 - two52, i01 - i00, i10 - two52, i11 - i10);
-    double gx2 = bilinear_fast(r.dx, r.dy, x00 - (two52 + 256.0), x01 - x00, x10 - (two52 + 256.0), x11 - x10);
-    double gy2 = bilinear_fast(r.dx, r.dy, y00 - (two52 + 256.0), y01 - y00, y10 - (two52 + 256.0), y11 - y10);
-    bool vc = r.ok, vj = r.jac;
-    const bool sat = (t.w & t.z & t.x & t.y & 0xffu) == 0xffu;
-    if (r.fix || (r.ok && (sat || r.ix < 1 || r.iy < 1))) {
+    const double i00 = tapd(t[j].w & 0xffu), i01 = tapd(t[j].z & 0xffu), i10 = tapd(t[j].x & 0xffu), i11 = tapd(t[j].y & 0xffu);
+    const double x00 = tapd((t[j].w >> 8) & 0x1ffu), x01 = tapd((t[j].z >> 8) & 0x1ffu);
+    const double x10 = tapd((t[j].x >> 8) & 0x1ffu), x11 = tapd((t[j].y >> 8) & 0x1ffu);
+    const double y00 = tapd(t[j].w >> 17), y01 = tapd(t[j].z >> 17), y10 = tapd(t[j].x >> 17), y11 = tapd(t[j].y >> 17);
+    double ic = bilinear_fast(r[j].dx, r[j].dy, i00 - two52, i01 - i00, i10 - two52, i11 - i10);
+    double gx2 = bilinear_fast(r[j].dx, r[j].dy, x00 - (two52 + 256.0), x01 - x00, x10 - (two52 + 256.0), x11 - x10);
+    double gy2 = bilinear_fast(r[j].dx, r[j].dy, y00 - (two52 + 256.0), y01 - y00, y10 - (two52 + 256.0), y11 - y10);
+    bool vc = r[j].ok, vj = r[j].jac;
+    const bool sat = (t[j].w & t[j].z & t[j].x & t[j].y & 0xffu) == 0xffu;
+    if (r[j].fix || (r[j].ok && (sat || r[j].ix < 1 || r[j].iy < 1))) {
       // the reference's literal sequence: cost validity and intensity from (u, v), Jacobian validity and gradient
       // from the second projection (types_six_dof_expmap.cpp:562-575, :407-435)
       const double* T1 = p.poses + 16 * job;
       const double* T0 = p.Twc0 + 16 * pair;
       const double* camg = p.cam + 4 * pair;
+      const unsigned id = ((unsigned)(row0 + j) << 16) | (unsigned)col;
       double e[5];
-      exact_uv<false>(T1, T0, camg, z, 0.0, 0.0, id, e);
+      exact_uv<false>(T1, T0, camg, z[j], 0.0, 0.0, id, e);
       vc = inb_cost(e[3], e[4], p.rows, p.cols);
       vj = false;
       ic = 0.0; gx2 = 0.0; gy2 = 0.0;
@@ -943,15 +963,15 @@ k_warp_sample_jobs(const __grid_constant__ EvalParams p, const __grid_constant__
         const uint8_t* im1 = p.im1 + (size_t)pair * p.N;
         ic = clamp_intensity(interp_u8(im1, p.cols, e[3], e[4]));
         double o6[6];
-        vj = jac_pixel_literal<false>(T1, T0, camg, p.rows, p.cols, im1, z, 0.0, 0.0, id, o6);
+        vj = jac_pixel_literal<false>(T1, T0, camg, p.rows, p.cols, im1, z[j], 0.0, 0.0, id, o6);
         if (vj) { gx2 = o6[4]; gy2 = o6[5]; }
       }
     }
     if (!vc) ic = 0.0;
     if (!vj) { gx2 = 0.0; gy2 = 0.0; }
-    o = make_float4((float)ic, (float)(0.5 * gx2), (float)(0.5 * gy2), (float)((vc ? 1 : 0) + (vj ? 2 : 0)));
+    out[(size_t)job * p.N + (size_t)(row0 + j) * p.cols + col] =
+        make_float4((float)ic, (float)(0.5 * gx2), (float)(0.5 * gy2), (float)((vc ? 1 : 0) + (vj ? 2 : 0)));
   }
-  out[(size_t)job * p.N + i] = o;
 }
 
 // ================================================================================================ launchers
@@ -1140,7 +1160,7 @@ int launch_warp_sample_jobs(nid_ctx* c, int n_jobs, float4* d_out) {
     fill_geo(c, gt, s0, n, false);
     EvalParams q = p;
     q.job0 = s0;
-    k_warp_sample_jobs<NID_GEO_LARGE><<<dim3(n, c->rows * bpr), 128, 0, c->stream>>>(q, gt, c->depth, d_out);
+    k_warp_sample_jobs<NID_GEO_LARGE><<<dim3(n, ((c->rows + NID_WS_ROWS - 1) / NID_WS_ROWS) * bpr), 128, 0, c->stream>>>(q, gt, c->depth, d_out);
     NID_LAUNCH_CHECK(c, "k_warp_sample_jobs");
   }
   return NID_OK;
