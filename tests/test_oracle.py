@@ -174,3 +174,32 @@ def test_lm_decreases_cost(orc, make_pair):
     assert 1 <= its <= 10 and counts[0] == its
     assert trace[-1, 0] < chi0
     assert np.all(np.diff(trace[:, 0]) <= 1e-12)  # accepted steps only ever lower the robust cost
+
+
+@pytest.mark.parametrize("bins", [8, 10, 14, 16, 32, 40])
+def test_uniform_basis_fold_equals_clamped_basis(orc, bins):
+    """the sorted kernels evaluate the *uniform* cubic B-spline per pixel and fold a 3x3 block at either
+    end once per task row (values) / class table (derivatives). Check the identity N = A U and N' = A U' against the
+    oracle's Cox-de Boor recursion (types_six_dof_expmap.cpp:738-800) over the whole domain, for every supported B."""
+    NS = bins - 3
+    A = np.eye(bins)
+    A[0, 0] = 6.0
+    A[1, 0], A[1, 1] = -6.0, 1.5
+    A[2, 0], A[2, 1], A[2, 2] = 1.0, -0.5, 1.0
+    A[bins - 1, bins - 1] = 6.0
+    A[bins - 2, bins - 1], A[bins - 2, bins - 2] = -6.0, 1.5
+    A[bins - 3, bins - 1], A[bins - 3, bins - 2], A[bins - 3, bins - 3] = 1.0, -0.5, 1.0
+    rng = np.random.default_rng(7)
+    us = np.concatenate([rng.uniform(0, NS, 400), rng.uniform(0, 2, 100), rng.uniform(NS - 2, NS, 100),
+                         [1e-9, 0.5, 1.0 - 1e-12, NS - 1e-9, 2.0 + 1e-7]])
+    for u in us:
+        k = min(int(u), NS - 1)
+        f = u - k
+        U = np.zeros(bins)
+        dU = np.zeros(bins)
+        U[k:k + 4] = [(1 - f) ** 3 / 6, (3 * f ** 3 - 6 * f ** 2 + 4) / 6, (-3 * f ** 3 + 3 * f ** 2 + 3 * f + 1) / 6, f ** 3 / 6]
+        dU[k:k + 4] = [-(1 - f) ** 2 / 2, (3 * f ** 2 - 4 * f) / 2, (-3 * f ** 2 + 2 * f + 1) / 2, f ** 2 / 2]
+        N = np.array([orc.bspline(j, 4, u, bins) for j in range(bins)])
+        dN = np.array([orc.bspline_der(j, 4, u, bins) for j in range(bins)])
+        np.testing.assert_allclose(A @ U, N, rtol=0, atol=2e-14)
+        np.testing.assert_allclose(A @ dU, dN, rtol=0, atol=2e-13)
