@@ -191,6 +191,7 @@ const char* nid_last_error(void) { return g_err.c_str(); }
 int nid_version(void) { return 100; }
 
 int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins, int degree, int n_pairs, int max_jobs) {
+  cudaGetLastError();  // a stale error of another library in this process must not fail our first launch check
   if (!out) { set_error("ctx out pointer is NULL"); return NID_ERR_ARG; }
   *out = nullptr;
   if (degree != 3) { set_error("only bs_degree == 3 (order-4 B-splines) is supported, as in the reference"); return NID_ERR_UNSUPPORTED; }
@@ -318,7 +319,7 @@ int nid_destroy(nid_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->pwx, c->pwy, c->pwz, c->im0, c->im1, c->inb0, c->n_c, c->href, c->cam, c->Twc0, c->cnt, c->d_depth,
-                  c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_pix4_jobs, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
+                  c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_pix4_jobs, c->chunk_cnt, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
                   c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
                   c->bs_coef, c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->nslices, c->task_pos,
                   c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->fp1, c->cls_task_start, c->span_start, c->wv};
@@ -328,6 +329,8 @@ int nid_destroy(nid_ctx* c) {
   if (c->h_poses) cudaFreeHost(c->h_poses);
   if (c->h_job_pair) cudaFreeHost(c->h_job_pair);
   if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->h_cnt) cudaFreeHost(c->h_cnt);
   for (int i = 0; i < 2; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 5; i++) if (c->kev[i]) cudaEventDestroy(c->kev[i]);
   cudaStreamDestroy(c->stream);
@@ -476,8 +479,16 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
     OKR(dalloc(&c->sd1, (size_t)c->n_pairs * c->sell_cap, "sd1"));
     OKR(dalloc(&c->sd2, (size_t)c->n_pairs * c->sell_cap, "sd2"));
   }
-  std::vector<unsigned int> cnt((size_t)NC * NID_NCLS);
-  CU(cudaMemcpyAsync(cnt.data(), c->cnt + (size_t)pair * NC * NID_NCLS, sizeof(unsigned int) * cnt.size(),
+  const size_t n_cnt = (size_t)NC * NID_NCLS;
+  if (c->h_cnt_cap < n_cnt) {
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    c->h_cnt = nullptr;
+    c->h_cnt_cap = 0;
+    CU(cudaMallocHost((void**)&c->h_cnt, sizeof(unsigned int) * n_cnt), "pinned cnt");
+    c->h_cnt_cap = n_cnt;
+  }
+  const unsigned int* cnt = c->h_cnt;
+  CU(cudaMemcpyAsync(c->h_cnt, c->cnt + (size_t)pair * NC * NID_NCLS, sizeof(unsigned int) * n_cnt,
                      cudaMemcpyDeviceToHost, c->stream), "D2H cnt");
   CU(cudaStreamSynchronize(c->stream), "sync cnt");
   std::vector<int> cts(NC + 1), clsts((size_t)NC * (NID_NCLS + 1));
@@ -535,26 +546,36 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
   const int ns = (int)sl_off.size() - 1;
   css[NC] = ns;
   if ((size_t)off > c->sell_cap || ns > c->max_slices) { set_error("sliced pixel store overflow"); return NID_ERR_STATE; }
-  if (nt) {
-    CU(cudaMemcpyAsync(c->tasks + (size_t)pair * c->max_tasks, tasks.data(), sizeof(int2) * nt, cudaMemcpyHostToDevice,
-                       c->stream), "H2D tasks");
-    CU(cudaMemcpyAsync(c->task_pos + (size_t)pair * c->max_tasks, task_pos.data(), sizeof(int) * nt,
-                       cudaMemcpyHostToDevice, c->stream), "H2D task_pos");
-    CU(cudaMemcpyAsync(c->sl_task + (size_t)pair * c->max_slices * 32, sl_task.data(), sizeof(int) * sl_task.size(),
-                       cudaMemcpyHostToDevice, c->stream), "H2D sl_task");
+  // One pinned staging arena for all tables (the copies are then truly asynchronous; the arena is not reused before
+  // the next nid_prepare's first synchronisation on the same stream).
+  {
+    const size_t n_i = (size_t)2 * nt + nt + sl_task.size() + (ns + 1) + 2 * (size_t)(NC + 1) + clsts.size() + 2;
+    if (c->h_stage_cap < n_i) {
+      if (c->h_stage) cudaFreeHost(c->h_stage);
+      c->h_stage = nullptr;
+      c->h_stage_cap = 0;
+      CU(cudaMallocHost((void**)&c->h_stage, sizeof(int) * (n_i + n_i / 4)), "pinned stage");
+      c->h_stage_cap = n_i + n_i / 4;
+    }
+    int* w = c->h_stage;
+    auto put = [&](void* dst, const void* src, size_t n_ints, const char* what) -> int {
+      if (!n_ints) return NID_OK;
+      memcpy(w, src, sizeof(int) * n_ints);
+      CU(cudaMemcpyAsync(dst, w, sizeof(int) * n_ints, cudaMemcpyHostToDevice, c->stream), what);
+      w += n_ints;
+      return NID_OK;
+    };
+    OKR(put(c->tasks + (size_t)pair * c->max_tasks, tasks.data(), (size_t)2 * nt, "H2D tasks"));
+    OKR(put(c->task_pos + (size_t)pair * c->max_tasks, task_pos.data(), nt, "H2D task_pos"));
+    OKR(put(c->sl_task + (size_t)pair * c->max_slices * 32, sl_task.data(), nt ? sl_task.size() : 0, "H2D sl_task"));
+    OKR(put(c->sl_off + (size_t)pair * (c->max_slices + 1), sl_off.data(), ns + 1, "H2D sl_off"));
+    OKR(put(c->nslices + pair, &ns, 1, "H2D nslices"));
+    OKR(put(c->cell_task_start + (size_t)pair * (NC + 1), cts.data(), NC + 1, "H2D cell_task_start"));
+    OKR(put(c->cell_slice_start + (size_t)pair * (NC + 1), css.data(), NC + 1, "H2D cell_slice_start"));
+    OKR(put(c->ntasks + pair, &nt, 1, "H2D ntasks"));
+    OKR(put(c->cls_task_start + (size_t)pair * NC * (NID_NCLS + 1), clsts.data(), clsts.size(), "H2D cls_task_start"));
   }
-  CU(cudaMemcpyAsync(c->sl_off + (size_t)pair * (c->max_slices + 1), sl_off.data(), sizeof(int) * (ns + 1),
-                     cudaMemcpyHostToDevice, c->stream), "H2D sl_off");
-  CU(cudaMemcpyAsync(c->nslices + pair, &ns, sizeof(int), cudaMemcpyHostToDevice, c->stream), "H2D nslices");
-  CU(cudaMemcpyAsync(c->cell_task_start + (size_t)pair * (NC + 1), cts.data(), sizeof(int) * (NC + 1),
-                     cudaMemcpyHostToDevice, c->stream), "H2D cell_task_start");
-  CU(cudaMemcpyAsync(c->cell_slice_start + (size_t)pair * (NC + 1), css.data(), sizeof(int) * (NC + 1),
-                     cudaMemcpyHostToDevice, c->stream), "H2D cell_slice_start");
-  CU(cudaMemcpyAsync(c->ntasks + pair, &nt, sizeof(int), cudaMemcpyHostToDevice, c->stream), "H2D ntasks");
-  CU(cudaMemcpyAsync(c->cls_task_start + (size_t)pair * NC * (NID_NCLS + 1), clsts.data(), sizeof(int) * clsts.size(),
-                     cudaMemcpyHostToDevice, c->stream), "H2D cls_task_start");
   OKR(launch_scatter(c, pair));
-  CU(cudaStreamSynchronize(c->stream), "sync scatter");  // host vectors go out of scope
   c->h_ntasks[pair] = nt;
   c->h_nslices[pair] = ns;
   c->pair_sorted[pair] = 1;

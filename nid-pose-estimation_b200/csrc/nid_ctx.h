@@ -81,6 +81,11 @@ struct nid_ctx {
   int n_pairs = 0, max_jobs = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  int* h_stage = nullptr;      // pinned staging arena of nid_prepare's tables
+  size_t h_stage_cap = 0;
+  unsigned int* h_cnt = nullptr;  // pinned copy of one pair's (cell, class) counts
+  size_t h_cnt_cap = 0;
+  int* chunk_cnt = nullptr;    // [ncell][chunks of 256 px][NID_NCLS] scratch of the regrouping scatter (nid_prepare)
   cudaStream_t stream2 = nullptr;  // second stream of the ping-pong LM driver (nid_solve_jobs)
   long long launches = 0;
 

@@ -123,18 +123,24 @@ __global__ void k_prepare(EvalParams p, int pair, const double* __restrict__ pos
 
 // a2 part 2: n_c, reference marginal and H_ref per cell (CudaComputeHref.cu:204-221;
 // types_six_dof_expmap.cpp:710-723). One block per cell, one thread per intensity value.
-__global__ void k_href(EvalParams p, int pair, const unsigned int* __restrict__ cnt, int* __restrict__ n_c,
-                       double* __restrict__ href) {
+__global__ void __launch_bounds__(256) k_href(EvalParams p, int pair, const unsigned int* __restrict__ cnt,
+                                              int* __restrict__ n_c, double* __restrict__ href) {
   extern __shared__ double sm[];
   double* pro = sm;  // [bins]
+  __shared__ double s_con[256][4];  // class v's contribution to bins k_r(v) .. k_r(v)+3
+  __shared__ int s_k[256];
   __shared__ unsigned int s_cnt[256];
   __shared__ int s_n;
   const int c = blockIdx.x;
   const unsigned int* cc = cnt + ((size_t)pair * p.ncell + c) * NID_NCLS;
   const int t = threadIdx.x;
-  s_cnt[t] = cc[t];
+  const unsigned int mine = cc[t];
+  s_cnt[t] = mine;
+  s_k[t] = p.lut_k[t];
+#pragma unroll
+  for (int m = 0; m < 4; m++) s_con[t][m] = mine ? (double)mine * p.lut_w[4 * t + m] : 0.0;
   __syncthreads();
-  if (t == 0) {
+  if (t == 32) {  // (a lane of the second warp, so that it runs beside the bin threads)
     int n = 0;
     for (int v = 0; v < 256; v++) n += (int)s_cnt[v];
     s_n = n;
@@ -143,9 +149,8 @@ __global__ void k_href(EvalParams p, int pair, const unsigned int* __restrict__ 
     // fixed order over intensity values -> deterministic
     double acc = 0.0;
     for (int v = 0; v < 256; v++) {
-      int k = p.lut_k[v];
-      int m = t - k;
-      if (m >= 0 && m < 4 && s_cnt[v]) acc += (double)s_cnt[v] * p.lut_w[4 * v + m];
+      const int m = t - s_k[v];
+      if (m >= 0 && m < 4 && s_cnt[v]) acc += s_con[v][m];
     }
     pro[t] = acc;
   }

@@ -61,58 +61,91 @@ __global__ void k_count_classes(EvalParams p, int pair, unsigned int* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// prepare: stable counting-sort scatter of a cell's valid pixels into the sliced-ELL layout. One CTA per
-// cell. key: 0..255 reference intensity (in bounds at the prepare pose), 256 valid but out of bounds,
-// -1 invalid depth. The r-th pixel (row-major order) of class `key` goes to pixel o = r % L of task
-// cls_task_start[key] + r / L, i.e. to  task_pos[task] + (o/4)*128 + o%4.
+// prepare: stable counting-sort scatter of every cell's valid pixels into the sliced-ELL layout, in three launches
+// over (chunk, cell) with chunks of 256 consecutive pixels of the cell (row-major): per-chunk class counts, an exclusive
+// scan of the counts along the chunks of a cell, then the scatter proper. key: 0..255 reference intensity (in
+// bounds at the prepare pose), 256 valid but out of bounds, -1 invalid depth. The r-th pixel (row-major order) of
+// class `key` goes to pixel o = r % L of task cls_task_start[key] + r / L, i.e. to  task_pos[task] + (o/4)*128 + o%4.
 // PTS: store the world point (pairs set from caller-supplied points); else the depth z only.
+__device__ __forceinline__ int sell_key(const EvalParams& p, size_t base, int c, int t, int& row, int& col) {
+  const int npx = p.rb * p.cb;
+  if (t >= npx) return -1;
+  row = (c / p.cell) * p.rb + t / p.cb;
+  col = (c % p.cell) * p.cb + t % p.cb;
+  const size_t i = base + (size_t)row * p.cols + col;
+  if (isnan(p.pwx[i])) return -1;
+  return p.inb0[i] ? (int)p.im0[i] : 256;
+}
+
+__global__ void __launch_bounds__(256) k_chunk_count(EvalParams p, int pair, int* __restrict__ chunk_cnt) {
+  __shared__ int s_cnt[NID_NCLS];
+  const int chunk = blockIdx.x, c = blockIdx.y;
+  for (int k = threadIdx.x; k < NID_NCLS; k += blockDim.x) s_cnt[k] = 0;
+  __syncthreads();
+  int row, col;
+  const int key = sell_key(p, (size_t)pair * p.N, c, chunk * 256 + threadIdx.x, row, col);
+  if (key >= 0) atomicAdd(&s_cnt[key], 1);  // integer counts: order does not matter
+  __syncthreads();
+  int* out = chunk_cnt + ((size_t)c * gridDim.x + chunk) * NID_NCLS;
+  for (int k = threadIdx.x; k < NID_NCLS; k += blockDim.x) out[k] = s_cnt[k];
+}
+
+// in place: chunk_cnt[cell][chunk][class] -> number of pixels of that class in the earlier chunks of the cell
+__global__ void __launch_bounds__(256) k_chunk_scan(int ncell, int nchunks, int* __restrict__ chunk_cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncell * NID_NCLS) return;
+  const int c = i / NID_NCLS, k = i - c * NID_NCLS;
+  int* q = chunk_cnt + (size_t)c * nchunks * NID_NCLS + k;
+  int run = 0, j = 0;
+  for (; j + 8 <= nchunks; j += 8) {
+    int v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = q[(size_t)(j + u) * NID_NCLS];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { q[(size_t)(j + u) * NID_NCLS] = run; run += v[u]; }
+  }
+  for (; j < nchunks; j++) { const int v = q[(size_t)j * NID_NCLS]; q[(size_t)j * NID_NCLS] = run; run += v; }
+}
+
 template <bool PTS>
 __global__ void __launch_bounds__(256) k_scatter_sell(EvalParams p, int pair, int L, const double* __restrict__ depth,
-                                                      const int* __restrict__ task_pos, double* __restrict__ sd0,
-                                                      double* __restrict__ sd1, double* __restrict__ sd2,
-                                                      unsigned* __restrict__ sid) {
+                                                      const int* __restrict__ task_pos, const int* __restrict__ chunk_off,
+                                                      double* __restrict__ sd0, double* __restrict__ sd1,
+                                                      double* __restrict__ sd2, unsigned* __restrict__ sid) {
   __shared__ int run[NID_NCLS];
   __shared__ int s_cts[NID_NCLS + 1];
-  const int c = blockIdx.x;
+  const int chunk = blockIdx.x, c = blockIdx.y;
   if (p.n_c[pair * p.ncell + c] < NID_MIN_CELL_POINTS) return;  // inactive cells have no tasks
   const size_t base = (size_t)pair * p.N;
   const int* cts = p.cls_task_start + ((size_t)pair * p.ncell + c) * (NID_NCLS + 1);
-  for (int k = threadIdx.x; k < NID_NCLS; k += blockDim.x) run[k] = 0;
+  const int* off = chunk_off + ((size_t)c * gridDim.x + chunk) * NID_NCLS;
+  for (int k = threadIdx.x; k < NID_NCLS; k += blockDim.x) run[k] = off[k];
   for (int k = threadIdx.x; k <= NID_NCLS; k += blockDim.x) s_cts[k] = cts[k];
   __syncthreads();
-  const int r0 = (c / p.cell) * p.rb, c0 = (c % p.cell) * p.cb;
-  const int npx = p.rb * p.cb;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t sbase = (size_t)pair * p.sell_cap;
-  for (int t0 = 0; t0 < npx; t0 += blockDim.x) {
-    const int t = t0 + threadIdx.x;
-    int key = -1, row = 0, col = 0;
-    size_t i = 0;
-    if (t < npx) {
-      row = r0 + t / p.cb; col = c0 + t % p.cb;
-      i = base + (size_t)row * p.cols + col;
-      if (!isnan(p.pwx[i])) key = p.inb0[i] ? (int)p.im0[i] : 256;
+  int row = 0, col = 0;
+  const int key = sell_key(p, base, c, chunk * 256 + threadIdx.x, row, col);
+  const unsigned mask = __match_any_sync(0xffffffffu, key);
+  const int leader = __ffs(mask) - 1;
+  const int rank = __popc(mask & ((1u << lane) - 1u));
+  const int cnt = __popc(mask);
+  int pos = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) {  // warps in order: stable
+    if (warp == w && lane == leader && key >= 0) {
+      pos = run[key];
+      run[key] = pos + cnt;
     }
-    const unsigned mask = __match_any_sync(0xffffffffu, key);
-    const int leader = __ffs(mask) - 1;
-    const int rank = __popc(mask & ((1u << lane) - 1u));
-    const int cnt = __popc(mask);
-    int pos = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
-      if (warp == w && lane == leader && key >= 0) {
-        pos = run[key];
-        run[key] = pos + cnt;
-      }
-      __syncthreads();
-    }
-    pos = __shfl_sync(0xffffffffu, pos, leader) + rank;
-    if (key >= 0) {
-      const int task = s_cts[key] + pos / L, o = pos % L;
-      const size_t dst = sbase + (size_t)task_pos[task] + (size_t)(o >> 2) * 128 + (o & 3);
-      if (PTS) { sd0[dst] = p.pwx[i]; sd1[dst] = p.pwy[i]; sd2[dst] = p.pwz[i]; }
-      else sd0[dst] = depth[(size_t)row * p.cols + col];
-      sid[dst] = ((unsigned)row << 16) | (unsigned)col;
-    }
+    __syncthreads();
+  }
+  pos = __shfl_sync(0xffffffffu, pos, leader) + rank;
+  if (key >= 0) {
+    const size_t i = base + (size_t)row * p.cols + col;
+    const int task = s_cts[key] + pos / L, o = pos % L;
+    const size_t dst = sbase + (size_t)task_pos[task] + (size_t)(o >> 2) * 128 + (o & 3);
+    if (PTS) { sd0[dst] = p.pwx[i]; sd1[dst] = p.pwy[i]; sd2[dst] = p.pwz[i]; }
+    else sd0[dst] = depth[(size_t)row * p.cols + col];
+    sid[dst] = ((unsigned)row << 16) | (unsigned)col;
   }
 }
 
@@ -993,12 +1026,22 @@ int launch_scatter(nid_ctx* c, int pair) {
   if (e != cudaSuccess) return check_cuda(e, "memset sd0");
   const int* tp = c->task_pos + (size_t)pair * c->max_tasks;
   const double* depth = c->depth + (size_t)pair * c->N;
+  const int nchunks = (c->rb * c->cb + 255) / 256;
+  if (!c->chunk_cnt) {
+    e = cudaMalloc((void**)&c->chunk_cnt, sizeof(int) * (size_t)c->ncell * nchunks * NID_NCLS);
+    if (e != cudaSuccess) return check_cuda(e, "cudaMalloc chunk_cnt");
+  }
+  const dim3 grid(nchunks, c->ncell);
+  k_chunk_count<<<grid, 256, 0, c->stream>>>(p, pair, c->chunk_cnt);
+  NID_LAUNCH_CHECK(c, "k_chunk_count");
+  k_chunk_scan<<<(c->ncell * NID_NCLS + 255) / 256, 256, 0, c->stream>>>(c->ncell, nchunks, c->chunk_cnt);
+  NID_LAUNCH_CHECK(c, "k_chunk_scan");
   if (c->sell_points) {
     cudaMemsetAsync(c->sd1 + sb, 0, sizeof(double) * c->sell_cap, c->stream);
     cudaMemsetAsync(c->sd2 + sb, 0, sizeof(double) * c->sell_cap, c->stream);
-    k_scatter_sell<true><<<c->ncell, 256, 0, c->stream>>>(p, pair, c->task_px, depth, tp, c->sd0, c->sd1, c->sd2, c->sid);
+    k_scatter_sell<true><<<grid, 256, 0, c->stream>>>(p, pair, c->task_px, depth, tp, c->chunk_cnt, c->sd0, c->sd1, c->sd2, c->sid);
   } else {
-    k_scatter_sell<false><<<c->ncell, 256, 0, c->stream>>>(p, pair, c->task_px, depth, tp, c->sd0, nullptr, nullptr, c->sid);
+    k_scatter_sell<false><<<grid, 256, 0, c->stream>>>(p, pair, c->task_px, depth, tp, c->chunk_cnt, c->sd0, nullptr, nullptr, c->sid);
   }
   NID_LAUNCH_CHECK(c, "k_scatter_sell");
   return NID_OK;
