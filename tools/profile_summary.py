@@ -30,7 +30,7 @@ with open(os.path.join(pr, f"{tag}_launches.txt"), "w") as f:
     f.write(f"{'kernel':24s} {'grid':16s} {'block':14s} {'launches':>8s} {'avg us':>10s} {'share of one evaluation step':>30s}\n")
     for k, v in agg.items():
         a = sum(v) / len(v)
-        sh = f"{100 * a / tot:5.1f} %" if k in step else "(setup, once per pair)"
+        sh = f"{100 * a / tot:5.1f} %" if k in step else ("(HBM probe, bench only)" if k[0] == "k_warp_sample_jobs" else "(setup, once per pair)")
         f.write(f"{k[0]:24s} {k[1]:16s} {k[2]:14s} {len(v):8d} {a / 1e3:10.1f} {sh:>30s}\n")
     f.write(f"one evaluation step ({pairs} cost+Jacobian evaluations): {tot / 1e3:.1f} us serialised under ncu\n")
 
