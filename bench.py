@@ -126,6 +126,15 @@ def measured_traffic(kernel, n_evals):
         return None, None
 
 
+def measured_pipes(kernel):
+    """fp64-pipe / issue utilisation of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return dict(d["pipes"][kernel], source=d["source"].split(" ")[0])
+    except Exception:
+        return None
+
+
 def cpu_layout(cores):
     """Use every host core: `workers` independent evaluations in flight, each an OpenMP team of `team` threads over
     the 16 cells (team divides 16 so that cells split evenly)."""
@@ -376,6 +385,7 @@ def main():
                          "note": "fp64 path: the binding roofs are fp64 issue and latency, not HBM (DESIGN.md 4)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_EVAL * n_slots,
                          "kernel_ms_per_launch": dom_ms,
+                         "ncu_pipes": measured_pipes(dom),
                          "kernel_share_of_step": {n: share[n] / tot for n in share}},
             "cpu_baseline": {"value": cpu_vm, "unit": "evals/s", "cores": cores, "kind": "port",
                              "single_thread_value": cpu_v,

@@ -55,6 +55,7 @@ keys = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'smsp__pcsamp_warps_issue_stalled_not_selected', 'smsp__pcsamp_warps_issue_stalled_selected',
         'smsp__pcsamp_warps_issue_stalled_barrier', 'smsp__pcsamp_warps_issue_stalled_branch_resolving']
 traffic = {}
+pipes = {}
 with open(os.path.join(pr, f"{tag}_ncu_full.txt"), "w") as f:
     f.write(f"ncu --set full --clock-control none --import-source on -k regex:'k_hist_sell|k_jac_sell|k_assemble|k_jac_final' -s 8 -c 4 python bench.py --pairs {pairs} --steps 3 --warmup 3\n")
     f.write(f"one launch = {pairs} cost+Jacobian evaluations of 640x480 pairs (4x4 cells, 16 bins)\n")
@@ -72,8 +73,12 @@ with open(os.path.join(pr, f"{tag}_ncu_full.txt"), "w") as f:
             u = units[i].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         traffic[name] = (val('dram__bytes_read.sum') + val('dram__bytes_write.sum')) / pairs
+        pipes[name] = {"fp64_pipe_pct": val('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'),
+                       "issue_active_pct": val('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                       "warps_active_pct": val('sm__warps_active.avg.pct_of_peak_sustained_active'),
+                       "registers_per_thread": val('launch__registers_per_thread')}
 json.dump({"source": f"profiles/{tag}_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch / {pairs} evaluations)",
-           "dram_bytes_per_eval": traffic}, open(os.path.join(pr, "traffic.json"), "w"), indent=1)
+           "dram_bytes_per_eval": traffic, "pipes": pipes}, open(os.path.join(pr, "traffic.json"), "w"), indent=1)
 lines = []
 for fn in (f"{tag}_bench_ref.json", f"{tag}_bench.json"):
     p = os.path.join(go, fn)
