@@ -426,14 +426,14 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
   for (int j = 0; j < W; j++) t[j] = __ldg(fp + (unsigned)(r[j].iy * cols + r[j].ix));
   bool sat = false;
 #pragma unroll
-  for (int j = 0; j < W; j++) sat |= r[j].ok && !r[j].exact && t[j] == 0xffffffffu;
+  for (int j = 0; j < W; j++) sat |= t[j] == 0xffffffffu;  // (qualified below: the common case is one compare per pixel)
   if (sat) {
     // saturated plateau: the clamp `>= 255 -> 254.999` (types_six_dof_expmap.cpp:572) depends on the last bit
     // of the bilinear weights, so the fractions must be the reference's own
-    anyexact = true;
 #pragma unroll
     for (int j = 0; j < W; j++)
       if (r[j].ok && !r[j].exact && t[j] == 0xffffffffu) {
+        anyexact = true;
         make_exact<PTS>(xs, rows, cols, ga, j0 + j, r[j]);
         t[j] = __ldg(fp + (unsigned)(r[j].iy * cols + r[j].ix));
       }
@@ -458,7 +458,7 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
 #pragma unroll
   for (int j = 0; j < W; j++) {
     const double ub = ic[j] * s;
-    kt[j] = r[j].ok ? min((int)ub, NS - 1) : 0;  // 0 <= ub <= NS (== NS only by rounding)
+    kt[j] = min((int)ub, NS - 1);  // 0 <= ub <= NS (== NS only by rounding); only used where acc[j]
     bspline4_uniform(ub - u2d((unsigned)kt[j]), wt[j]);
     const bool zero = ub == 0.0;
     acc[j] = r[j].ok && !zero;
