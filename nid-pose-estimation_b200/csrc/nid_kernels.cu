@@ -483,10 +483,20 @@ __global__ void __launch_bounds__(256) k_hard(EvalParams p, double* __restrict__
     int kr = (int)floor(__ddiv_rn(__dmul_rn(i0, (double)B), 255.0));
     double ic = clamp_intensity(interp_u8(im1, p.cols, u, v));
     int kt = (int)floor(__ddiv_rn(__dmul_rn(ic, (double)B), 255.0));
-    atomicAdd(&cr[kr], 1u);
-    atomicAdd(&cc[kt], 1u);
-    atomicAdd(&cj[kr * B + kt], 1u);
-    atomicAdd(cn, 1u);
+    atomicAdd(&cj[kr * B + kt], 1u);  // the only per-pixel atomic: marginals and n are sums of the joint counts
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * B; i += blockDim.x) {
+    unsigned int a = 0;
+    if (i < B) for (int k = 0; k < B; k++) a += cj[i * B + k];          // reference marginal: row sums
+    else for (int k = 0; k < B; k++) a += cj[k * B + (i - B)];          // target marginal: column sums
+    cr[i] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int a = 0;
+    for (int k = 0; k < B; k++) a += cr[k];
+    *cn = a;
   }
   __syncthreads();
   const unsigned int n = *cn;
