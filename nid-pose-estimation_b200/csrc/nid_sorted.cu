@@ -490,6 +490,9 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
 #ifndef NID_HIST_MINB
 #define NID_HIST_MINB 2  // CTAs of 256 threads per SM (128 registers)
 #endif
+// up to this many bins pass 2 stages the cell's log tables per warp and k_assemble the reference weight table in shared memory;
+// beyond, the staging areas would cost a resident CTA per SM and the tables are read through L1
+#define NID_FEW_BINS(bins) ((bins) <= 20)
 #ifndef NID_JAC_MINB
 #define NID_JAC_MINB 4  // CTAs of 128 threads per SM (128 registers)
 #endif
@@ -585,13 +588,13 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
   extern __shared__ double sm[];
   __shared__ double scratch[NID_ASM_THREADS / 32];
   __shared__ int s_cts[NID_NCLS + 1];
-  __shared__ int s_bnd[NID_ASM_THREADS / 8 + 2];
+  __shared__ int s_bnd[NID_ASM_THREADS / 4 + 2];
   const int B = p.bins, BB = B * B, NS = B - 3;
   double* Pall = sm;                    // [BB + B]
   double* red = sm + BB + B;            // [NID_ASM_THREADS] partial sums of P_t
   double* hvs = red + NID_ASM_THREADS;  // [NID_NCLS][B] per-class soft histograms
   double* part = hvs + NID_NCLS * B;    // [4][BB] per-span partial sums of P_j
-  double* wl = part + 4 * BB;           // [256][4] reference weights
+  double* wl = part + 4 * BB;           // [256][4] reference weights (up to 20 bins)
   const int c = blockIdx.x, job = blockIdx.y + p.job0;
   const int pair = p.job_pair[job];
   const int nc = p.n_c[pair * p.ncell + c];
@@ -602,14 +605,17 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
   }
   // ---- per-class soft histograms h_v[t] = sum over the tasks of class v (task order) of G[task][t], straight from
   // pass 1's task rows. The cell's tasks are one contiguous range ordered by class; the 257 classes are cut into
-  // NID_ASM_THREADS/B runs of about equal task count, and thread (run, t) streams through its run with eight
-  // independent row loads in flight, closing a class whenever the task index passes the class's end.
+  // runs of about equal task count, one per group of threads that covers a row, and every thread streams through its
+  // run with eight independent row loads in flight, closing a class whenever the task index passes the class's end.
   {
     const int* cts = p.cls_task_start + ((size_t)pair * p.ncell + c) * (NID_NCLS + 1);
     for (int i = threadIdx.x; i <= NID_NCLS; i += blockDim.x) s_cts[i] = cts[i];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) wl[i] = p.lut_w[i];
+    if (NID_FEW_BINS(B)) for (int i = threadIdx.x; i < 1024; i += blockDim.x) wl[i] = p.lut_w[i];
     __syncthreads();
-    const int ng = NID_ASM_THREADS / B;
+    // a thread owns two adjacent bins of a row (one 16-byte load) when the rows are 16-byte aligned (B even)
+    const bool pairs = (B & 1) == 0;
+    const int tpr = pairs ? B >> 1 : B;  // threads per row
+    const int ng = NID_ASM_THREADS / tpr;
     const int tfirst = s_cts[0], ntask = s_cts[NID_NCLS] - tfirst;
     if ((int)threadIdx.x <= ng) {
       const int target = tfirst + (int)(((long long)threadIdx.x * ntask) / ng);
@@ -621,7 +627,7 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
       s_bnd[threadIdx.x] = (int)threadIdx.x == ng ? NID_NCLS : lo;
     }
     __syncthreads();
-    const int g = threadIdx.x / B, tt = threadIdx.x % B;
+    const int g = threadIdx.x / tpr, tt = (threadIdx.x % tpr) * (pairs ? 2 : 1);
     if (g < ng) {
       int v = s_bnd[g];
       const int vend = s_bnd[g + 1];
@@ -629,23 +635,46 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
         int t = s_cts[v], nxt = s_cts[v + 1];
         const int tend = s_cts[vend];
         const double* gp = p.G + ((size_t)job * p.g_stride + t) * B + tt;
-        double acc = 0.0;
-        while (t < tend) {
-          const int rem = tend - t;
-          double x[8];
+        if (pairs) {
+          double a0 = 0.0, a1 = 0.0;
+          while (t < tend) {
+            const int rem = tend - t;
+            double2 x[8];
 #pragma unroll
-          for (int i = 0; i < 8; i++) x[i] = (i < rem) ? gp[i * B] : 0.0;
+            for (int i = 0; i < 8; i++) x[i] = (i < rem) ? *reinterpret_cast<const double2*>(gp + i * B) : make_double2(0.0, 0.0);
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            if (i < rem) {
-              while (t + i >= nxt) { hvs[v * B + tt] = acc; acc = 0.0; v++; nxt = s_cts[v + 1]; }
-              acc += x[i];
+            for (int i = 0; i < 8; i++) {
+              if (i < rem) {
+                while (t + i >= nxt) {
+                  *reinterpret_cast<double2*>(hvs + v * B + tt) = make_double2(a0, a1);
+                  a0 = 0.0; a1 = 0.0; v++; nxt = s_cts[v + 1];
+                }
+                a0 += x[i].x; a1 += x[i].y;
+              }
             }
+            t += 8;
+            gp += 8 * B;
           }
-          t += 8;
-          gp += 8 * B;
+          for (; v < vend; v++) { *reinterpret_cast<double2*>(hvs + v * B + tt) = make_double2(a0, a1); a0 = 0.0; a1 = 0.0; }
+        } else {
+          double acc = 0.0;
+          while (t < tend) {
+            const int rem = tend - t;
+            double x[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = (i < rem) ? gp[i * B] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              if (i < rem) {
+                while (t + i >= nxt) { hvs[v * B + tt] = acc; acc = 0.0; v++; nxt = s_cts[v + 1]; }
+                acc += x[i];
+              }
+            }
+            t += 8;
+            gp += 8 * B;
+          }
+          for (; v < vend; v++) { hvs[v * B + tt] = acc; acc = 0.0; }
         }
-        for (; v < vend; v++) { hvs[v * B + tt] = acc; acc = 0.0; }
       }
     }
   }
@@ -658,7 +687,11 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
     double a = 0.0;
     if (k >= 0 && k < NS) {
       const int vlo = p.span_start[k], vhi = p.span_start[k + 1];
-      for (int v = vlo; v < vhi; v++) a += wl[4 * v + kk] * hvs[v * B + tt];
+      if (NID_FEW_BINS(B)) {
+        for (int v = vlo; v < vhi; v++) a += wl[4 * v + kk] * hvs[v * B + tt];
+      } else {  // many bins: the 8 KB copy of the weight table would cost a resident CTA per SM
+        for (int v = vlo; v < vhi; v++) a += __ldg(p.lut_w + 4 * v + kk) * hvs[v * B + tt];
+      }
     }
     part[it] = a;
   }
@@ -834,33 +867,45 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   // the uniform basis (fold_table). Pass 2 then needs  c_i = sum_m U'_m(f_i) * W^v[k_i+m]  per pixel
   // (types_six_dof_expmap.cpp:467-528 re-associated).
   {
-    const int BP = B + 1;
-    double* Ww = sm + B * T + warp * (B * BP + B);
-    double* Vw = Ww + B * BP;
     const int desc = task >= 0 ? p.tasks[(size_t)pair * p.max_tasks + task].y : 0;
     const int cell = __shfl_sync(0xffffffffu, (desc >> 18) & 0x3fff, 0);  // lane 0 always owns a task
     const double* wvg = p.wv + ((size_t)job * p.ncell + cell) * (size_t)(B * B + B);
-    for (int i = lane; i < B * B; i += 32) Ww[(i / B) * BP + i % B] = wvg[i];
-    for (int i = lane; i < B; i += 32) Vw[i] = wvg[B * B + i];
-    __syncwarp();
-    if (task >= 0) {
-      const int cls = (desc >> 9) & 0x1ff;
-      double wr[4] = {0.0, 0.0, 0.0, 0.0};
-      int kr = 0;
-      if (cls < 256) {
-        kr = p.lut_k[cls];
+    const int cls = (desc >> 9) & 0x1ff;
+    double wr[4] = {0.0, 0.0, 0.0, 0.0};
+    int kr = 0;
+    if (task >= 0 && cls < 256) {
+      kr = p.lut_k[cls];
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) wr[kk] = p.lut_w[4 * cls + kk];
+      for (int kk = 0; kk < 4; kk++) wr[kk] = p.lut_w[4 * cls + kk];
+    }
+    if (NID_FEW_BINS(B)) {
+      // the cell's tables staged per warp (rows padded to B+1): the lanes then read their four rows bank-conflict free
+      const int BP = B + 1;
+      double* Ww = sm + B * T + warp * (B * BP + B);
+      double* Vw = Ww + B * BP;
+      for (int i = lane; i < B * B; i += 32) Ww[(i / B) * BP + i % B] = wvg[i];
+      for (int i = lane; i < B; i += 32) Vw[i] = wvg[B * B + i];
+      __syncwarp();
+      if (task >= 0) {
+        const double* Wr = Ww + kr * BP;
+        for (int t = 0; t < B; t++) {
+          double a = Vw[t];
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) a += wr[kk] * Wr[kk * BP + t];
+          wq[t * T] = a;
+        }
       }
-      const double* Wr = Ww + kr * BP;
+    } else if (task >= 0) {
+      // many bins: no staging area (it would cost a resident CTA per SM); the rows come through L1
+      const double* Wr = wvg + kr * B;
       for (int t = 0; t < B; t++) {
-        double a = Vw[t];
+        double a = __ldg(wvg + B * B + t);
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) a += wr[kk] * Wr[kk * BP + t];
+        for (int kk = 0; kk < 4; kk++) a += wr[kk] * __ldg(Wr + kk * B + t);
         wq[t * T] = a;
       }
-      fold_table(wq, T, B);
     }
+    if (task >= 0) fold_table(wq, T, B);
   }
   const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
   const double* q0 = p.sd0 + sbase;
@@ -1066,7 +1111,7 @@ int launch_pack_tex(nid_ctx* c, int pair, unsigned* d_out) {
 size_t hist_sell_smem(const nid_ctx* c, int T = 256) { return sizeof(double) * ((size_t)c->bins * T); }
 size_t jac_sell_smem(const nid_ctx* c, int T = 128) {
   const size_t B = c->bins;
-  return sizeof(double) * (B * T + (size_t)(T / 32) * (B * (B + 1) + B));
+  return sizeof(double) * (B * T + (NID_FEW_BINS(c->bins) ? (size_t)(T / 32) * (B * (B + 1) + B) : 0));
 }
 
 // Threads per CTA of the pixel kernels: the largest of 32..tmax that still gives every SM about two CTAs; a
@@ -1076,7 +1121,9 @@ static int pick_block(const nid_ctx* c, int ns, int n_jobs, int tmax) {
     if ((long long)n_jobs * ((ns + T / 32 - 1) / (T / 32)) >= 2LL * c->sm_count) return T;
   return 32;
 }
-size_t assemble_smem(const nid_ctx* c) { return sizeof(double) * ((size_t)5 * c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins + 1024); }
+size_t assemble_smem(const nid_ctx* c) {
+  return sizeof(double) * ((size_t)5 * c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins + (NID_FEW_BINS(c->bins) ? 1024 : 0));
+}
 
 // Host side of the geometry table: job (first + i) -> gt.g[i] from the staged poses (pinned mirror), the pair's
 // T_wc0 and intrinsics. pass1: rows 0 and 1 of M pre-multiplied by fx, fy.

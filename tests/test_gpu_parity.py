@@ -43,7 +43,8 @@ def test_points3d(nid, orc, make_pair):
 
 
 @pytest.mark.parametrize("path", [NATURAL, SORTED])
-@pytest.mark.parametrize("cell,bins,rows,cols", [(1, 8, 120, 160), (4, 16, 240, 320), (16, 10, 480, 640), (4, 32, 240, 320), (3, 12, 125, 170)])
+@pytest.mark.parametrize("cell,bins,rows,cols", [(1, 8, 120, 160), (4, 16, 240, 320), (16, 10, 480, 640), (4, 32, 240, 320), (3, 12, 125, 170),
+                                                 (2, 9, 120, 160), (2, 21, 120, 160), (2, 40, 240, 320)])
 def test_prepare_eval_parity(nid, orc, make_pair, cell, bins, rows, cols, path):
     p = make_pair(1000, rows, cols)
     P, ctx, pose0 = _setup(nid, orc, p, cell, bins, path=path)

@@ -36,6 +36,13 @@ for path in (1, 2):
             ctx.stage_jobs(poses, jp); ctx.eval_staged(pairs, want_jac)
         ctx.event_record(1)
         ms = ctx.event_elapsed_ms()
+        ctx.set_option("time_kernels", 1)
+        for _ in range(3):
+            ctx.stage_jobs(poses, jp); ctx.eval_staged(pairs, want_jac)
+        ctx.sync()
+        kt = ctx.kernel_times()
+        ctx.set_option("time_kernels", 0)
+        split = " ".join(f"{k}={v[0] / max(v[1], 1) / pairs * 1e3:.2f}us" for k, v in kt.items() if v[1])
         print(f"{rows}x{cols} cell={cell} bins={bins} path={'natural' if path == 1 else 'sorted'} want_jac={int(want_jac)}: "
-              f"{pairs * steps / ms * 1e3:.0f} evals/s ({ms / steps / pairs * 1e3:.1f} us/eval)")
+              f"{pairs * steps / ms * 1e3:.0f} evals/s ({ms / steps / pairs * 1e3:.1f} us/eval)  per eval: {split}")
     ctx.close()
