@@ -554,10 +554,23 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
     const int rpi = 32 / BP2;                          // rows per store instruction
     const int b = lane & (BP2 - 1), sub = lane / BP2;
     double* Gj = p.G + (size_t)job * p.g_stride * B;
-    for (int t0 = 0; t0 < 32; t0 += rpi) {
-      const int tl = t0 + sub;
-      const int tk = __shfl_sync(0xffffffffu, task, tl);
-      if (b < B && tk >= 0) Gj[(size_t)tk * B + b] = hw[b * T + ((tl + b) & 31)];
+    {
+      const double* src = hw + min(b, B - 1) * T;  // (lanes beyond the row length read a valid plane and store nothing)
+      double* dst = Gj + b;
+      const int nit = 32 / rpi;  // 8, 16 or 32 store instructions
+      for (int i0 = 0; i0 < nit; i0 += 8) {
+        double v[8];
+        int tk[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int tl = (i0 + i) * rpi + sub;
+          tk[i] = __shfl_sync(0xffffffffu, task, tl);
+          v[i] = src[(tl + b) & 31];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (b < B && tk[i] >= 0) dst[(size_t)tk[i] * B] = v[i];
+      }
     }
     for (int b1 = BP2; b1 < B; b1 += BP2) {  // B > 32: remaining columns
       for (int t0 = 0; t0 < 32; t0 += rpi) {
@@ -580,6 +593,9 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
 // k_r(v) is monotone in v, so the classes of a span are a contiguous range (span_start).
 #ifndef NID_ASM_THREADS
 #define NID_ASM_THREADS 256
+#endif
+#ifndef NID_ASM_BATCH
+#define NID_ASM_BATCH 12  // task rows a thread keeps in flight
 #endif
 #ifndef NID_ASM_MINB
 #define NID_ASM_MINB 4
@@ -612,8 +628,9 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
     for (int i = threadIdx.x; i <= NID_NCLS; i += blockDim.x) s_cts[i] = cts[i];
     if (NID_FEW_BINS(B)) for (int i = threadIdx.x; i < 1024; i += blockDim.x) wl[i] = p.lut_w[i];
     __syncthreads();
-    // a thread owns two adjacent bins of a row (one 16-byte load) when the rows are 16-byte aligned (B even)
-    const bool pairs = (B & 1) == 0;
+    // many bins: a thread owns two adjacent bins of a row (one 16-byte load; rows are 16-byte aligned when B is even),
+    // which doubles the number of class runs in flight; with few bins there are enough runs already
+    const bool pairs = (B & 1) == 0 && !NID_FEW_BINS(B);
     const int tpr = pairs ? B >> 1 : B;  // threads per row
     const int ng = NID_ASM_THREADS / tpr;
     const int tfirst = s_cts[0], ntask = s_cts[NID_NCLS] - tfirst;
@@ -660,18 +677,18 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
           double acc = 0.0;
           while (t < tend) {
             const int rem = tend - t;
-            double x[8];
+            double x[NID_ASM_BATCH];
 #pragma unroll
-            for (int i = 0; i < 8; i++) x[i] = (i < rem) ? gp[i * B] : 0.0;
+            for (int i = 0; i < NID_ASM_BATCH; i++) x[i] = (i < rem) ? gp[i * B] : 0.0;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
+            for (int i = 0; i < NID_ASM_BATCH; i++) {
               if (i < rem) {
                 while (t + i >= nxt) { hvs[v * B + tt] = acc; acc = 0.0; v++; nxt = s_cts[v + 1]; }
                 acc += x[i];
               }
             }
-            t += 8;
-            gp += 8 * B;
+            t += NID_ASM_BATCH;
+            gp += NID_ASM_BATCH * B;
           }
           for (; v < vend; v++) { hvs[v * B + tt] = acc; acc = 0.0; }
         }
