@@ -68,6 +68,10 @@ int nid_sync(nid_ctx* ctx);
  * depth: rows*cols metres (host). im0/im1: 8-bit gray (host). T_wc0: camera-0-to-world. */
 int nid_set_pair(nid_ctx* ctx, int pair, const double* depth, const uint8_t* im0, const uint8_t* im1,
                  const double T_wc0[16], const double intr[5]);
+/* Reference-frame reuse (tracking against a key frame): replace only the target image of a pair that has been
+ * set; depth, reference image and world points stay on the device. The pair must be prepared again
+ * (nid_prepare at the new initial pose: the in-bounds set, n_c and H_ref depend on it, CudaComputeHref.cu:33-135). */
+int nid_set_target(nid_ctx* ctx, int pair, const uint8_t* im1);
 /* same, from the reference's double-valued images; values must be integral after the reference's
  * clamp to [0,255) else NID_ERR_UNSUPPORTED. Either image may be NULL to keep the current one. */
 int nid_set_pair_f64(nid_ctx* ctx, int pair, const double* depth, const double* im0, const double* im1,

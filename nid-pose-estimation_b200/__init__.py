@@ -50,6 +50,7 @@ def lib():
         L.nid_destroy.argtypes = [C.c_void_p]
         L.nid_sync.argtypes = [C.c_void_p]
         L.nid_set_pair.argtypes = [C.c_void_p, C.c_int, _dp, _u8p, _u8p, _dp, _dp]
+        L.nid_set_target.argtypes = [C.c_void_p, C.c_int, _u8p]
         L.nid_set_pair_f64.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
         L.nid_set_pair_points.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
         L.nid_import_prepare.argtypes = [C.c_void_p, C.c_int, _dp, _ip, _dp]
@@ -132,6 +133,13 @@ class Context:
         im1 = np.ascontiguousarray(im1, dtype=np.uint8)
         _chk(lib().nid_set_pair(self._h, pair, _d(_f64(depth, self.n)), im0.ctypes.data_as(_u8p),
                                 im1.ctypes.data_as(_u8p), _d(_f64(T_wc0, 16)), _d(_f64(intr, 5))))
+
+    def set_target(self, pair, im1):
+        """Replace only the target image of a pair (reference-frame reuse); prepare() must be called again."""
+        im1 = np.ascontiguousarray(im1, dtype=np.uint8)
+        if im1.size != self.n:
+            raise ValueError(f"expected {self.n} pixels, got {im1.size}")
+        _chk(lib().nid_set_target(self._h, pair, im1.ctypes.data_as(_u8p)))
 
     def set_pair_f64(self, pair, depth, im0, im1, T_wc0, intr):
         _chk(lib().nid_set_pair_f64(self._h, pair, _d(_f64(depth, self.n)), _d(_f64(im0, self.n)),

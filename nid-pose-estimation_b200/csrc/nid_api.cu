@@ -371,6 +371,18 @@ int nid_set_pair(nid_ctx* c, int pair, const double* depth, const uint8_t* im0, 
   return NID_OK;
 }
 
+int nid_set_target(nid_ctx* c, int pair, const uint8_t* im1) {
+  if (!c || !im1) { set_error("bad argument"); return NID_ERR_ARG; }
+  if (pair < 0 || pair >= c->n_pairs) { set_error("pair index out of range"); return NID_ERR_ARG; }
+  if (!c->pair_set[pair]) { set_error("pair not set (nid_set_target replaces the target of an existing pair)"); return NID_ERR_STATE; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
+  CU(cudaMemcpyAsync(c->im1 + (size_t)pair * c->N, im1, c->N, cudaMemcpyDefault, c->stream), "H2D im1");
+  OKR(update_texture(c, pair));
+  CU(cudaStreamSynchronize(c->stream), "sync set_target");
+  c->pair_prepared[pair] = 0;
+  return NID_OK;
+}
+
 static int upload_images_f64(nid_ctx* c, int pair, const double* im0, const double* im1);
 static int build_sorted_layout(nid_ctx* c, int pair);
 

@@ -463,3 +463,37 @@ def test_full_size_c2_batch_properties(nid, orc, make_pair):
     np.testing.assert_allclose(Ht[j], Hto, rtol=1e-10)
     np.testing.assert_allclose(Hj[j], Hjo, rtol=1e-10)
     assert _jrel(J[j], Jo) < 1e-8
+
+
+def test_set_target_reuses_the_reference_frame(nid, orc, make_pair):
+    """Tracking against a key frame: the second target replaces only im1 of the pair slot; results equal
+    those of a context that was given the (reference, second target) pair from scratch, bit for bit, and evaluating
+    before the new prepare is refused."""
+    import dataclasses
+    pa = make_pair(1000, 240, 320)
+    pb = make_pair(1001, 240, 320)
+    pose0 = orc.reference_perturbation(pa.T_wc1)
+    M0 = orc.se3_to_mat16(pose0)
+    ctx = nid.Context(pa.rows, pa.cols, 4, 16)
+    ctx.set_pair(0, pa.depth0, pa.im0, pa.im1, pa.T_wc0, pa.intr)
+    ctx.prepare(0, M0)
+    ctx.eval(0, M0, True)
+    ctx.set_target(0, pb.im1)
+    with pytest.raises(nid.NidError):
+        ctx.eval(0, M0, True)
+    nc, href = ctx.prepare(0, M0)
+    got = ctx.eval(0, M0, True)
+    ref = nid.Context(pa.rows, pa.cols, 4, 16)
+    ref.set_pair(0, pa.depth0, pa.im0, pb.im1, pa.T_wc0, pa.intr)
+    nc2, href2 = ref.prepare(0, M0)
+    exp = ref.eval(0, M0, True)
+    assert np.array_equal(nc, nc2) and np.array_equal(href, href2)
+    for a, b in zip(got, exp):
+        assert np.array_equal(a, b, equal_nan=True)
+    P = orc.Problem(pa.im0, pa.depth0, pb.im1, pa.T_wc0, pa.intr, 4, 16, threads=4)
+    P.set_quirks(0, 1)
+    P.prepare(pose0)
+    Hto, Hjo, erro, Jo = P.eval(pose0, True)
+    np.testing.assert_allclose(got[0], Hto, rtol=1e-11)
+    np.testing.assert_allclose(got[1], Hjo, rtol=1e-11)
+    assert _jrel(got[2], Jo) < 1e-8
