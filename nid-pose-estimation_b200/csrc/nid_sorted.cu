@@ -900,7 +900,16 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
       const int BP = B + 1;
       double* Ww = sm + B * T + warp * (B * BP + B);
       double* Vw = Ww + B * BP;
-      for (int i = lane; i < B * B; i += 32) Ww[(i / B) * BP + i % B] = wvg[i];
+      {
+        // element i = r * B + c of the table, stepped by 32 without a division per element
+        const int dr = 32 / B, dc = 32 % B;
+        int r = lane / B, cc = lane % B;
+        for (int i = lane; i < B * B; i += 32) {
+          Ww[r * BP + cc] = wvg[i];
+          r += dr; cc += dc;
+          if (cc >= B) { cc -= B; r++; }
+        }
+      }
       for (int i = lane; i < B; i += 32) Vw[i] = wvg[B * B + i];
       __syncwarp();
       if (task >= 0) {
