@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(256) k_href(EvalParams p, int pair, const unsi
   __shared__ double s_con[256][4];  // class v's contribution to bins k_r(v) .. k_r(v)+3
   __shared__ int s_k[256];
   __shared__ unsigned int s_cnt[256];
+  __shared__ int s_part[8];
   __shared__ int s_n;
   const int c = blockIdx.x;
   const unsigned int* cc = cnt + ((size_t)pair * p.ncell + c) * NID_NCLS;
@@ -140,19 +141,29 @@ __global__ void __launch_bounds__(256) k_href(EvalParams p, int pair, const unsi
 #pragma unroll
   for (int m = 0; m < 4; m++) s_con[t][m] = mine ? (double)mine * p.lut_w[4 * t + m] : 0.0;
   __syncthreads();
-  if (t == 32) {  // (a lane of the second warp, so that it runs beside the bin threads)
-    int n = 0;
-    for (int v = 0; v < 256; v++) n += (int)s_cnt[v];
-    s_n = n;
+  {  // n_c: integer sum, any order
+    int n = (int)mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((t & 31) == 0) s_part[t >> 5] = n;
   }
   if (t < p.bins) {
-    // fixed order over intensity values -> deterministic
+    // fixed order over intensity values -> deterministic; only the classes of spans t-3 .. t reach bin t
+    // (k_r(v) is monotone in v: span_start)
+    const int NS = p.bins - 3;
+    const int vlo = p.span_start[max(t - 3, 0)], vhi = p.span_start[min(t, NS - 1) + 1];
     double acc = 0.0;
-    for (int v = 0; v < 256; v++) {
+    for (int v = vlo; v < vhi; v++) {
       const int m = t - s_k[v];
       if (m >= 0 && m < 4 && s_cnt[v]) acc += s_con[v][m];
     }
     pro[t] = acc;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int n = 0;
+    for (int w = 0; w < 8; w++) n += s_part[w];
+    s_n = n;
   }
   __syncthreads();
   if (t == 0) {

@@ -97,12 +97,12 @@ __global__ void __launch_bounds__(256) k_chunk_scan(int ncell, int nchunks, int*
   const int c = i / NID_NCLS, k = i - c * NID_NCLS;
   int* q = chunk_cnt + (size_t)c * nchunks * NID_NCLS + k;
   int run = 0, j = 0;
-  for (; j + 8 <= nchunks; j += 8) {
-    int v[8];
+  for (; j + 16 <= nchunks; j += 16) {  // sixteen independent loads in flight per thread
+    int v[16];
 #pragma unroll
-    for (int u = 0; u < 8; u++) v[u] = q[(size_t)(j + u) * NID_NCLS];
+    for (int u = 0; u < 16; u++) v[u] = q[(size_t)(j + u) * NID_NCLS];
 #pragma unroll
-    for (int u = 0; u < 8; u++) { q[(size_t)(j + u) * NID_NCLS] = run; run += v[u]; }
+    for (int u = 0; u < 16; u++) { q[(size_t)(j + u) * NID_NCLS] = run; run += v[u]; }
   }
   for (; j < nchunks; j++) { const int v = q[(size_t)j * NID_NCLS]; q[(size_t)j * NID_NCLS] = run; run += v; }
 }
@@ -594,21 +594,25 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
 #ifndef NID_ASM_THREADS
 #define NID_ASM_THREADS 256
 #endif
+#define NID_ASM_SMALL 128
 #ifndef NID_ASM_BATCH
 #define NID_ASM_BATCH 12  // task rows a thread keeps in flight
 #endif
 #ifndef NID_ASM_MINB
 #define NID_ASM_MINB 4
 #endif
-__global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(EvalParams p, int want_jac) {
+// NT threads per CTA: 256 in general, 128 for small cells (many cells per job, little work per cell: twice the CTAs
+// resident per SM). Fixed per geometry, so results never depend on how a batch is launched.
+template <int NT>
+__device__ __forceinline__ void assemble_body(const EvalParams& p, int want_jac) {
   extern __shared__ double sm[];
-  __shared__ double scratch[NID_ASM_THREADS / 32];
+  __shared__ double scratch[NT / 32];
   __shared__ int s_cts[NID_NCLS + 1];
-  __shared__ int s_bnd[NID_ASM_THREADS / 4 + 2];
+  __shared__ int s_bnd[NT / 4 + 2];
   const int B = p.bins, BB = B * B, NS = B - 3;
   double* Pall = sm;                    // [BB + B]
-  double* red = sm + BB + B;            // [NID_ASM_THREADS] partial sums of P_t
-  double* hvs = red + NID_ASM_THREADS;  // [NID_NCLS][B] per-class soft histograms
+  double* red = sm + BB + B;            // [NT] partial sums of P_t
+  double* hvs = red + NT;  // [NID_NCLS][B] per-class soft histograms
   double* part = hvs + NID_NCLS * B;    // [4][BB] per-span partial sums of P_j
   double* wl = part + 4 * BB;           // [256][4] reference weights (up to 20 bins)
   const int c = blockIdx.x, job = blockIdx.y + p.job0;
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
     // which doubles the number of class runs in flight; with few bins there are enough runs already
     const bool pairs = (B & 1) == 0 && !NID_FEW_BINS(B);
     const int tpr = pairs ? B >> 1 : B;  // threads per row
-    const int ng = NID_ASM_THREADS / tpr;
+    const int ng = NT / tpr;
     const int tfirst = s_cts[0], ntask = s_cts[NID_NCLS] - tfirst;
     if ((int)threadIdx.x <= ng) {
       const int target = tfirst + (int)(((long long)threadIdx.x * ntask) / ng);
@@ -714,7 +718,7 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
   }
   // ---- P_t: thread (g, tt) sums classes g, g+ng, ... ; groups are then added in order
   {
-    const int ng = NID_ASM_THREADS / B;
+    const int ng = NT / B;
     const int g = threadIdx.x / B, tt = threadIdx.x % B;
     double a = 0.0;
     if (g < ng)
@@ -731,9 +735,9 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
     ej -= q * lg;
     part[idx] = (q < kSigma) ? 0.0 : 1.0 + lg;  // this thread's own slot: 1 + log2 P_j for the tables below
   }
-  if ((int)threadIdx.x >= NID_ASM_THREADS - B) {  // the last B threads (idle in the loop above for B <= 22)
-    const int tt = threadIdx.x - (NID_ASM_THREADS - B);
-    const int ng = NID_ASM_THREADS / B;
+  if ((int)threadIdx.x >= NT - B) {  // the last B threads (idle in the loop above for B <= 22)
+    const int tt = threadIdx.x - (NT - B);
+    const int ng = NT / B;
     double a = 0.0;
     for (int g = 0; g < ng; g++) a += red[g * B + tt];
     const double q = a / (double)nc;
@@ -759,6 +763,13 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
     for (int i = threadIdx.x; i < BB; i += blockDim.x) wv[i] = part[i] * coefJ;
     if ((int)threadIdx.x < B) wv[BB + threadIdx.x] = red[threadIdx.x] * coefT;
   }
+}
+
+__global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(EvalParams p, int want_jac) {
+  assemble_body<NID_ASM_THREADS>(p, want_jac);
+}
+__global__ void __launch_bounds__(NID_ASM_SMALL, 2 * NID_ASM_MINB) k_assemble_small(EvalParams p, int want_jac) {
+  assemble_body<NID_ASM_SMALL>(p, want_jac);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1147,6 +1158,8 @@ static int pick_block(const nid_ctx* c, int ns, int n_jobs, int tmax) {
     if ((long long)n_jobs * ((ns + T / 32 - 1) / (T / 32)) >= 2LL * c->sm_count) return T;
   return 32;
 }
+// cells of fewer than 4096 pixels take the 128-thread assembly
+static bool assemble_small(const nid_ctx* c) { return (long long)c->rb * c->cb < 4096; }
 size_t assemble_smem(const nid_ctx* c) {
   return sizeof(double) * ((size_t)5 * c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins + (NID_FEW_BINS(c->bins) ? 1024 : 0));
 }
@@ -1246,7 +1259,8 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
   c->launches--;
   NID_LAUNCH_CHECK(c, "k_hist_sell");
   ktime_mark(c, 1);
-  k_assemble<<<dim3(c->ncell, n_jobs), NID_ASM_THREADS, assemble_smem(c), c->stream>>>(p, want_jac);
+  if (assemble_small(c)) k_assemble_small<<<dim3(c->ncell, n_jobs), NID_ASM_SMALL, assemble_smem(c), c->stream>>>(p, want_jac);
+  else k_assemble<<<dim3(c->ncell, n_jobs), NID_ASM_THREADS, assemble_smem(c), c->stream>>>(p, want_jac);
   NID_LAUNCH_CHECK(c, "k_assemble");
   ktime_mark(c, 2);
   if (want_jac) {
@@ -1302,6 +1316,7 @@ int sorted_init(nid_ctx* c) {
   NID_SMEM_ATTR_PX(false, NID_GEO_LARGE)
 #undef NID_SMEM_ATTR_PX
   NID_SMEM_ATTR(k_assemble, assemble_smem(c));
+  NID_SMEM_ATTR(k_assemble_small, assemble_smem(c));
 #undef NID_SMEM_ATTR
   return NID_OK;
 }
