@@ -487,6 +487,12 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
 #ifndef NID_JAC_INTTAP
 #define NID_JAC_INTTAP 0
 #endif
+#ifndef NID_HIST_TMAX
+#define NID_HIST_TMAX 128  // largest CTA of pass 1 / pass 2 (pick_block shrinks it when few jobs are in flight); measured best
+#endif
+#ifndef NID_JAC_TMAX
+#define NID_JAC_TMAX 64
+#endif
 #ifndef NID_HIST_MINB
 #define NID_HIST_MINB 2  // CTAs of 256 threads per SM (128 registers)
 #endif
@@ -1192,7 +1198,7 @@ static void fill_geo(const nid_ctx* c, GeoTable<NG>& gt, int first, int n, bool 
 
 template <bool PTS, int NG>
 static void launch_hist_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
-  const int T = pick_block(c, ns, n_jobs, 256);
+  const int T = pick_block(c, ns, n_jobs, NID_HIST_TMAX);
   const size_t sm = hist_sell_smem(c, T);
   for (int s0 = 0; s0 < n_jobs; s0 += NG) {
     const int n = std::min(NG, n_jobs - s0);
@@ -1212,7 +1218,7 @@ static void launch_hist_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0
 }
 template <bool PTS, int NG>
 static void launch_jac_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
-  const int T = pick_block(c, ns, n_jobs, 128);
+  const int T = pick_block(c, ns, n_jobs, NID_JAC_TMAX);
   const size_t sm = jac_sell_smem(c, T);
   for (int s0 = 0; s0 < n_jobs; s0 += NG) {
     const int n = std::min(NG, n_jobs - s0);
