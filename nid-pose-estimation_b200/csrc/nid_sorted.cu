@@ -1165,7 +1165,10 @@ static int pick_block(const nid_ctx* c, int ns, int n_jobs, int tmax) {
   return 32;
 }
 // cells of fewer than 4096 pixels take the 128-thread assembly
-static bool assemble_small(const nid_ctx* c) { return (long long)c->rb * c->cb < 4096; }
+#ifndef NID_ASM_SMALL_PX
+#define NID_ASM_SMALL_PX 4096
+#endif
+static bool assemble_small(const nid_ctx* c) { return (long long)c->rb * c->cb < NID_ASM_SMALL_PX; }
 size_t assemble_smem(const nid_ctx* c) {
   return sizeof(double) * ((size_t)5 * c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins + (NID_FEW_BINS(c->bins) ? 1024 : 0));
 }
