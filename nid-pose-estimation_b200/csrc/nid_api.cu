@@ -54,7 +54,7 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.pwx = c->pwx; p.pwy = c->pwy; p.pwz = c->pwz;
   p.im0 = c->im0; p.im1 = c->im1; p.inb0 = c->inb0;
   p.n_c = c->n_c; p.href = c->href; p.cam = c->cam;
-  p.lut_w = c->lut_w; p.lut_k = c->lut_k; p.bs_coef = c->bs_coef;
+  p.lut_w = c->lut_w; p.lut_k = c->lut_k;
   p.poses = c->poses; p.job_pair = c->job_pair;
   const bool sorted = use_sorted(c);
   p.part = c->part; p.jpart = sorted ? c->jpart_s : c->jpart; p.hist = c->opt_keep_hist ? c->hist : nullptr;
@@ -78,37 +78,6 @@ bool use_sorted(const nid_ctx* c) {
   if (c->bins > NID_SORTED_MAX_BINS || c->bins < 8) return false;
   if (c->opt_path == 1) return false;
   return true;
-}
-
-// Per-span polynomial form of the clamped cubic B-spline basis: for span k (k <= ub < k+1) and m = 0..3,
-// N_{k+m}(k + f) = sum_j coef[(k*4+m)*4 + j] f^j. de Boor's triangle (the non-recursive form of
-// types_six_dof_expmap.cpp:738-764) run on polynomials in f over the knots t_i = clamp(i-3, 0, B-3).
-static void build_bspline_table(int bins, std::vector<double>& coef) {
-  auto knot = [bins](int i) { return (double)std::min(std::max(i - 3, 0), bins - 3); };
-  coef.assign((size_t)(bins - 3) * 16, 0.0);
-  for (int k = 0; k < bins - 3; k++) {
-    const int mu = k + 3;
-    double N[4][4] = {{1, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-    for (int j = 1; j <= 3; j++) {
-      double saved[4] = {0, 0, 0, 0};
-      for (int r = 0; r < j; r++) {
-        const double den = knot(mu + r + 1) - knot(mu + 1 - j + r);
-        double temp[4];
-        for (int q = 0; q < 4; q++) temp[q] = N[r][q] / den;
-        const double right0 = knot(mu + r + 1) - k;    // right = right0 - f
-        const double left0 = k - knot(mu + 1 - j + r);  // left = left0 + f
-        double nr[4], ns[4];
-        for (int q = 0; q < 4; q++) {
-          nr[q] = saved[q] + right0 * temp[q] - (q > 0 ? temp[q - 1] : 0.0);
-          ns[q] = left0 * temp[q] + (q > 0 ? temp[q - 1] : 0.0);
-        }
-        for (int q = 0; q < 4; q++) { N[r][q] = nr[q]; saved[q] = ns[q]; }
-      }
-      for (int q = 0; q < 4; q++) N[j][q] = saved[q];
-    }
-    for (int m = 0; m < 4; m++)
-      for (int q = 0; q < 4; q++) coef[((size_t)k * 4 + m) * 4 + q] = N[m][q];
-  }
 }
 
 template <typename T>
@@ -302,12 +271,6 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   c->pair_prepared.assign(P, 0);
   c->pair_sorted.assign(P, 0);
   OKR(launch_build_lut(c));
-  {
-    std::vector<double> coef;
-    build_bspline_table(bins, coef);
-    OKR(dalloc(&c->bs_coef, coef.size(), "bs_coef"));
-    CU(cudaMemcpy(c->bs_coef, coef.data(), sizeof(double) * coef.size(), cudaMemcpyHostToDevice), "H2D bs_coef");
-  }
   OKR(sorted_init(c));
   CU(cudaStreamSynchronize(c->stream), "sync after lut");
   *out = c;
@@ -321,7 +284,7 @@ int nid_destroy(nid_ctx* c) {
   void* ptrs[] = {c->pwx, c->pwy, c->pwz, c->im0, c->im1, c->inb0, c->n_c, c->href, c->cam, c->Twc0, c->cnt, c->d_depth,
                   c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_pix4_jobs, c->chunk_cnt, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
                   c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
-                  c->bs_coef, c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->nslices, c->task_pos,
+                  c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->nslices, c->task_pos,
                   c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->fp1, c->cls_task_start, c->span_start, c->wv};
   for (auto t : c->h_tex2) if (t) cudaDestroyTextureObject(t);
   for (auto arr : c->tex2_arrays) if (arr) cudaFreeArray(arr);

@@ -33,7 +33,6 @@ struct EvalParams {
   // reference-intensity lookup (depends on bins only)
   const double* lut_w;  // [256][4]
   const int* lut_k;     // [256]
-  const double* bs_coef; // [(bins-3)][4][4] per-span polynomial coefficients of the cubic basis
   // per job
   const double* poses;  // [jobs][16]
   const int* job_pair;  // [jobs]
@@ -140,7 +139,6 @@ struct nid_ctx {
   double* d_bsv = nullptr;     // [4N] scratch for nid_get_ref_weights
   int* d_bsi = nullptr;        // [N]
   // luts
-  double* bs_coef = nullptr;
   double* lut_w = nullptr;
   int* lut_k = nullptr;
   // per job

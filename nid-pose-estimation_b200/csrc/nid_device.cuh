@@ -161,24 +161,6 @@ __device__ __forceinline__ double i2d_small(int v) {  // |v| < 2^20
   return __hiloint2double(0x43300000, v + 1048576) - (4503599627370496.0 + 1048576.0);
 }
 
-// Cubic B-spline basis values (and derivatives) from the per-span polynomial table built at context
-// creation (nid_api.cu: build_bspline_table): coef[(k*4 + m)*4 + j] is the coefficient of f^j, f = ub - k,
-// of N_{k+m}. Same functions as bspline4<> (de Boor on the clamped knot vector), 16 loads + Horner.
-template <bool WANT_DER>
-__device__ __forceinline__ void bspline4_tab(const double* __restrict__ coef, double ub, int k, double w[4], double dw[4]) {
-  const double f = ub - u2d((unsigned)k);
-  const double2* c2 = reinterpret_cast<const double2*>(coef + (size_t)k * 16);
-#pragma unroll
-  for (int m = 0; m < 4; m++) {
-    const double2 a = c2[2 * m], b = c2[2 * m + 1];  // a = {c0, c1}, b = {c2, c3}
-    w[m] = fma(f, fma(f, fma(f, b.y, b.x), a.y), a.x);
-    if (WANT_DER) {
-      const double d = fma(f, fma(f, 3.0 * b.y, b.x + b.x), a.y);
-      dw[m] = (ub == 0.0) ? 0.0 : d;  // the reference's BsplineDer returns 0 at u == 0 (SURVEY A-3)
-    }
-  }
-}
-
 // Centre sample and central-difference gradient (types_six_dof_expmap.cpp:434-435 via .h:310-328) from
 // 12 taps instead of 5 x 4: for u,v >= 1 the five bilinear samples share their fractional weights.
 // The first image row/column (where (int)(u-1) truncates towards zero) takes the literal formula.
