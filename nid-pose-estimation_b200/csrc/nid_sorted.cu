@@ -355,19 +355,30 @@ __device__ __forceinline__ void fold_table(double* w, int stride, int B) {
 }
 
 // ------------------------------------------------------------------------------------------------
+#ifndef NID_STREAM_LOADS
+#define NID_STREAM_LOADS 1
+#endif
+#if NID_STREAM_LOADS
+#define NID_LDS4(p) __ldcs(p)
+#define NID_LDS2(p) __ldcs(p)
+#else
+#define NID_LDS4(p) (*(p))
+#define NID_LDS2(p) (*(p))
+#endif
 // One group = four consecutive pixels of a lane's task (32 B of depths + 16 B of pixel ids per lane).
 template <bool PTS>
 struct Group {
   unsigned id[4];
   double a0[4], a1[4], a2[4];
   __device__ __forceinline__ void load(const double* q0, const double* q1, const double* q2, const unsigned* qi, size_t o) {
-    const uint4 i4 = *reinterpret_cast<const uint4*>(qi + o);
+    // read-once stream: evict-first loads keep L1 for the target-image gathers
+    const uint4 i4 = NID_LDS4(reinterpret_cast<const uint4*>(qi + o));
     id[0] = i4.x; id[1] = i4.y; id[2] = i4.z; id[3] = i4.w;
-    const double2 xa = *reinterpret_cast<const double2*>(q0 + o), xb = *reinterpret_cast<const double2*>(q0 + o + 2);
+    const double2 xa = NID_LDS2(reinterpret_cast<const double2*>(q0 + o)), xb = NID_LDS2(reinterpret_cast<const double2*>(q0 + o + 2));
     a0[0] = xa.x; a0[1] = xa.y; a0[2] = xb.x; a0[3] = xb.y;
     if (PTS) {
-      const double2 ya = *reinterpret_cast<const double2*>(q1 + o), yb = *reinterpret_cast<const double2*>(q1 + o + 2);
-      const double2 za = *reinterpret_cast<const double2*>(q2 + o), zb = *reinterpret_cast<const double2*>(q2 + o + 2);
+      const double2 ya = NID_LDS2(reinterpret_cast<const double2*>(q1 + o)), yb = NID_LDS2(reinterpret_cast<const double2*>(q1 + o + 2));
+      const double2 za = NID_LDS2(reinterpret_cast<const double2*>(q2 + o)), zb = NID_LDS2(reinterpret_cast<const double2*>(q2 + o + 2));
       a1[0] = ya.x; a1[1] = ya.y; a1[2] = yb.x; a1[3] = yb.y;
       a2[0] = za.x; a2[1] = za.y; a2[2] = zb.x; a2[3] = zb.y;
     } else {
