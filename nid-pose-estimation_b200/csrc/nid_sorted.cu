@@ -47,6 +47,9 @@ namespace nid {
   } while (0)
 
 #define NID_PAD_ID 0xFFFFFFFFu
+#ifndef NID_PREFETCH_L2
+#define NID_PREFETCH_L2 2  // groups beyond the register prefetch that the pixel kernels pull into L2 (0: off)
+#endif
 
 // counts per (cell, class) from existing in-bounds flags (nid_import_prepare path)
 __global__ void k_count_classes(EvalParams p, int pair, unsigned int* __restrict__ cnt) {
@@ -543,6 +546,13 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
   for (int gi = 0; gi < ngroups; gi++) {
     Group<PTS> Gn = G;
     if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
+#if NID_PREFETCH_L2 > 0
+    if (gi + 1 + NID_PREFETCH_L2 < ngroups) {
+      const size_t po = (size_t)(gi + 1 + NID_PREFETCH_L2) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + po));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(qi + po));
+    }
+#endif
     const size_t go = (size_t)gi * 128;
     const GroupAddr ga{q0 + go, PTS ? q1 + go : nullptr, PTS ? q2 + go : nullptr, qi + go};
 #pragma unroll
@@ -612,6 +622,14 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
 #define NID_ASM_THREADS 256
 #endif
 #define NID_ASM_SMALL 128
+#ifndef NID_ASM_STREAM
+#define NID_ASM_STREAM 1  // task rows are read once: evict-first loads
+#endif
+#if NID_ASM_STREAM
+#define NID_ASM_LD(p) __ldcs(p)
+#else
+#define NID_ASM_LD(p) (*(p))
+#endif
 #ifndef NID_ASM_BATCH
 #define NID_ASM_BATCH 12  // task rows a thread keeps in flight
 #endif
@@ -700,7 +718,7 @@ __device__ __forceinline__ void assemble_body(const EvalParams& p, int want_jac)
             const int rem = tend - t;
             double x[NID_ASM_BATCH];
 #pragma unroll
-            for (int i = 0; i < NID_ASM_BATCH; i++) x[i] = (i < rem) ? gp[i * B] : 0.0;
+            for (int i = 0; i < NID_ASM_BATCH; i++) x[i] = (i < rem) ? NID_ASM_LD(gp + i * B) : 0.0;
 #pragma unroll
             for (int i = 0; i < NID_ASM_BATCH; i++) {
               if (i < rem) {
@@ -977,6 +995,13 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   for (int gi = 0; gi < ngroups; gi++) {
     Group<PTS> Gn = G;
     if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
+#if NID_PREFETCH_L2 > 0
+    if (gi + 1 + NID_PREFETCH_L2 < ngroups) {
+      const size_t po = (size_t)(gi + 1 + NID_PREFETCH_L2) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + po));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(qi + po));
+    }
+#endif
 #pragma unroll
     for (int j0 = 0; j0 < 4; j0 += NID_JAC_W) jac_pixels<PTS, NID_JAC_W, T>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, acc);
     G = Gn;
