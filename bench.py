@@ -262,13 +262,17 @@ def main():
     distinct = [synth.make_pair(1000 + rank * DISTINCT_PAIRS + i, ROWS, COLS) for i in range(DISTINCT_PAIRS)]
     for i, p in enumerate(distinct):
         pose0.append(orc.reference_perturbation(p.T_wc1))
-    t_prep = time.perf_counter()
+    t_prep = 0.0
     for s in range(n_slots):
+        if s == min(DISTINCT_PAIRS, n_slots - 1):  # the first pairs pay the one-time allocations (pixel store, pinned staging): not timed
+            ctx.sync()
+            t_prep = time.perf_counter()
         p = distinct[s % DISTINCT_PAIRS]
         ctx.set_pair(s, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
         ctx.prepare(s, orc.se3_to_mat16(pose0[s % DISTINCT_PAIRS]))
     ctx.sync()
     t_prep = time.perf_counter() - t_prep
+    n_prep = n_slots - min(DISTINCT_PAIRS, n_slots - 1)
     job_pair = np.arange(n_slots, dtype=np.int32)
     total_steps = args.warmup + args.steps
     poses = [make_poses(orc, pose0, k, n_slots) for k in range(total_steps)]
@@ -403,9 +407,10 @@ def main():
             probe["frac"] = probe["achieved"] / peak
             probe["frac_moved"] = probe["moved"] / peak
         line["roofline"]["warp_sample_probe"] = probe
-        line["pair_setup"] = {"value": n_slots / t_prep, "unit": "pairs/s", "pairs": n_slots,
+        line["pair_setup"] = {"value": n_prep / t_prep, "unit": "pairs/s", "pairs": n_prep,
                               "call": "nid_set_pair + nid_prepare per pair (H2D of depth and both images, points, reference "
-                                      "spline data, H_ref, regrouped pixel store), wall clock, rank 0"}
+                                      "spline data, H_ref, regrouped pixel store), wall clock on the host (pageable "
+                                      "source buffers: varies with host load), rank 0"}
         if args.solves and solve_ms > 0:
             line["pose_solves"] = {"value": n_slots * world / (solve_ms * 1e-3), "unit": "solves/s",
                                    "solves": n_slots * world, "ms": solve_ms,

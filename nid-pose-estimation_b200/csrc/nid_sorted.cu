@@ -47,6 +47,13 @@ namespace nid {
   } while (0)
 
 #define NID_PAD_ID 0xFFFFFFFFu
+// grid of the pixel kernels: the job index is the fast dimension (chunk-of-slices fast was measured 6 % slower)
+#define NID_BLK_JOB blockIdx.x
+#define NID_BLK_CHUNK blockIdx.y
+#define NID_GRID(jobs, chunks) dim3(jobs, chunks)
+#ifndef NID_CARVEOUT
+#define NID_CARVEOUT 1
+#endif
 #ifndef NID_PREFETCH_L2
 #define NID_PREFETCH_L2 2  // groups beyond the register prefetch that the pixel kernels pull into L2 (0: off)
 #endif
@@ -522,10 +529,10 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
   extern __shared__ double sm[];
   const int B = p.bins, NS = B - 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int job = blockIdx.x + p.job0;
+  const int job = NID_BLK_JOB + p.job0;
   const int pair = p.job_pair[job];
-  const double* g = gt.g[blockIdx.x];
-  const int slice = blockIdx.y * (T >> 5) + warp;
+  const double* g = gt.g[NID_BLK_JOB];
+  const int slice = NID_BLK_CHUNK * (T >> 5) + warp;
   if (slice >= p.nslices[pair]) return;  // (no block-wide barrier below)
   const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
@@ -914,11 +921,11 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   extern __shared__ double sm[];
   const int B = p.bins, NS = B - 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int job = blockIdx.x + p.job0;
+  const int job = NID_BLK_JOB + p.job0;
   const int pair = p.job_pair[job];
-  const double* g = gt.g[blockIdx.x];
+  const double* g = gt.g[NID_BLK_JOB];
   // shared: the lanes' class tables W^v [B][T] | per-warp log tables W|V (prologue only)
-  const int slice = blockIdx.y * (T >> 5) + warp;
+  const int slice = NID_BLK_CHUNK * (T >> 5) + warp;
   if (slice >= p.nslices[pair]) return;  // (no block-wide barrier below)
   const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
@@ -1245,7 +1252,7 @@ static void launch_hist_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0
     fill_geo(c, gt, job0 + s0, n, true);
     EvalParams q = p;
     q.job0 = job0 + s0;
-    const dim3 grid(n, (ns + T / 32 - 1) / (T / 32));
+    const dim3 grid = NID_GRID(n, (ns + T / 32 - 1) / (T / 32));
     switch (T) {
       case 256: k_hist_sell<PTS, NG, 256><<<grid, 256, sm, c->stream>>>(q, gt); break;
       case 128: k_hist_sell<PTS, NG, 128><<<grid, 128, sm, c->stream>>>(q, gt); break;
@@ -1265,7 +1272,7 @@ static void launch_jac_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0,
     fill_geo(c, gt, job0 + s0, n, false);
     EvalParams q = p;
     q.job0 = job0 + s0;
-    const dim3 grid(n, (ns + T / 32 - 1) / (T / 32));
+    const dim3 grid = NID_GRID(n, (ns + T / 32 - 1) / (T / 32));
     switch (T) {
       case 128: k_jac_sell<PTS, NG, 128><<<grid, 128, sm, c->stream>>>(q, gt); break;
       case 64: k_jac_sell<PTS, NG, 64><<<grid, 64, sm, c->stream>>>(q, gt); break;
@@ -1347,6 +1354,17 @@ int sorted_init(nid_ctx* c) {
 #define NID_SMEM_ATTR(k, bytes)                                                                     \
   e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));            \
   if (e != cudaSuccess) return check_cuda(e, "smem attr " #k);
+#if NID_CARVEOUT
+  // shared-memory carve-out of the pixel kernels: what their resident CTAs need and no more, the rest of the 256 KB
+  // stays L1 for the target-image gathers. (hint only; per kernel: threads T, CTAs per SM = warps per SM * 32 / T)
+#define NID_CARVE(k, bytes, ctas)                                                                                  \
+  {                                                                                                                 \
+    const int pct = (int)std::min<size_t>(100, (((bytes) + 1024) * (size_t)(ctas) * 100 + 228 * 1024 - 1) / (228 * 1024)); \
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);                                   \
+  }
+#else
+#define NID_CARVE(k, bytes, ctas)
+#endif
 #define NID_SMEM_ATTR_PX(PTS, NG)                                           \
   NID_SMEM_ATTR((k_hist_sell<PTS, NG, 256>), hist_sell_smem(c, 256));       \
   NID_SMEM_ATTR((k_hist_sell<PTS, NG, 128>), hist_sell_smem(c, 128));       \
@@ -1354,7 +1372,11 @@ int sorted_init(nid_ctx* c) {
   NID_SMEM_ATTR((k_hist_sell<PTS, NG, 32>), hist_sell_smem(c, 32));         \
   NID_SMEM_ATTR((k_jac_sell<PTS, NG, 128>), jac_sell_smem(c, 128));         \
   NID_SMEM_ATTR((k_jac_sell<PTS, NG, 64>), jac_sell_smem(c, 64));           \
-  NID_SMEM_ATTR((k_jac_sell<PTS, NG, 32>), jac_sell_smem(c, 32));
+  NID_SMEM_ATTR((k_jac_sell<PTS, NG, 32>), jac_sell_smem(c, 32));                \
+  NID_CARVE((k_hist_sell<PTS, NG, 128>), hist_sell_smem(c, 128), NID_HIST_MINB * 2);   \
+  NID_CARVE((k_hist_sell<PTS, NG, 64>), hist_sell_smem(c, 64), NID_HIST_MINB * 4);     \
+  NID_CARVE((k_jac_sell<PTS, NG, 64>), jac_sell_smem(c, 64), NID_JAC_MINB * 2);        \
+  NID_CARVE((k_jac_sell<PTS, NG, 32>), jac_sell_smem(c, 32), NID_JAC_MINB * 4);
   NID_SMEM_ATTR_PX(true, NID_GEO_SMALL)
   NID_SMEM_ATTR_PX(false, NID_GEO_SMALL)
   NID_SMEM_ATTR_PX(true, NID_GEO_LARGE)
