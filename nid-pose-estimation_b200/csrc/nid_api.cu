@@ -60,7 +60,7 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.part = c->part; p.jpart = sorted ? c->jpart_s : c->jpart; p.hist = c->opt_keep_hist ? c->hist : nullptr;
   p.ht = c->ht; p.hj = c->hj; p.err = c->err; p.der = c->der; p.gn = c->gn;
   p.sd0 = c->sd0; p.sd1 = c->sd1; p.sd2 = c->sd2; p.sid = c->sid;
-  p.sl_off = c->sl_off; p.sl_task = c->sl_task; p.nslices = c->nslices;
+  p.sl_off = c->sl_off; p.sl_task = c->sl_task; p.sl_cell = c->sl_cell; p.nslices = c->nslices;
   p.sell_cap = c->sell_cap; p.max_slices = c->max_slices; p.Twc0 = c->Twc0;
   p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start; p.cell_slice_start = c->cell_slice_start;
   p.cls_task_start = c->cls_task_start; p.span_start = c->span_start; p.wv = c->wv;
@@ -202,6 +202,7 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   OKR(dalloc(&c->depth, P * N, "depth"));
   OKR(dalloc(&c->sl_off, P * ((size_t)c->max_slices + 1), "sl_off"));
   OKR(dalloc(&c->sl_task, P * (size_t)c->max_slices * 32, "sl_task"));
+  OKR(dalloc(&c->sl_cell, P * (size_t)c->max_slices, "sl_cell"));
   OKR(dalloc(&c->task_pos, P * (size_t)c->max_tasks, "task_pos"));
   OKR(dalloc(&c->nslices, P, "nslices"));
   CU(cudaMemset(c->nslices, 0, sizeof(int) * P), "memset nslices");
@@ -284,7 +285,7 @@ int nid_destroy(nid_ctx* c) {
   void* ptrs[] = {c->pwx, c->pwy, c->pwz, c->im0, c->im1, c->inb0, c->n_c, c->href, c->cam, c->Twc0, c->cnt, c->d_depth,
                   c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_pix4_jobs, c->chunk_cnt, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
                   c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
-                  c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->nslices, c->task_pos,
+                  c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->sl_cell, c->nslices, c->task_pos,
                   c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->fp1, c->cls_task_start, c->span_start, c->wv};
   for (auto t : c->h_tex2) if (t) cudaDestroyTextureObject(t);
   for (auto arr : c->tex2_arrays) if (arr) cudaFreeArray(arr);
@@ -492,7 +493,7 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
   // Slices: the tasks of a cell ordered by length (longest first; counting sort, ties keep task order) and cut
   // into groups of 32. Slices never mix cells: the lanes of a warp then sample one cell-sized region of the
   // target image (texture-cache locality) and still run out of work together.
-  std::vector<int> sl_off(1, 0), sl_task, task_pos(std::max(nt, 1)), css(NC + 1, 0);
+  std::vector<int> sl_off(1, 0), sl_task, sl_cell, task_pos(std::max(nt, 1)), css(NC + 1, 0);
   sl_task.reserve((size_t)nt + 32 * (size_t)NC);
   long long off = 0;
   {
@@ -515,6 +516,7 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
         }
         off += (long long)((longest + 3) / 4) * 128;
         sl_off.push_back((int)off);
+        sl_cell.push_back(cell);
       }
     }
   }
@@ -524,7 +526,7 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
   // One pinned staging arena for all tables (the copies are then truly asynchronous; the arena is not reused before
   // the next nid_prepare's first synchronisation on the same stream).
   {
-    const size_t n_i = (size_t)2 * nt + nt + sl_task.size() + (ns + 1) + 2 * (size_t)(NC + 1) + clsts.size() + 2;
+    const size_t n_i = (size_t)2 * nt + nt + sl_task.size() + sl_cell.size() + (ns + 1) + 2 * (size_t)(NC + 1) + clsts.size() + 2;
     if (c->h_stage_cap < n_i) {
       if (c->h_stage) cudaFreeHost(c->h_stage);
       c->h_stage = nullptr;
@@ -544,6 +546,7 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
     OKR(put(c->task_pos + (size_t)pair * c->max_tasks, task_pos.data(), nt, "H2D task_pos"));
     OKR(put(c->sl_task + (size_t)pair * c->max_slices * 32, sl_task.data(), nt ? sl_task.size() : 0, "H2D sl_task"));
     OKR(put(c->sl_off + (size_t)pair * (c->max_slices + 1), sl_off.data(), ns + 1, "H2D sl_off"));
+    OKR(put(c->sl_cell + (size_t)pair * c->max_slices, sl_cell.data(), sl_cell.size(), "H2D sl_cell"));
     OKR(put(c->nslices + pair, &ns, 1, "H2D nslices"));
     OKR(put(c->cell_task_start + (size_t)pair * (NC + 1), cts.data(), NC + 1, "H2D cell_task_start"));
     OKR(put(c->cell_slice_start + (size_t)pair * (NC + 1), css.data(), NC + 1, "H2D cell_slice_start"));

@@ -53,6 +53,7 @@ struct EvalParams {
   const unsigned* sid;  // [n_pairs][sell_cap] (row << 16) | col, 0xFFFFFFFF = padding
   const int* sl_off;    // [n_pairs][max_slices+1] first pixel slot of every slice (multiples of 128)
   const int* sl_task;   // [n_pairs][max_slices*32] task of every lane, -1 = none
+  const int* sl_cell;   // [n_pairs][max_slices] cell of every slice
   const int* nslices;   // [n_pairs]
   size_t sell_cap;      // pixel slots per pair
   int max_slices;
@@ -101,7 +102,7 @@ struct nid_ctx {
   double *sd0 = nullptr, *sd1 = nullptr, *sd2 = nullptr;
   unsigned* sid = nullptr;
   size_t sell_cap = 0;
-  int *sl_off = nullptr, *sl_task = nullptr, *nslices = nullptr, *task_pos = nullptr;
+  int *sl_off = nullptr, *sl_task = nullptr, *sl_cell = nullptr, *nslices = nullptr, *task_pos = nullptr;
   int max_slices = 0;
   std::vector<int> h_nslices;
   int max_nslices_prepared = 0;

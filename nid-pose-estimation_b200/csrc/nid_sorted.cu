@@ -931,15 +931,25 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
   const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
   double* wq = sm + threadIdx.x;  // wq[t * T]
+  // the first group of pixels is requested before the prologue, so that it arrives while the class table is built
+  const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
+  const double* q0 = p.sd0 + sbase;
+  const double* q1 = PTS ? p.sd1 + sbase : nullptr;
+  const double* q2 = PTS ? p.sd2 + sbase : nullptr;
+  const unsigned* qi = p.sid + sbase;
+  Group<PTS> G;
+  G.load(q0, q1, q2, qi, 0);
   // ---- class table of the lane's task (class v, cell of the slice):
   //   Wv[t] = V[t] + sum_kk w_ref,v[kk] W[k_r(v)+kk][t]     (class 256: V only)
   // from the cell's scaled log tables W|V (k_assemble), staged per warp with rows padded to B+1, then folded onto
   // the uniform basis (fold_table). Pass 2 then needs  c_i = sum_m U'_m(f_i) * W^v[k_i+m]  per pixel
   // (types_six_dof_expmap.cpp:467-528 re-associated).
   {
-    const int desc = task >= 0 ? p.tasks[(size_t)pair * p.max_tasks + task].y : 0;
-    const int cell = __shfl_sync(0xffffffffu, (desc >> 18) & 0x3fff, 0);  // lane 0 always owns a task
+    // (the slice's cell comes from its own small table, so that the table loads below do not wait for the
+    // sl_task -> tasks chain of dependent loads)
+    const int cell = p.sl_cell[(size_t)pair * p.max_slices + slice];
     const double* wvg = p.wv + ((size_t)job * p.ncell + cell) * (size_t)(B * B + B);
+    const int desc = task >= 0 ? p.tasks[(size_t)pair * p.max_tasks + task].y : 0;
     const int cls = (desc >> 9) & 0x1ff;
     double wr[4] = {0.0, 0.0, 0.0, 0.0};
     int kr = 0;
@@ -986,19 +996,12 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
     }
     if (task >= 0) fold_table(wq, T, B);
   }
-  const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
-  const double* q0 = p.sd0 + sbase;
-  const double* q1 = PTS ? p.sd1 + sbase : nullptr;
-  const double* q2 = PTS ? p.sd2 + sbase : nullptr;
-  const unsigned* qi = p.sid + sbase;
   const cudaTextureObject_t tex2 = p.tex2[pair];
   const uint8_t* im1 = p.im1 + (size_t)pair * p.N;
   const ExactSrc xs{p.poses + 16 * job, p.Twc0 + 16 * pair, p.cam + 4 * pair};
   const double s = (double)NS / 255.0;
   const double hfx = 0.5 * g[16], hfy = 0.5 * g[17];  // the /2 of the central differences folded in
   double acc[6] = {0, 0, 0, 0, 0, 0};
-  Group<PTS> G;
-  G.load(q0, q1, q2, qi, 0);
   for (int gi = 0; gi < ngroups; gi++) {
     Group<PTS> Gn = G;
     if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
