@@ -9,7 +9,7 @@
 // (types_six_dof_expmap.cpp:598-601) factors into  w_ref[m] * ( sum_i w_t,i[n] ): one *un-weighted* soft
 // histogram h_v[B] per class, 4 accumulations per pixel instead of 20, and
 //     P_j[r][t] = sum_v w_ref,v[r - k_r(v)] * h_v[t],      P_t[t] = sum_v h_v[t].
-// The same factorisation turns the Jacobian's 16-term table lookup into one quadratic per (class, span).
+// The same factorisation turns the Jacobian's 16-term table lookup into a 4-term one against a per-class table.
 //
 // Idea 2 -- one lane per task, sliced-ELL storage. A "task" is up to L consecutive pixels of one
 // (cell, class) segment. 64-bit shared-memory atomics are CAS loops on sm_100
@@ -30,6 +30,13 @@
 // of an integer, or whose four taps are all 255, is therefore re-evaluated with the reference's exact
 // sequence (exact_uv), so every decision is bit-identical to the reference's and everything else agrees
 // to ~1e-13.
+//
+// Idea 4 -- the uniform spline basis with an exact end-block fold instead of per-span polynomials (see
+// bspline4_uniform below): one branch-free weight formula per pixel in both passes.
+//
+// Memory-system details that were measured to matter: the pixel store is read with evict-first
+// loads and prefetched into L2 two groups ahead, so that L1 stays with the target-image gathers; CTAs are small
+// (128 / 64 threads) at the same number of resident warps; the shared-memory carve-out is requested per kernel.
 #include <math.h>
 
 #include <algorithm>
@@ -365,15 +372,14 @@ __device__ __forceinline__ void fold_table(double* w, int stride, int B) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// The sliced pixel store is read once per evaluation: evict-first loads (ld.global.cs)
 #ifndef NID_STREAM_LOADS
 #define NID_STREAM_LOADS 1
 #endif
 #if NID_STREAM_LOADS
-#define NID_LDS4(p) __ldcs(p)
-#define NID_LDS2(p) __ldcs(p)
+#define NID_LD_STREAM(p) __ldcs(p)
 #else
-#define NID_LDS4(p) (*(p))
-#define NID_LDS2(p) (*(p))
+#define NID_LD_STREAM(p) (*(p))
 #endif
 // One group = four consecutive pixels of a lane's task (32 B of depths + 16 B of pixel ids per lane).
 template <bool PTS>
@@ -382,13 +388,13 @@ struct Group {
   double a0[4], a1[4], a2[4];
   __device__ __forceinline__ void load(const double* q0, const double* q1, const double* q2, const unsigned* qi, size_t o) {
     // read-once stream: evict-first loads keep L1 for the target-image gathers
-    const uint4 i4 = NID_LDS4(reinterpret_cast<const uint4*>(qi + o));
+    const uint4 i4 = NID_LD_STREAM(reinterpret_cast<const uint4*>(qi + o));
     id[0] = i4.x; id[1] = i4.y; id[2] = i4.z; id[3] = i4.w;
-    const double2 xa = NID_LDS2(reinterpret_cast<const double2*>(q0 + o)), xb = NID_LDS2(reinterpret_cast<const double2*>(q0 + o + 2));
+    const double2 xa = NID_LD_STREAM(reinterpret_cast<const double2*>(q0 + o)), xb = NID_LD_STREAM(reinterpret_cast<const double2*>(q0 + o + 2));
     a0[0] = xa.x; a0[1] = xa.y; a0[2] = xb.x; a0[3] = xb.y;
     if (PTS) {
-      const double2 ya = NID_LDS2(reinterpret_cast<const double2*>(q1 + o)), yb = NID_LDS2(reinterpret_cast<const double2*>(q1 + o + 2));
-      const double2 za = NID_LDS2(reinterpret_cast<const double2*>(q2 + o)), zb = NID_LDS2(reinterpret_cast<const double2*>(q2 + o + 2));
+      const double2 ya = NID_LD_STREAM(reinterpret_cast<const double2*>(q1 + o)), yb = NID_LD_STREAM(reinterpret_cast<const double2*>(q1 + o + 2));
+      const double2 za = NID_LD_STREAM(reinterpret_cast<const double2*>(q2 + o)), zb = NID_LD_STREAM(reinterpret_cast<const double2*>(q2 + o + 2));
       a1[0] = ya.x; a1[1] = ya.y; a1[2] = yb.x; a1[3] = yb.y;
       a2[0] = za.x; a2[1] = za.y; a2[2] = zb.x; a2[3] = zb.y;
     } else {
