@@ -1,5 +1,5 @@
 #!/bin/bash
-# sweep of developer knobs: each argument is "pairs:NID_OPTS" (e.g. "24:task_px=32,ilp_hist=2")
+# sweep of developer knobs: each argument is "pairs:NID_OPTS" (e.g. "24:task_px=32")
 tag=$1; shift
 mkdir -p gpurun_out
 for spec in "$@"; do
