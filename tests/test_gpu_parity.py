@@ -497,3 +497,31 @@ def test_set_target_reuses_the_reference_frame(nid, orc, make_pair):
     np.testing.assert_allclose(got[0], Hto, rtol=1e-11)
     np.testing.assert_allclose(got[1], Hjo, rtol=1e-11)
     assert _jrel(got[2], Jo) < 1e-8
+
+
+def test_more_jobs_than_one_geometry_table(nid, orc, make_pair):
+    """The pixel kernels take the per-job geometry as a by-value table of 96 entries; a larger batch is issued in
+    chunks. Jobs on either side of the chunk boundary must equal the same evaluation submitted alone, bit for bit;
+    the batched kernel-1 entry point and the LM driver (two half-batches) cross the same boundary."""
+    p = make_pair(1000, 120, 160)
+    n_jobs = 100
+    ctx = nid.Context(p.rows, p.cols, 2, 16, n_pairs=2, max_jobs=n_jobs)
+    pose0 = orc.reference_perturbation(p.T_wc1)
+    for s in range(2):
+        ctx.set_pair(s, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+        ctx.prepare(s, orc.se3_to_mat16(pose0))
+    rng = np.random.default_rng(3)
+    job_pair = (np.arange(n_jobs) % 2).astype(np.int32)
+    xis = rng.uniform(-1, 1, size=(n_jobs, 6)) * 3e-3
+    poses = np.stack([orc.se3_to_mat16(orc.se3_mul(orc.se3_exp(xis[j]), pose0)) for j in range(n_jobs)])
+    Ht, Hj, J = ctx.eval_jobs(poses, job_pair, True)
+    for j in (0, 95, 96, 99):
+        a, b, c = ctx.eval(int(job_pair[j]), poses[j], True)
+        assert np.array_equal(a, Ht[j]) and np.array_equal(b, Hj[j]) and np.array_equal(c, J[j])
+    ws = ctx.warp_sample_jobs(poses, job_pair)
+    one = ctx.warp_sample_jobs(poses[97:98], job_pair[97:98])
+    assert np.array_equal(ws[97], one[0])
+    p7 = np.stack([pose0] * n_jobs)
+    out, stats = ctx.solve_jobs(p7, job_pair, 3)
+    solo, _, st1 = ctx.solve(1, pose0, 3)
+    assert np.array_equal(out[99], solo) and stats[99, 0] == st1[0]
