@@ -15,6 +15,9 @@
  *   LM::solve / optimize(10)    optimization_algorithm_levenberg.cpp:61-225,
  *                               sparse_optimizer.cpp:356-450        nid_solve / nid_solve_jobs
  *   NID::ComputeHref/ComputeH   NID_standard_property.cpp:342-485   nid_hard_eval_jobs
+ *   CalculateProKernel, per-pixel part (warp, bounds, sample, gradient)
+ *                               computeH.cu:137-176                 nid_warp_sample / nid_warp_sample_jobs
+ *   (no counterpart: a new target frame against a resident reference) nid_set_target
  *
  * The exact-signature C++ shims (`Calculate3Dpoint`, `CudaComputeHref`, `g2o::CudaComputeH`) live in
  * the same shared library (csrc/ref_shims.cu) and forward to these entry points.
