@@ -174,8 +174,9 @@ class Context:
         poses = _f64(poses)
         n = poses.size // 16
         jp = None if job_pair is None else np.ascontiguousarray(job_pair, dtype=np.int32)
-        Ht, Hj = np.zeros((n, self.ncell)), np.zeros((n, self.ncell))
-        der = np.full((n, self.ncell, 6), np.nan)
+        # (the library writes every element of Ht, Hj and, with want_jac, of der: no need to clear them first)
+        Ht, Hj = np.empty((n, self.ncell)), np.empty((n, self.ncell))
+        der = np.empty((n, self.ncell, 6)) if want_jac else np.full((n, self.ncell, 6), np.nan)
         _chk(lib().nid_eval_jobs(self._h, n, None if jp is None else jp.ctypes.data_as(_ip), _d(poses), int(want_jac),
                                  _d(Ht), _d(Hj), _d(der)))
         return Ht, Hj, der
