@@ -6,8 +6,8 @@
  *
  *   reference interface                                             replaced by
  *   ------------------------------------------------------------    ----------------------------------
- *   Calculate3Dpoint            CudaPoints3d.cuh:6                  nid_set_pair + nid_get_points3d
- *   CudaComputeHref             CudaComputeHref.cuh:6               nid_prepare + nid_get_ref_weights
+ *   Calculate3Dpoint            CudaPoints3d.cuh:6                  nid_set_pair / nid_set_pairs_u16 + nid_get_points3d
+ *   CudaComputeHref             CudaComputeHref.cuh:6               nid_prepare / nid_prepare_pairs + nid_get_ref_weights
  *   g2o::CudaComputeH           g2o/g2o/core/computeH.cuh:8         nid_eval / nid_eval_jobs
  *   Edge::computeError          types_six_dof_expmap.h:220-228      nid_eval_gn (err[])
  *   Edge::linearizeOplus        types_six_dof_expmap.cpp:381-541    nid_eval_gn (J[])
@@ -71,6 +71,14 @@ int nid_sync(nid_ctx* ctx);
  * depth: rows*cols metres (host). im0/im1: 8-bit gray (host). T_wc0: camera-0-to-world. */
 int nid_set_pair(nid_ctx* ctx, int pair, const double* depth, const uint8_t* im0, const uint8_t* im1,
                  const double T_wc0[16], const double intr[5]);
+/* The same for n consecutive pair slots [pair0, pair0 + n) in one submission (a tracking sequence, BASELINE config 4),
+ * from the dataset's own formats: raw 16-bit depth (metres = raw * intr[4], the driver's
+ * `depth.convertTo(CV_64F, depth_factor)`, NID_pose_estimation.cpp:105-106, config_eth_cvg.yaml:13) and 8-bit gray.
+ * depth_raw/im0/im1: [n][rows*cols]; T_wc0: [n][16]; intr: [n][5]. ASYNCHRONOUS: copies and kernels are queued on the
+ * context stream and the call returns; from pinned host memory nothing blocks. The host buffers must stay untouched
+ * until nid_sync or the next blocking call on this context (nid_prepare_pairs is one). */
+int nid_set_pairs_u16(nid_ctx* ctx, int pair0, int n, const uint16_t* depth_raw, const uint8_t* im0, const uint8_t* im1,
+                      const double* T_wc0, const double* intr);
 /* Reference-frame reuse (tracking against a key frame): replace only the target image of a pair that has been
  * set; depth, reference image and world points stay on the device. The pair must be prepared again
  * (nid_prepare at the new initial pose: the in-bounds set, n_c and H_ref depend on it, CudaComputeHref.cu:33-135). */
@@ -95,6 +103,10 @@ int nid_get_points3d(nid_ctx* ctx, int pair, double* points_3d);
 /* a2 (CudaComputeHref.cu:33-223 == computeHref, types_six_dof_expmap.cpp:655-725) at the initial pose.
  * bs_counter[cell^2] = n_c, Href[cell^2] is OVERWRITTEN (NaN when n_c < 300). Either may be NULL. */
 int nid_prepare(nid_ctx* ctx, int pair, const double T_cw1_init[16], int* bs_counter, double* Href);
+/* a2 for the n consecutive pairs [pair0, pair0 + n) in a handful of launches: T_cw1_init [n][16]; bs_counter and Href
+ * [n][cell^2] (either may be NULL). The task / slice tables of the regrouped pixel store are built on the device.
+ * Blocking (one synchronisation for the whole range). */
+int nid_prepare_pairs(nid_ctx* ctx, int pair0, int n, const double* T_cw1_init, int* bs_counter, double* Href);
 /* per-pixel reference spline data in the reference's layout: bs_value[4*N], bs_index[N];
  * pixels without a valid in-bounds sample at the prepare pose get NaN weights / index 0. */
 int nid_get_ref_weights(nid_ctx* ctx, int pair, double* bs_value, int* bs_index);

@@ -50,6 +50,8 @@ def lib():
         L.nid_destroy.argtypes = [C.c_void_p]
         L.nid_sync.argtypes = [C.c_void_p]
         L.nid_set_pair.argtypes = [C.c_void_p, C.c_int, _dp, _u8p, _u8p, _dp, _dp]
+        L.nid_set_pairs_u16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint16), _u8p, _u8p, _dp, _dp]
+        L.nid_prepare_pairs.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _ip, _dp]
         L.nid_set_target.argtypes = [C.c_void_p, C.c_int, _u8p]
         L.nid_set_pair_f64.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
         L.nid_set_pair_points.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp]
@@ -133,6 +135,31 @@ class Context:
         im1 = np.ascontiguousarray(im1, dtype=np.uint8)
         _chk(lib().nid_set_pair(self._h, pair, _d(_f64(depth, self.n)), im0.ctypes.data_as(_u8p),
                                 im1.ctypes.data_as(_u8p), _d(_f64(T_wc0, 16)), _d(_f64(intr, 5))))
+
+    def set_pairs_u16(self, pair0, depth_raw, im0, im1, T_wc0, intr):
+        """Batched, asynchronous set-up of pairs [pair0, pair0 + n) from raw 16-bit depth and 8-bit images
+        ([n, rows, cols] each; T_wc0 [n, 16]; intr [n, 5]). The arrays must stay alive and untouched until sync() or
+        prepare_pairs(); they are returned so that the caller can hold on to them."""
+        d = np.ascontiguousarray(depth_raw, dtype=np.uint16)
+        a = np.ascontiguousarray(im0, dtype=np.uint8)
+        b = np.ascontiguousarray(im1, dtype=np.uint8)
+        n = d.size // self.n
+        if d.size != n * self.n or a.size != d.size or b.size != d.size:
+            raise ValueError("depth_raw, im0, im1 must hold n * rows * cols elements each")
+        T = _f64(T_wc0, 16 * n)
+        K = _f64(intr, 5 * n)
+        _chk(lib().nid_set_pairs_u16(self._h, pair0, n, d.ctypes.data_as(C.POINTER(C.c_uint16)), a.ctypes.data_as(_u8p),
+                                     b.ctypes.data_as(_u8p), _d(T), _d(K)))
+        return d, a, b, T, K
+
+    def prepare_pairs(self, pair0, T_cw1):
+        """a2 of pairs [pair0, pair0 + n) in one submission -> (n_c [n, cell^2], H_ref [n, cell^2])."""
+        T = _f64(T_cw1)
+        n = T.size // 16
+        nc = np.zeros((n, self.ncell), dtype=np.int32)
+        href = np.zeros((n, self.ncell))
+        _chk(lib().nid_prepare_pairs(self._h, pair0, n, _d(T), nc.ctypes.data_as(_ip), _d(href)))
+        return nc, href
 
     def set_target(self, pair, im1):
         """Replace only the target image of a pair (reference-frame reuse); prepare() must be called again."""

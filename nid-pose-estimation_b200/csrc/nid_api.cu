@@ -35,11 +35,16 @@ int check_cuda(cudaError_t e, const char* what) {
   } while (0)
 
 static int strips_for(const nid_ctx* c, int n_jobs) {
-  if (c->opt_force_strips > 0) return std::min(c->opt_force_strips, c->rb);
-  long long want = 2LL * c->sm_count;
-  long long per = (long long)c->ncell * n_jobs;
-  int S = (int)((want + per - 1) / per);
-  S = std::max(1, std::min(S, std::min(c->rb, 32)));
+  int S;
+  if (c->opt_force_strips > 0) S = std::min(c->opt_force_strips, c->rb);
+  else {
+    long long want = 2LL * c->sm_count;
+    long long per = (long long)c->ncell * n_jobs;
+    S = (int)((want + per - 1) / per);
+    S = std::max(1, std::min(S, std::min(c->rb, 32)));
+  }
+  // the natural-order kernels write n_jobs * S (job, strip) partials: never more than the buffers hold
+  if (c->part_slots > 0 && n_jobs > 0) S = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, c->part_slots / (size_t)n_jobs));
   return S;
 }
 
@@ -71,11 +76,12 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
 
 // Path selection. The sorted path (no floating-point atomics) wins wherever it is available: measured on B200 at
 // 640x480, cost+Jacobian: 4x4 cells/16 bins 77k vs 9k evals/s, the reference's default 16x16 cells/10 bins 29k vs 9k
-// (tools/time_config.py). The natural-order kernels remain for bin counts outside [8, 40] and as a second,
+// (tools/time_config.py). The natural-order kernels remain for bin counts outside [6, 40] and as a second,
 // independently written implementation the parity tests hold to the same bar.
 bool use_sorted(const nid_ctx* c) {
-  // the assembly tables must fit in shared memory; below 8 bins every span is an end span
-  if (c->bins > NID_SORTED_MAX_BINS || c->bins < 8) return false;
+  // the assembly tables must fit in shared memory; the end-block fold needs the two 3x3 blocks disjoint (B >= 6, the
+  // reference's smallest knot table, computeH.cu:100)
+  if (c->bins > NID_SORTED_MAX_BINS || c->bins < NID_SORTED_MIN_BINS) return false;
   if (c->opt_path == 1) return false;
   return true;
 }
@@ -111,29 +117,69 @@ int ensure_job_buffers(nid_ctx* c) {
   return NID_OK;
 }
 
-static int update_texture(nid_ctx* c, int pair) {
-  OKR(launch_pack_fp(c, pair));
-  OKR(launch_pack_tex(c, pair, c->d_pack));
-  CU(cudaMemcpy2DToArrayAsync(c->tex2_arrays[pair], 0, 0, c->d_pack, sizeof(unsigned) * c->cols, sizeof(unsigned) * c->cols,
-                              c->rows, cudaMemcpyDeviceToDevice, c->stream), "packed im1 -> texture array");
+// footprint-packed plane and gather texture of the targets of pairs [pair0, pair0 + n)
+static int update_textures(nid_ctx* c, int pair0, int n) {
+  for (int p0 = pair0; p0 < pair0 + n; p0 += c->setup_batch) {
+    const int nb = std::min(c->setup_batch, pair0 + n - p0);
+    OKR(launch_pack(c, p0, nb));
+    for (int i = 0; i < nb; i++)
+      CU(cudaMemcpy2DToArrayAsync(c->tex2_arrays[p0 + i], 0, 0, c->d_pack + (size_t)i * c->N, sizeof(unsigned) * c->cols,
+                                  sizeof(unsigned) * c->cols, c->rows, cudaMemcpyDeviceToDevice, c->stream), "packed im1 -> texture array");
+  }
+  return NID_OK;
+}
+static int update_texture(nid_ctx* c, int pair) { return update_textures(c, pair, 1); }
+
+// Pinned bump arena for the small per-pair arrays (poses, intrinsics) that the asynchronous set-up calls copy to the
+// device: a region is only handed out again after the stream was synchronised.
+static int arena_take(nid_ctx* c, size_t bytes, void** out) {
+  bytes = (bytes + 63) & ~(size_t)63;
+  if (bytes > c->h_arena_cap) {
+    CU(cudaStreamSynchronize(c->stream), "sync before growing the staging arena");
+    if (c->h_arena) cudaFreeHost(c->h_arena);
+    c->h_arena = nullptr; c->h_arena_cap = 0; c->h_arena_used = 0;
+    const size_t cap = std::max(bytes * 4, (size_t)1 << 20);
+    CU(cudaMallocHost((void**)&c->h_arena, cap), "pinned staging arena");
+    c->h_arena_cap = cap;
+  }
+  if (c->h_arena_used + bytes > c->h_arena_cap) {
+    CU(cudaStreamSynchronize(c->stream), "sync to recycle the staging arena");
+    c->h_arena_used = 0;
+  }
+  *out = c->h_arena + c->h_arena_used;
+  c->h_arena_used += bytes;
   return NID_OK;
 }
 
-static int stage_jobs(nid_ctx* c, int n_jobs, const int* job_pair, const double* poses) {
+// Staging of n_jobs (pair, pose) jobs: the next slot of the pinned ring is taken (waiting, if need be, for the copies
+// that last read it), filled, and copied to the device asynchronously on the context stream.
+// mode 0: pairs must be prepared (evaluation); 1: pairs must be set (hard-binned NID, kernel 1).
+static int stage_jobs(nid_ctx* c, int n_jobs, const int* job_pair, const double* poses, int mode = 0) {
   if (n_jobs < 1 || n_jobs > c->max_jobs) { set_error("n_jobs out of range"); return NID_ERR_ARG; }
   for (int j = 0; j < n_jobs; j++) {
     int pr = job_pair ? job_pair[j] : 0;
     if (pr < 0 || pr >= c->n_pairs) { set_error("job_pair out of range"); return NID_ERR_ARG; }
+    if (mode == 1) {
+      if (!c->pair_set[pr]) { set_error("job_pair invalid or pair not set"); return NID_ERR_ARG; }
+      continue;
+    }
     if (!c->pair_prepared[pr]) { set_error("pair not prepared (call nid_prepare)"); return NID_ERR_STATE; }
     if (use_sorted(c) && !c->pair_sorted[pr]) {
       set_error("pair not prepared for the sorted path (call nid_prepare after selecting the path)");
       return NID_ERR_STATE;
     }
-    c->h_job_pair[j] = pr;
   }
+  const int slot = (c->stage_slot + 1) % NID_STAGE_RING;
+  CU(cudaEventSynchronize(c->stage_ev[slot]), "wait for the staging slot");  // (returns at once for an unrecorded event)
+  c->stage_slot = slot;
+  c->h_poses = c->h_poses_ring + (size_t)slot * 16 * c->max_jobs;
+  c->h_job_pair = c->h_job_pair_ring + (size_t)slot * c->max_jobs;
+  for (int j = 0; j < n_jobs; j++) c->h_job_pair[j] = job_pair ? job_pair[j] : 0;
   memcpy(c->h_poses, poses, sizeof(double) * 16 * n_jobs);
   CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16 * n_jobs, cudaMemcpyHostToDevice, c->stream), "H2D poses");
   CU(cudaMemcpyAsync(c->job_pair, c->h_job_pair, sizeof(int) * n_jobs, cudaMemcpyHostToDevice, c->stream), "H2D job_pair");
+  CU(cudaEventRecord(c->stage_ev[slot], c->stream), "record staging event");
+  c->staged_jobs = n_jobs;
   return NID_OK;
 }
 
@@ -165,8 +211,9 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   *out = nullptr;
   if (degree != 3) { set_error("only bs_degree == 3 (order-4 B-splines) is supported, as in the reference"); return NID_ERR_UNSUPPORTED; }
   if (rows > 65535 || cols > 65535) { set_error("rows, cols must be < 65536"); return NID_ERR_ARG; }
-  if (rows < 8 || cols < 8 || cell < 1 || bins < 7 || bins > 64 || n_pairs < 1 || max_jobs < 1 || cell > rows || cell > cols) {
-    set_error("bad geometry (need rows,cols>=8, 1<=cell<=min(rows,cols), 7<=bins<=64, n_pairs,max_jobs>=1)");
+  if (cell > 90) { set_error("cell must be <= 90 (the task descriptors keep the cell index in 13 bits)"); return NID_ERR_ARG; }
+  if (rows < 8 || cols < 8 || cell < 1 || bins < 6 || bins > 64 || n_pairs < 1 || max_jobs < 1 || cell > rows || cell > cols) {
+    set_error("bad geometry (need rows,cols>=8, 1<=cell<=min(rows,cols), 6<=bins<=64, n_pairs,max_jobs>=1)");
     return NID_ERR_ARG;
   }
   int ndev = 0;
@@ -253,20 +300,36 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
     }
     OKR(dalloc(&c->d_tex2, P, "d_tex2"));
     CU(cudaMemcpy(c->d_tex2, c->h_tex2.data(), sizeof(cudaTextureObject_t) * P, cudaMemcpyHostToDevice), "H2D tex2 handles");
-    OKR(dalloc(&c->d_pack, N, "d_pack"));
+    c->setup_batch = (int)std::min<size_t>(P, 32);
+    OKR(dalloc(&c->d_pack, N * (size_t)c->setup_batch, "d_pack"));
+    OKR(dalloc(&c->lay_tot, (size_t)c->setup_batch * NC * 3, "lay_tot"));
+    OKR(dalloc(&c->lay_base, (size_t)c->setup_batch * NC * 3, "lay_base"));
+    OKR(dalloc(&c->prep_poses, (size_t)c->setup_batch * 16, "prep_poses"));
+    OKR(dalloc(&c->depth_factor, P, "depth_factor"));
+    c->pair_u16.assign(P, 0);
     OKR(dalloc(&c->fp1, P * N, "fp1"));
     c->h_Twc0.assign(P * 16, 0.0);
     c->h_cam.assign(P * 4, 1.0);
   }
-  OKR(dalloc(&c->d_depth, N, "d_depth")); OKR(dalloc(&c->d_img64, N, "d_img64")); OKR(dalloc(&c->d_flag, 1, "d_flag"));
+  OKR(dalloc(&c->d_depth, N, "d_depth")); OKR(dalloc(&c->d_img64, N, "d_img64")); OKR(dalloc(&c->d_flag, 2, "d_flag"));
+  CU(cudaMemset(c->d_flag, 0, sizeof(int) * 2), "memset flag");
   OKR(dalloc(&c->lut_w, 256 * 4, "lut_w")); OKR(dalloc(&c->lut_k, 256, "lut_k"));
   OKR(dalloc(&c->poses, J * 16, "poses")); OKR(dalloc(&c->job_pair, J, "job_pair"));
+  CU(cudaMemset(c->job_pair, 0, sizeof(int) * J), "memset job_pair");
+  CU(cudaMemset(c->poses, 0, sizeof(double) * 16 * J), "memset poses");
+  OKR(dalloc(&c->aux_pose, 16, "aux_pose"));
   (void)hs;
   OKR(dalloc(&c->ht, J * NC, "ht")); OKR(dalloc(&c->hj, J * NC, "hj")); OKR(dalloc(&c->err, J * NC, "err"));
   OKR(dalloc(&c->der, J * NC * 6, "der")); OKR(dalloc(&c->gn, J * 44, "gn"));
   OKR(dalloc(&c->hard, J * (NC + 1), "hard"));
-  CU(cudaMallocHost((void**)&c->h_poses, sizeof(double) * 16 * J), "pinned poses");
-  CU(cudaMallocHost((void**)&c->h_job_pair, sizeof(int) * J), "pinned job_pair");
+  CU(cudaMallocHost((void**)&c->h_poses_ring, sizeof(double) * 16 * J * NID_STAGE_RING), "pinned poses");
+  CU(cudaMallocHost((void**)&c->h_job_pair_ring, sizeof(int) * J * NID_STAGE_RING), "pinned job_pair");
+  memset(c->h_poses_ring, 0, sizeof(double) * 16 * J * NID_STAGE_RING);
+  memset(c->h_job_pair_ring, 0, sizeof(int) * J * NID_STAGE_RING);
+  c->h_poses = c->h_poses_ring;
+  c->h_job_pair = c->h_job_pair_ring;
+  for (int i = 0; i < NID_STAGE_RING; i++) CU(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming), "cudaEventCreate (staging)");
+  CU(cudaMallocHost((void**)&c->h_aux_pose, sizeof(double) * 16), "pinned aux pose");
   CU(cudaMallocHost((void**)&c->h_out, sizeof(double) * J * (NC * 8 + 44)), "pinned out");
   c->pair_set.assign(P, 0);
   c->pair_prepared.assign(P, 0);
@@ -284,17 +347,19 @@ int nid_destroy(nid_ctx* c) {
   cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->pwx, c->pwy, c->pwz, c->im0, c->im1, c->inb0, c->n_c, c->href, c->cam, c->Twc0, c->cnt, c->d_depth,
                   c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_pix4_jobs, c->chunk_cnt, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
-                  c->job_pair, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
+                  c->job_pair, c->aux_pose, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
                   c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->sl_cell, c->nslices, c->task_pos,
-                  c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->fp1, c->cls_task_start, c->span_start, c->wv};
+                  c->lay_tot, c->lay_base, c->prep_poses, c->depth16, c->depth_factor, c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->fp1, c->cls_task_start, c->span_start, c->wv};
   for (auto t : c->h_tex2) if (t) cudaDestroyTextureObject(t);
   for (auto arr : c->tex2_arrays) if (arr) cudaFreeArray(arr);
   for (void* p : ptrs) if (p) cudaFree(p);
-  if (c->h_poses) cudaFreeHost(c->h_poses);
-  if (c->h_job_pair) cudaFreeHost(c->h_job_pair);
+  if (c->h_poses_ring) cudaFreeHost(c->h_poses_ring);
+  if (c->h_job_pair_ring) cudaFreeHost(c->h_job_pair_ring);
+  if (c->h_aux_pose) cudaFreeHost(c->h_aux_pose);
+  for (int i = 0; i < NID_STAGE_RING; i++) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
   if (c->h_out) cudaFreeHost(c->h_out);
-  if (c->h_stage) cudaFreeHost(c->h_stage);
-  if (c->h_cnt) cudaFreeHost(c->h_cnt);
+  if (c->h_arena) cudaFreeHost(c->h_arena);
+  if (c->h_res) cudaFreeHost(c->h_res);
   for (int i = 0; i < 2; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 5; i++) if (c->kev[i]) cudaEventDestroy(c->kev[i]);
   cudaStreamDestroy(c->stream);
@@ -304,22 +369,47 @@ int nid_destroy(nid_ctx* c) {
 }
 
 int nid_sync(nid_ctx* c) {
+  if (!c) { set_error("NULL ctx"); return NID_ERR_ARG; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
   CU(cudaStreamSynchronize(c->stream), "nid_sync");
+  c->h_arena_used = 0;
   return NID_OK;
 }
 
+// Geometry of pairs [pair0, pair0 + n): T_wc0 [n][16] and intr [n][5] go through the pinned arena (the device keeps
+// fx fy cx cy and the depth factor in separate tables), then the world points. depth64 / depth16: [n][N], one of them.
+static int set_pairs_geometry(nid_ctx* c, int pair0, int n, const double* depth64, const uint16_t* depth16, const double* T_wc0,
+                              const double* intr) {
+  if (pair0 < 0 || n < 1 || pair0 + n > c->n_pairs) { set_error("pair range out of bounds"); return NID_ERR_ARG; }
+  if ((!depth64 && !depth16) || !T_wc0 || !intr) { set_error("NULL argument"); return NID_ERR_ARG; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
+  const size_t N = c->N;
+  if (depth16) {
+    if (!c->depth16) OKR(dalloc(&c->depth16, (size_t)c->n_pairs * N, "depth16"));
+    CU(cudaMemcpyAsync(c->depth16 + (size_t)pair0 * N, depth16, sizeof(uint16_t) * N * n, cudaMemcpyDefault, c->stream), "H2D depth (u16)");
+  } else {
+    CU(cudaMemcpyAsync(c->depth + (size_t)pair0 * N, depth64, sizeof(double) * N * n, cudaMemcpyDefault, c->stream), "H2D depth");
+  }
+  double* a = nullptr;
+  OKR(arena_take(c, sizeof(double) * 21 * n, (void**)&a));
+  double *aT = a, *acam = a + 16 * (size_t)n, *afac = a + 20 * (size_t)n;
+  memcpy(aT, T_wc0, sizeof(double) * 16 * n);
+  for (int i = 0; i < n; i++) {
+    memcpy(acam + 4 * i, intr + 5 * (size_t)i, sizeof(double) * 4);
+    afac[i] = intr[5 * (size_t)i + 4];
+  }
+  CU(cudaMemcpyAsync(c->Twc0 + 16 * (size_t)pair0, aT, sizeof(double) * 16 * n, cudaMemcpyHostToDevice, c->stream), "H2D Twc0");
+  CU(cudaMemcpyAsync(c->cam + 4 * (size_t)pair0, acam, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, c->stream), "H2D intr");
+  CU(cudaMemcpyAsync(c->depth_factor + pair0, afac, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream), "H2D depth factor");
+  memcpy(c->h_Twc0.data() + 16 * (size_t)pair0, aT, sizeof(double) * 16 * n);
+  memcpy(c->h_cam.data() + 4 * (size_t)pair0, acam, sizeof(double) * 4 * n);
+  OKR(launch_points(c, pair0, n, depth16 != nullptr));
+  for (int i = 0; i < n; i++) { c->pair_prepared[pair0 + i] = 0; c->pair_u16[pair0 + i] = depth16 ? 1 : 0; }
+  return NID_OK;
+}
 static int set_pair_common(nid_ctx* c, int pair, const double* depth, const double T_wc0[16], const double intr[5]) {
   if (pair < 0 || pair >= c->n_pairs) { set_error("pair index out of range"); return NID_ERR_ARG; }
-  if (!depth || !T_wc0 || !intr) { set_error("NULL argument"); return NID_ERR_ARG; }
-  CU(cudaSetDevice(c->device), "cudaSetDevice");
-  CU(cudaMemcpyAsync(c->depth + (size_t)pair * c->N, depth, sizeof(double) * c->N, cudaMemcpyDefault, c->stream), "H2D depth");
-  CU(cudaMemcpyAsync(c->Twc0 + 16 * pair, T_wc0, sizeof(double) * 16, cudaMemcpyDefault, c->stream), "H2D Twc0");
-  CU(cudaMemcpyAsync(c->cam + 4 * pair, intr, sizeof(double) * 4, cudaMemcpyDefault, c->stream), "H2D intr");
-  memcpy(c->h_Twc0.data() + 16 * (size_t)pair, T_wc0, sizeof(double) * 16);
-  memcpy(c->h_cam.data() + 4 * (size_t)pair, intr, sizeof(double) * 4);
-  OKR(launch_points(c, pair));
-  c->pair_prepared[pair] = 0;
-  return NID_OK;
+  return set_pairs_geometry(c, pair, 1, depth, nullptr, T_wc0, intr);
 }
 
 int nid_set_pair(nid_ctx* c, int pair, const double* depth, const uint8_t* im0, const uint8_t* im1, const double T_wc0[16],
@@ -335,6 +425,20 @@ int nid_set_pair(nid_ctx* c, int pair, const double* depth, const uint8_t* im0, 
   return NID_OK;
 }
 
+int nid_set_pairs_u16(nid_ctx* c, int pair0, int n, const uint16_t* depth_raw, const uint8_t* im0, const uint8_t* im1,
+                      const double* T_wc0, const double* intr) {
+  if (!c) { set_error("NULL ctx"); return NID_ERR_ARG; }
+  if (!im0 || !im1 || !depth_raw) { set_error("NULL image"); return NID_ERR_ARG; }
+  if (c->sell_points) { set_error("this context holds caller-supplied world points (nid_set_pair_points)"); return NID_ERR_STATE; }
+  OKR(set_pairs_geometry(c, pair0, n, nullptr, depth_raw, T_wc0, intr));
+  const size_t N = c->N;
+  CU(cudaMemcpyAsync(c->im0 + (size_t)pair0 * N, im0, N * n, cudaMemcpyDefault, c->stream), "H2D im0");
+  CU(cudaMemcpyAsync(c->im1 + (size_t)pair0 * N, im1, N * n, cudaMemcpyDefault, c->stream), "H2D im1");
+  OKR(update_textures(c, pair0, n));
+  for (int i = 0; i < n; i++) c->pair_set[pair0 + i] = 1;
+  return NID_OK;  // (asynchronous: see the header)
+}
+
 int nid_set_target(nid_ctx* c, int pair, const uint8_t* im1) {
   if (!c || !im1) { set_error("bad argument"); return NID_ERR_ARG; }
   if (pair < 0 || pair >= c->n_pairs) { set_error("pair index out of range"); return NID_ERR_ARG; }
@@ -348,7 +452,8 @@ int nid_set_target(nid_ctx* c, int pair, const uint8_t* im1) {
 }
 
 static int upload_images_f64(nid_ctx* c, int pair, const double* im0, const double* im1);
-static int build_sorted_layout(nid_ctx* c, int pair);
+static int build_sorted_layout(nid_ctx* c, int pair0, int n);
+static int finish_sorted_layout(nid_ctx* c, int pair0, int n, int* bs_counter, double* Href);
 
 int nid_set_pair_f64(nid_ctx* c, int pair, const double* depth, const double* im0, const double* im1,
                      const double T_wc0[16], const double intr[5]) {
@@ -415,8 +520,8 @@ int nid_import_prepare(nid_ctx* c, int pair, const double* bs_value, const int* 
   CU(cudaMemcpyAsync(c->href + pair * c->ncell, Href, sizeof(double) * c->ncell, cudaMemcpyDefault, c->stream), "H2D href");
   CU(cudaMemsetAsync(c->cnt + (size_t)pair * c->ncell * NID_NCLS, 0, sizeof(unsigned int) * c->ncell * NID_NCLS, c->stream), "memset cnt");
   OKR(launch_count_classes(c, pair));
-  OKR(build_sorted_layout(c, pair));
-  CU(cudaStreamSynchronize(c->stream), "sync import");
+  OKR(build_sorted_layout(c, pair, 1));
+  OKR(finish_sorted_layout(c, pair, 1, nullptr, nullptr));
   c->pair_prepared[pair] = 1;
   return NID_OK;
 }
@@ -424,6 +529,7 @@ int nid_import_prepare(nid_ctx* c, int pair, const double* bs_value, const int* 
 int nid_get_inbounds(nid_ctx* c, int pair, uint8_t* flags) {
   if (!c || pair < 0 || pair >= c->n_pairs || !flags) { set_error("bad argument"); return NID_ERR_ARG; }
   if (!c->pair_prepared[pair]) { set_error("pair not prepared"); return NID_ERR_STATE; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
   CU(cudaMemcpyAsync(flags, c->inb0 + (size_t)pair * c->N, c->N, cudaMemcpyDefault, c->stream), "D2H inb0");
   CU(cudaStreamSynchronize(c->stream), "sync inb0");
   return NID_OK;
@@ -432,6 +538,7 @@ int nid_get_inbounds(nid_ctx* c, int pair, uint8_t* flags) {
 int nid_get_points3d(nid_ctx* c, int pair, double* points_3d) {
   if (!c || pair < 0 || pair >= c->n_pairs || !points_3d) { set_error("bad argument"); return NID_ERR_ARG; }
   if (!c->pair_set[pair]) { set_error("pair not set"); return NID_ERR_STATE; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
   if (!c->d_pix) OKR(dalloc(&c->d_pix, (size_t)8 * c->N, "d_pix"));
   OKR(launch_points_aos(c, pair, c->d_pix));
   CU(cudaMemcpyAsync(points_3d, c->d_pix, sizeof(double) * 3 * c->N, cudaMemcpyDefault, c->stream), "copy points3d");
@@ -439,13 +546,11 @@ int nid_get_points3d(nid_ctx* c, int pair, double* points_3d) {
   return NID_OK;
 }
 
-// Regroup the pair's valid pixels by (cell, reference class), cut the segments into tasks of at most
-// task_px pixels, order the tasks by length and pack them 32 to a slice (nid_sorted.cu). The class counts
-// come from the device; offsets and tables are integer bookkeeping done here, the pixels are moved by
-// k_scatter_sell.
-static int build_sorted_layout(nid_ctx* c, int pair) {
-  const int NC = c->ncell, L = c->task_px;
-  c->pair_sorted[pair] = 0;
+// Regroup the valid pixels of pairs [pair0, pair0 + n) by (cell, reference class), cut the segments into tasks of at most
+// task_px pixels, order the tasks by length and pack them 32 to a slice (nid_sorted.cu). Everything happens on the
+// device, from the class counts k_prepare left there: table kernels, then the regrouping scatter. Asynchronous.
+static int build_sorted_layout(nid_ctx* c, int pair0, int n) {
+  for (int i = 0; i < n; i++) c->pair_sorted[pair0 + i] = 0;
   if (!use_sorted(c)) return NID_OK;  // the natural-order kernels need none of this
   if (!c->sd0) {
     OKR(dalloc(&c->sd0, (size_t)c->n_pairs * c->sell_cap, "sd0"));
@@ -455,138 +560,87 @@ static int build_sorted_layout(nid_ctx* c, int pair) {
     OKR(dalloc(&c->sd1, (size_t)c->n_pairs * c->sell_cap, "sd1"));
     OKR(dalloc(&c->sd2, (size_t)c->n_pairs * c->sell_cap, "sd2"));
   }
-  const size_t n_cnt = (size_t)NC * NID_NCLS;
-  if (c->h_cnt_cap < n_cnt) {
-    if (c->h_cnt) cudaFreeHost(c->h_cnt);
-    c->h_cnt = nullptr;
-    c->h_cnt_cap = 0;
-    CU(cudaMallocHost((void**)&c->h_cnt, sizeof(unsigned int) * n_cnt), "pinned cnt");
-    c->h_cnt_cap = n_cnt;
+  if (!c->chunk_cnt) {
+    const size_t nchunks = ((size_t)c->rb * c->cb + 255) / 256;
+    OKR(dalloc(&c->chunk_cnt, (size_t)c->setup_batch * c->ncell * nchunks * NID_NCLS, "chunk_cnt"));
   }
-  const unsigned int* cnt = c->h_cnt;
-  CU(cudaMemcpyAsync(c->h_cnt, c->cnt + (size_t)pair * NC * NID_NCLS, sizeof(unsigned int) * n_cnt,
-                     cudaMemcpyDeviceToHost, c->stream), "D2H cnt");
-  CU(cudaStreamSynchronize(c->stream), "sync cnt");
-  std::vector<int> cts(NC + 1), clsts((size_t)NC * (NID_NCLS + 1));
-  std::vector<int2> tasks;
-  tasks.reserve(c->max_tasks);
-  for (int cell = 0; cell < NC; cell++) {
-    cts[cell] = (int)tasks.size();
-    long long n_c = 0;
-    for (int v = 0; v < 256; v++) n_c += cnt[(size_t)cell * NID_NCLS + v];
-    const bool active = n_c >= NID_MIN_CELL_POINTS;  // inactive cells get no work at all
-    for (int v = 0; v < NID_NCLS; v++) {
-      const int len = (int)cnt[(size_t)cell * NID_NCLS + v];
-      clsts[(size_t)cell * (NID_NCLS + 1) + v] = (int)tasks.size();
-      for (int o = 0; active && o < len; o += L) {
-        int2 t;
-        t.x = o;
-        t.y = std::min(L, len - o) | (v << 9) | (cell << 18);
-        tasks.push_back(t);
-      }
+  for (int p0 = pair0; p0 < pair0 + n; p0 += c->setup_batch)
+    OKR(launch_layout_and_scatter(c, p0, std::min(c->setup_batch, pair0 + n - p0)));
+  return NID_OK;
+}
+
+// One synchronisation for the whole range: n_c and H_ref for the caller, task and slice counts for the launch geometry.
+static int finish_sorted_layout(nid_ctx* c, int pair0, int n, int* bs_counter, double* Href) {
+  const size_t NC = c->ncell;
+  const size_t bytes = (size_t)n * (NC * (sizeof(double) + sizeof(int)) + 2 * sizeof(int)) + sizeof(int) + 64;
+  if (c->h_res_cap < bytes) {
+    CU(cudaStreamSynchronize(c->stream), "sync before growing the result buffer");
+    if (c->h_res) cudaFreeHost(c->h_res);
+    c->h_res = nullptr; c->h_res_cap = 0;
+    CU(cudaMallocHost((void**)&c->h_res, bytes * 2), "pinned prepare results");
+    c->h_res_cap = bytes * 2;
+  }
+  double* h_href = (double*)c->h_res;
+  int* h_nc = (int*)(h_href + (size_t)n * NC);
+  int* h_nt = h_nc + (size_t)n * NC;
+  int* h_ns = h_nt + n;
+  int* h_ovf = h_ns + n;
+  CU(cudaMemcpyAsync(h_nc, c->n_c + (size_t)pair0 * NC, sizeof(int) * NC * n, cudaMemcpyDeviceToHost, c->stream), "D2H n_c");
+  CU(cudaMemcpyAsync(h_href, c->href + (size_t)pair0 * NC, sizeof(double) * NC * n, cudaMemcpyDeviceToHost, c->stream), "D2H href");
+  const bool sorted = use_sorted(c);
+  if (sorted) {
+    CU(cudaMemcpyAsync(h_nt, c->ntasks + pair0, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream), "D2H ntasks");
+    CU(cudaMemcpyAsync(h_ns, c->nslices + pair0, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream), "D2H nslices");
+    CU(cudaMemcpyAsync(h_ovf, c->d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream), "D2H overflow flag");
+  }
+  CU(cudaStreamSynchronize(c->stream), "sync prepare");
+  c->h_arena_used = 0;
+  if (sorted) {
+    if (*h_ovf) { set_error("sliced pixel store overflow"); return NID_ERR_STATE; }
+    for (int i = 0; i < n; i++) {
+      c->h_ntasks[pair0 + i] = h_nt[i];
+      c->h_nslices[pair0 + i] = h_ns[i];
+      c->pair_sorted[pair0 + i] = 1;
     }
-    clsts[(size_t)cell * (NID_NCLS + 1) + NID_NCLS] = (int)tasks.size();
+    c->max_ntasks_prepared = 0;
+    for (int v : c->h_ntasks) c->max_ntasks_prepared = std::max(c->max_ntasks_prepared, v);
+    c->max_nslices_prepared = 0;
+    for (int v : c->h_nslices) c->max_nslices_prepared = std::max(c->max_nslices_prepared, v);
   }
-  cts[NC] = (int)tasks.size();
-  const int nt = (int)tasks.size();
-  if (nt > c->max_tasks || NC > 0x3fff) { set_error("task table overflow"); return NID_ERR_STATE; }
-  // Slices: the tasks of a cell ordered by length (longest first; counting sort, ties keep task order) and cut
-  // into groups of 32. Slices never mix cells: the lanes of a warp then sample one cell-sized region of the
-  // target image (texture-cache locality) and still run out of work together.
-  std::vector<int> sl_off(1, 0), sl_task, sl_cell, task_pos(std::max(nt, 1)), css(NC + 1, 0);
-  sl_task.reserve((size_t)nt + 32 * (size_t)NC);
-  long long off = 0;
-  {
-    std::vector<int> order, bucket(NID_TASK_PX_MAX + 2);
-    for (int cell = 0; cell < NC; cell++) {
-      css[cell] = (int)sl_off.size() - 1;
-      const int t0 = cts[cell], t1 = cts[cell + 1];
-      if (t1 == t0) continue;
-      order.assign(t1 - t0, 0);
-      std::fill(bucket.begin(), bucket.end(), 0);
-      for (int t = t0; t < t1; t++) bucket[NID_TASK_PX_MAX - (tasks[t].y & 0x1ff) + 1]++;
-      for (int i = 1; i <= NID_TASK_PX_MAX + 1; i++) bucket[i] += bucket[i - 1];
-      for (int t = t0; t < t1; t++) order[bucket[NID_TASK_PX_MAX - (tasks[t].y & 0x1ff)]++] = t;
-      for (int s0 = 0; s0 < t1 - t0; s0 += 32) {
-        const int longest = tasks[order[s0]].y & 0x1ff;
-        for (int l = 0; l < 32; l++) {
-          const int t = s0 + l < t1 - t0 ? order[s0 + l] : -1;
-          sl_task.push_back(t);
-          if (t >= 0) task_pos[t] = (int)off + 4 * l;
-        }
-        off += (long long)((longest + 3) / 4) * 128;
-        sl_off.push_back((int)off);
-        sl_cell.push_back(cell);
-      }
-    }
+  if (bs_counter) memcpy(bs_counter, h_nc, sizeof(int) * NC * n);
+  if (Href) memcpy(Href, h_href, sizeof(double) * NC * n);
+  return NID_OK;
+}
+
+int nid_prepare_pairs(nid_ctx* c, int pair0, int n, const double* T_cw1, int* bs_counter, double* Href) {
+  if (!c || !T_cw1 || n < 1 || pair0 < 0 || pair0 + n > c->n_pairs) { set_error("bad argument"); return NID_ERR_ARG; }
+  for (int i = 0; i < n; i++)
+    if (!c->pair_set[pair0 + i]) { set_error("pair not set"); return NID_ERR_STATE; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
+  for (int p0 = pair0; p0 < pair0 + n; p0 += c->setup_batch) {
+    const int nb = std::min(c->setup_batch, pair0 + n - p0);
+    double* a = nullptr;
+    OKR(arena_take(c, sizeof(double) * 16 * nb, (void**)&a));
+    memcpy(a, T_cw1 + 16 * (size_t)(p0 - pair0), sizeof(double) * 16 * nb);
+    CU(cudaMemcpyAsync(c->prep_poses, a, sizeof(double) * 16 * nb, cudaMemcpyHostToDevice, c->stream), "H2D initial poses");
+    OKR(launch_prepare(c, p0, nb, c->prep_poses));
+    OKR(launch_href(c, p0, nb));
+    OKR(build_sorted_layout(c, p0, nb));
   }
-  const int ns = (int)sl_off.size() - 1;
-  css[NC] = ns;
-  if ((size_t)off > c->sell_cap || ns > c->max_slices) { set_error("sliced pixel store overflow"); return NID_ERR_STATE; }
-  // One pinned staging arena for all tables (the copies are then truly asynchronous; the arena is not reused before
-  // the next nid_prepare's first synchronisation on the same stream).
-  {
-    const size_t n_i = (size_t)2 * nt + nt + sl_task.size() + sl_cell.size() + (ns + 1) + 2 * (size_t)(NC + 1) + clsts.size() + 2;
-    if (c->h_stage_cap < n_i) {
-      if (c->h_stage) cudaFreeHost(c->h_stage);
-      c->h_stage = nullptr;
-      c->h_stage_cap = 0;
-      CU(cudaMallocHost((void**)&c->h_stage, sizeof(int) * (n_i + n_i / 4)), "pinned stage");
-      c->h_stage_cap = n_i + n_i / 4;
-    }
-    int* w = c->h_stage;
-    auto put = [&](void* dst, const void* src, size_t n_ints, const char* what) -> int {
-      if (!n_ints) return NID_OK;
-      memcpy(w, src, sizeof(int) * n_ints);
-      CU(cudaMemcpyAsync(dst, w, sizeof(int) * n_ints, cudaMemcpyHostToDevice, c->stream), what);
-      w += n_ints;
-      return NID_OK;
-    };
-    OKR(put(c->tasks + (size_t)pair * c->max_tasks, tasks.data(), (size_t)2 * nt, "H2D tasks"));
-    OKR(put(c->task_pos + (size_t)pair * c->max_tasks, task_pos.data(), nt, "H2D task_pos"));
-    OKR(put(c->sl_task + (size_t)pair * c->max_slices * 32, sl_task.data(), nt ? sl_task.size() : 0, "H2D sl_task"));
-    OKR(put(c->sl_off + (size_t)pair * (c->max_slices + 1), sl_off.data(), ns + 1, "H2D sl_off"));
-    OKR(put(c->sl_cell + (size_t)pair * c->max_slices, sl_cell.data(), sl_cell.size(), "H2D sl_cell"));
-    OKR(put(c->nslices + pair, &ns, 1, "H2D nslices"));
-    OKR(put(c->cell_task_start + (size_t)pair * (NC + 1), cts.data(), NC + 1, "H2D cell_task_start"));
-    OKR(put(c->cell_slice_start + (size_t)pair * (NC + 1), css.data(), NC + 1, "H2D cell_slice_start"));
-    OKR(put(c->ntasks + pair, &nt, 1, "H2D ntasks"));
-    OKR(put(c->cls_task_start + (size_t)pair * NC * (NID_NCLS + 1), clsts.data(), clsts.size(), "H2D cls_task_start"));
-  }
-  OKR(launch_scatter(c, pair));
-  c->h_ntasks[pair] = nt;
-  c->h_nslices[pair] = ns;
-  c->pair_sorted[pair] = 1;
-  c->max_ntasks_prepared = 0;
-  for (int v : c->h_ntasks) c->max_ntasks_prepared = std::max(c->max_ntasks_prepared, v);
-  c->max_nslices_prepared = 0;
-  for (int v : c->h_nslices) c->max_nslices_prepared = std::max(c->max_nslices_prepared, v);
+  OKR(finish_sorted_layout(c, pair0, n, bs_counter, Href));
+  for (int i = 0; i < n; i++) c->pair_prepared[pair0 + i] = 1;
   return NID_OK;
 }
 
 int nid_prepare(nid_ctx* c, int pair, const double T_cw1[16], int* bs_counter, double* Href) {
   if (!c || pair < 0 || pair >= c->n_pairs || !T_cw1) { set_error("bad argument"); return NID_ERR_ARG; }
-  if (!c->pair_set[pair]) { set_error("pair not set"); return NID_ERR_STATE; }
-  CU(cudaSetDevice(c->device), "cudaSetDevice");
-  memcpy(c->h_poses, T_cw1, sizeof(double) * 16);
-  CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream), "H2D pose");
-  OKR(launch_prepare(c, pair, c->poses));
-  OKR(launch_href(c, pair));
-  OKR(build_sorted_layout(c, pair));
-  int* h_nc = (int*)c->h_out;
-  double* h_href = c->h_out + c->ncell;  // ncell ints fit in ncell doubles
-  CU(cudaMemcpyAsync(h_nc, c->n_c + pair * c->ncell, sizeof(int) * c->ncell, cudaMemcpyDeviceToHost, c->stream), "D2H n_c");
-  CU(cudaMemcpyAsync(h_href, c->href + pair * c->ncell, sizeof(double) * c->ncell, cudaMemcpyDeviceToHost, c->stream), "D2H href");
-  CU(cudaStreamSynchronize(c->stream), "sync prepare");
-  if (bs_counter) memcpy(bs_counter, h_nc, sizeof(int) * c->ncell);
-  if (Href) memcpy(Href, h_href, sizeof(double) * c->ncell);
-  c->pair_prepared[pair] = 1;
-  return NID_OK;
+  return nid_prepare_pairs(c, pair, 1, T_cw1, bs_counter, Href);
 }
 
 int nid_get_ref_weights(nid_ctx* c, int pair, double* bs_value, int* bs_index) {
   if (!c || pair < 0 || pair >= c->n_pairs) { set_error("bad argument"); return NID_ERR_ARG; }
   if (!c->pair_prepared[pair]) { set_error("pair not prepared"); return NID_ERR_STATE; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
   if (!c->d_bsv) { OKR(dalloc(&c->d_bsv, (size_t)4 * c->N, "d_bsv")); OKR(dalloc(&c->d_bsi, (size_t)c->N, "d_bsi")); }
   OKR(launch_ref_weights(c, pair));
   if (bs_value) CU(cudaMemcpyAsync(bs_value, c->d_bsv, sizeof(double) * 4 * c->N, cudaMemcpyDefault, c->stream), "D2H bs_value");
@@ -597,16 +651,20 @@ int nid_get_ref_weights(nid_ctx* c, int pair, double* bs_value, int* bs_index) {
 
 int nid_stage_jobs(nid_ctx* c, int n_jobs, const int* job_pair, const double* poses) {
   if (!c || !poses) { set_error("bad argument"); return NID_ERR_ARG; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
   return stage_jobs(c, n_jobs, job_pair, poses);
 }
 
 int nid_eval_staged(nid_ctx* c, int n_jobs, int want_jac) {
   if (!c || n_jobs < 1 || n_jobs > c->max_jobs) { set_error("bad argument"); return NID_ERR_ARG; }
+  if (n_jobs > c->staged_jobs) { set_error("nid_eval_staged: more jobs than the last nid_stage_jobs staged"); return NID_ERR_STATE; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
   return launch_eval(c, n_jobs, want_jac);
 }
 
 int nid_fetch_results(nid_ctx* c, int n_jobs, int want_jac, double* Ht, double* Hj, double* der) {
   if (!c || n_jobs < 1 || n_jobs > c->max_jobs) { set_error("bad argument"); return NID_ERR_ARG; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
   return fetch(c, n_jobs, want_jac, Ht, Hj, der);
 }
 
@@ -751,6 +809,7 @@ int nid_solve_jobs(nid_ctx* c, int n, const int* job_pair, double* poses7, int m
     s.phase = max_iters > 0 ? 0 : 2;
   }
   OKR(ensure_job_buffers(c));
+  c->staged_jobs = 0;  // the solver rewrites the staged poses and job table
   // (the natural-order kernels size their per-job partial buffers by the job count of a launch: one range there)
   const int nh = (n >= 8 && use_sorted(c)) ? 2 : 1;
   if (nh == 2 && !c->stream2) {
@@ -821,15 +880,8 @@ int nid_solve(nid_ctx* c, int pair, double pose7[7], int max_iters, double delta
 int nid_hard_eval_jobs(nid_ctx* c, int n_jobs, const int* job_pair, const double* poses, double* total, double* nid_cells) {
   if (!c || !poses) { set_error("bad argument"); return NID_ERR_ARG; }
   CU(cudaSetDevice(c->device), "cudaSetDevice");
-  if (n_jobs < 1 || n_jobs > c->max_jobs) { set_error("n_jobs out of range"); return NID_ERR_ARG; }
-  for (int j = 0; j < n_jobs; j++) {
-    int pr = job_pair ? job_pair[j] : 0;
-    if (pr < 0 || pr >= c->n_pairs || !c->pair_set[pr]) { set_error("job_pair invalid or pair not set"); return NID_ERR_ARG; }
-    c->h_job_pair[j] = pr;
-  }
-  memcpy(c->h_poses, poses, sizeof(double) * 16 * n_jobs);
-  CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16 * n_jobs, cudaMemcpyHostToDevice, c->stream), "H2D poses");
-  CU(cudaMemcpyAsync(c->job_pair, c->h_job_pair, sizeof(int) * n_jobs, cudaMemcpyHostToDevice, c->stream), "H2D job_pair");
+  OKR(stage_jobs(c, n_jobs, job_pair, poses, 1));
+  c->staged_jobs = 0;  // (not evaluation jobs: the pairs need not be prepared)
   OKR(launch_hard(c, n_jobs));
   const size_t w = c->ncell + 1;
   CU(cudaMemcpyAsync(c->h_out, c->hard, sizeof(double) * w * n_jobs, cudaMemcpyDeviceToHost, c->stream), "D2H hard");
@@ -847,9 +899,9 @@ static int warp_sample_common(nid_ctx* c, int pair, const double T_cw1[16], int 
   CU(cudaSetDevice(c->device), "cudaSetDevice");
   if (f64 && !c->d_pix) OKR(dalloc(&c->d_pix, (size_t)8 * c->N, "d_pix"));
   if (!f64 && !c->d_pix4) OKR(dalloc(&c->d_pix4, (size_t)4 * c->N, "d_pix4"));
-  memcpy(c->h_poses, T_cw1, sizeof(double) * 16);
-  CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream), "H2D pose");
-  return launch_warp_sample(c, pair, c->poses, f64);
+  memcpy(c->h_aux_pose, T_cw1, sizeof(double) * 16);  // (both callers synchronise before returning)
+  CU(cudaMemcpyAsync(c->aux_pose, c->h_aux_pose, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream), "H2D pose");
+  return launch_warp_sample(c, pair, c->aux_pose, f64);
 }
 
 int nid_warp_sample(nid_ctx* c, int pair, const double T_cw1[16], float* out) {
@@ -864,17 +916,15 @@ int nid_warp_sample_jobs(nid_ctx* c, int n_jobs, const int* job_pair, const doub
   CU(cudaSetDevice(c->device), "cudaSetDevice");
   if (n_jobs < 1 || n_jobs > c->max_jobs) { set_error("n_jobs out of range"); return NID_ERR_ARG; }
   if (c->sell_points) { set_error("nid_warp_sample_jobs needs depth pairs (nid_set_pair), not caller-supplied points"); return NID_ERR_UNSUPPORTED; }
-  if (!c->d_tex2) { set_error("nid_warp_sample_jobs needs the packed target textures (8 to 40 bins)"); return NID_ERR_UNSUPPORTED; }
-  for (int j = 0; j < n_jobs; j++) {
-    const int pr = job_pair ? job_pair[j] : 0;
-    if (pr < 0 || pr >= c->n_pairs || !c->pair_set[pr]) { set_error("job_pair invalid or pair not set"); return NID_ERR_ARG; }
-    c->h_job_pair[j] = pr;
-  }
+  if (!c->d_tex2) { set_error("nid_warp_sample_jobs needs the packed target textures (6 to 40 bins)"); return NID_ERR_UNSUPPORTED; }
   if (!c->d_pix4_jobs) OKR(dalloc(&c->d_pix4_jobs, (size_t)4 * c->N * c->max_jobs, "d_pix4_jobs"));
-  memcpy(c->h_poses, poses, sizeof(double) * 16 * n_jobs);
-  CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16 * n_jobs, cudaMemcpyHostToDevice, c->stream), "H2D poses");
-  CU(cudaMemcpyAsync(c->job_pair, c->h_job_pair, sizeof(int) * n_jobs, cudaMemcpyHostToDevice, c->stream), "H2D job_pair");
-  OKR(launch_warp_sample_jobs(c, n_jobs, (float4*)c->d_pix4_jobs));
+  OKR(stage_jobs(c, n_jobs, job_pair, poses, 1));
+  c->staged_jobs = 0;  // (not evaluation jobs: the pairs need not be prepared)
+  // pairs uploaded as raw 16-bit depth are read as such (2 B/px); a mixed batch falls back to the fp64 planes, which
+  // every pair has
+  bool u16 = true;
+  for (int j = 0; j < n_jobs; j++) u16 = u16 && c->pair_u16[c->h_job_pair[j]];
+  OKR(launch_warp_sample_jobs(c, n_jobs, (float4*)c->d_pix4_jobs, u16));
   if (out) CU(cudaMemcpyAsync(out, c->d_pix4_jobs, sizeof(float) * 4 * c->N * (size_t)n_jobs, cudaMemcpyDefault, c->stream), "D2H pix4 jobs");
   CU(cudaStreamSynchronize(c->stream), "sync warp_sample_jobs");
   return NID_OK;
@@ -892,6 +942,7 @@ int nid_debug_hist(nid_ctx* c, int job, int cell_index, double* P_t, double* P_j
   const size_t hs = (size_t)c->bins * c->bins + c->bins;
   if (!c->hist) { set_error("set option keep_hist=1 before the evaluation"); return NID_ERR_STATE; }
   const double* src = c->hist + ((size_t)job * c->ncell + cell_index) * hs;
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
   CU(cudaStreamSynchronize(c->stream), "sync");
   if (P_j) CU(cudaMemcpy(P_j, src, sizeof(double) * c->bins * c->bins, cudaMemcpyDeviceToHost), "D2H P_j");
   if (P_t) CU(cudaMemcpy(P_t, src + c->bins * c->bins, sizeof(double) * c->bins, cudaMemcpyDeviceToHost), "D2H P_t");
@@ -910,6 +961,7 @@ void* nid_stream(nid_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int nid_event_record(nid_ctx* c, int slot) {
   if (!c || slot < 0 || slot > 1) { set_error("bad argument"); return NID_ERR_ARG; }
+  CU(cudaSetDevice(c->device), "cudaSetDevice");
   if (!c->ev[slot]) CU(cudaEventCreate(&c->ev[slot]), "cudaEventCreate");
   CU(cudaEventRecord(c->ev[slot], c->stream), "cudaEventRecord");
   return NID_OK;
@@ -924,10 +976,14 @@ int nid_event_elapsed_ms(nid_ctx* c, float* ms) {
 
 int nid_set_option(nid_ctx* c, const char* key, int value) {
   if (!c || !key) { set_error("bad argument"); return NID_ERR_ARG; }
-  if (!strcmp(key, "force_strips")) { c->opt_force_strips = value; return NID_OK; }
+  if (!strcmp(key, "force_strips")) {
+    if (value < 0) { set_error("force_strips must be >= 0 (0 = automatic)"); return NID_ERR_ARG; }
+    c->opt_force_strips = value;
+    return NID_OK;
+  }
   if (!strcmp(key, "path")) {
     if (value < 0 || value > 2) { set_error("path must be 0 (auto), 1 (natural) or 2 (sorted)"); return NID_ERR_ARG; }
-    if (value == 2 && (c->bins > NID_SORTED_MAX_BINS || c->bins < 8)) { set_error("the sorted path supports 8 to 40 bins"); return NID_ERR_UNSUPPORTED; }
+    if (value == 2 && (c->bins > NID_SORTED_MAX_BINS || c->bins < NID_SORTED_MIN_BINS)) { set_error("the sorted path supports 6 to 40 bins"); return NID_ERR_UNSUPPORTED; }
     c->opt_path = value;
     return NID_OK;
   }

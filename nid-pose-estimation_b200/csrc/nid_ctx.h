@@ -8,7 +8,9 @@
 #include "../../include/nid_b200.h"
 
 #define NID_NCLS 257  /* reference-intensity classes 0..255 + 256 = valid point without reference sample */
+#define NID_SORTED_MIN_BINS 6  /* the two 3x3 end blocks of the basis fold must not overlap */
 #define NID_SORTED_MAX_BINS 40 /* k_assemble keeps 5*B^2 + 257*B doubles in shared memory */
+#define NID_STAGE_RING 4
 #define NID_TASK_PX_MAX 256 /* upper bound of the pixels per task of the sorted path (option "task_px") */
 
 namespace nid {
@@ -81,11 +83,19 @@ struct nid_ctx {
   int n_pairs = 0, max_jobs = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  int* h_stage = nullptr;      // pinned staging arena of nid_prepare's tables
-  size_t h_stage_cap = 0;
-  unsigned int* h_cnt = nullptr;  // pinned copy of one pair's (cell, class) counts
-  size_t h_cnt_cap = 0;
-  int* chunk_cnt = nullptr;    // [ncell][chunks of 256 px][NID_NCLS] scratch of the regrouping scatter (nid_prepare)
+  int* chunk_cnt = nullptr;    // [setup_batch][ncell][chunks of 256 px][NID_NCLS] scratch of the regrouping scatter
+  // batched pair set-up (nid_set_pairs_u16 / nid_prepare_pairs): up to setup_batch pairs per launch
+  int setup_batch = 1;
+  int* lay_tot = nullptr;      // [setup_batch][ncell][3] tasks, slices, pixel slots of every cell
+  int* lay_base = nullptr;     // [setup_batch][ncell][3] their exclusive scans over the cells of a pair
+  double* prep_poses = nullptr;  // [setup_batch][16] initial poses of the batch
+  uint16_t* depth16 = nullptr; // [n_pairs][N] raw 16-bit depth (allocated by the first nid_set_pairs_u16)
+  double* depth_factor = nullptr;  // [n_pairs]
+  std::vector<char> pair_u16;  // the pair's depth16 plane is valid
+  char* h_arena = nullptr;     // pinned bump arena for the small per-pair arrays of the asynchronous set-up calls
+  size_t h_arena_cap = 0, h_arena_used = 0;
+  char* h_res = nullptr;       // pinned results of nid_prepare_pairs (n_c, H_ref, task and slice counts)
+  size_t h_res_cap = 0;
   cudaStream_t stream2 = nullptr;  // second stream of the ping-pong LM driver (nid_solve_jobs)
   long long launches = 0;
 
@@ -125,7 +135,7 @@ struct nid_ctx {
   cudaTextureObject_t* d_tex2 = nullptr;
   unsigned* fp1 = nullptr;     // [n_pairs][N]
   std::vector<double> h_Twc0, h_cam;  // host copies per pair (geometry tables are built on the host)
-  unsigned* d_pack = nullptr;  // [N] scratch for the packed texture
+  unsigned* d_pack = nullptr;  // [setup_batch][N] scratch for the packed textures
   size_t g_stride = 0;
   int opt_path = 0;            // 0 auto, 1 natural-order atomics (v1), 2 sorted
   int opt_keep_hist = 0;
@@ -149,9 +159,20 @@ struct nid_ctx {
   double *ht = nullptr, *hj = nullptr, *err = nullptr, *der = nullptr, *gn = nullptr;
   double* hard = nullptr;      // [jobs][ncell+1]
   size_t part_slots = 0;       // capacity in (job,strip) units
-  // pinned host mirrors
-  double* h_poses = nullptr;
-  int* h_job_pair = nullptr;
+  // pinned host mirrors of the staged jobs: a ring of NID_STAGE_RING slots, each guarded by an event recorded after
+  // the slot's H2D copies, so that a slot is never rewritten while a copy from it is still pending (the staged
+  // API is asynchronous: stage, eval, stage, eval ... without a synchronisation in between)
+  double* h_poses = nullptr;      // current slot: [max_jobs][16]
+  int* h_job_pair = nullptr;      // current slot: [max_jobs]
+  double* h_poses_ring = nullptr;
+  int* h_job_pair_ring = nullptr;
+  cudaEvent_t stage_ev[NID_STAGE_RING] = {};
+  int stage_slot = 0;
+  int staged_jobs = 0;            // jobs of the last nid_stage_jobs (nid_eval_staged refuses more)
+  // nid_prepare / nid_warp_sample* take their pose through their own scratch (both calls are blocking), so that
+  // they never disturb staged jobs
+  double* h_aux_pose = nullptr;   // pinned [16]
+  double* aux_pose = nullptr;     // device [16]
   double* h_out = nullptr;     // [max_jobs][ncell*8 + 44]
   int opt_force_strips = 0;
   double* lm_trace = nullptr;  // set by nid_solve for the duration of one call
@@ -190,16 +211,15 @@ int ensure_job_buffers(nid_ctx* c);
 // sorted path (nid_sorted.cu)
 int sorted_init(nid_ctx* c);
 int launch_count_classes(nid_ctx* c, int pair);
-int launch_scatter(nid_ctx* c, int pair);
-int launch_pack_tex(nid_ctx* c, int pair, unsigned* d_out);
-int launch_pack_fp(nid_ctx* c, int pair);
+int launch_layout_and_scatter(nid_ctx* c, int pair0, int n);
+int launch_pack(nid_ctx* c, int pair0, int n);
 int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int want_jac);
-int launch_href(nid_ctx* c, int pair);
+int launch_href(nid_ctx* c, int pair0, int n);
 
 // kernel launchers (nid_kernels.cu)
 int launch_build_lut(nid_ctx* c);
-int launch_points(nid_ctx* c, int pair);
-int launch_prepare(nid_ctx* c, int pair, const double* d_pose16);
+int launch_points(nid_ctx* c, int pair0, int n, bool u16);
+int launch_prepare(nid_ctx* c, int pair0, int n, const double* d_poses16);
 int launch_ref_weights(nid_ctx* c, int pair);
 int launch_points_aos(nid_ctx* c, int pair, double* d_out);
 int launch_eval(nid_ctx* c, int n_jobs, int want_jac);
@@ -207,7 +227,7 @@ int launch_eval_natural(nid_ctx* c, int n_jobs, int want_jac);
 int launch_gn(nid_ctx* c, int n_jobs, double delta);
 int launch_hard(nid_ctx* c, int n_jobs);
 int launch_warp_sample(nid_ctx* c, int pair, const double* d_pose16, int f64);
-int launch_warp_sample_jobs(nid_ctx* c, int n_jobs, float4* d_out);
+int launch_warp_sample_jobs(nid_ctx* c, int n_jobs, float4* d_out, bool u16);
 int launch_check_integral(nid_ctx* c, const double* d_src, uint8_t* d_dst, int is_ref);
 int launch_chi2(nid_ctx* c, int n_jobs, double delta);
 int launch_eval_mixed(nid_ctx* c, int base, int nj, int nt, double delta);

@@ -74,10 +74,14 @@ __device__ __forceinline__ bool inb_jac(double u, double v, int rows, int cols) 
 }
 
 // types_six_dof_expmap.h:310-328: bilinear with (int) truncation (so u in (-1,0) extrapolates from
-// columns 0/1, which the gradient taps u-1 / v-1 rely on)
+// columns 0/1, which the gradient taps u-1 / v-1 rely on). The Jacobian bounds test admits u == 0 and v == 0
+// exactly (types_six_dof_expmap.cpp:433), whose taps u-1 / v-1 == -1.0 truncate to column / row -1: upstream
+// that is an out-of-bounds cv::Mat access (undefined). Defined here, and in the oracle, as the continuous
+// extension of the (-1, 0) case: the index is clamped to 0 and the fraction becomes -1 (extrapolation from
+// columns / rows 0 and 1), so no byte outside the image is ever read.
 __device__ __forceinline__ double interp_u8(const uint8_t* __restrict__ im, int cols, double x, double y) {
-  int ix = (int)x;
-  int iy = (int)y;
+  int ix = max((int)x, 0);
+  int iy = max((int)y, 0);
   double dx = x - (double)ix;
   double dy = y - (double)iy;
   double dxdy = __dmul_rn(dx, dy);

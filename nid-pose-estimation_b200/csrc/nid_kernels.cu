@@ -3,6 +3,8 @@
 // roofline of each kernel.
 #include <math.h>
 
+#include <algorithm>
+
 #include "nid_ctx.h"
 #include "nid_device.cuh"
 
@@ -33,22 +35,33 @@ __global__ void k_build_lut(int bins, double* __restrict__ lut_w, int* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// a1: depth -> world points (CudaPoints3d.cu:5-32), SoA planes, NaN for invalid depth
-__global__ void k_points(int rows, int cols, const double* __restrict__ depth, const double* __restrict__ Twc0,
-                         const double* __restrict__ camp, double* __restrict__ pwx, double* __restrict__ pwy,
-                         double* __restrict__ pwz) {
+// a1: depth -> world points (CudaPoints3d.cu:5-32), SoA planes, NaN for invalid depth. Pair pair0 + blockIdx.y.
+// U16: the depth arrives as the raw 16-bit plane of the dataset and is converted like the reference's driver does,
+// `depth.convertTo(CV_64F, depth_factor)` (NID_pose_estimation.cpp:105-106): one rounding of raw * factor; the fp64
+// plane is kept for the regrouping scatter and kernel 1.
+template <bool U16>
+__global__ void k_points(int rows, int cols, int pair0, double* __restrict__ depth_all, const uint16_t* __restrict__ d16_all,
+                         const double* __restrict__ factor_all, const double* __restrict__ Twc0_all,
+                         const double* __restrict__ cam_all, double* __restrict__ pwx_all, double* __restrict__ pwy_all,
+                         double* __restrict__ pwz_all) {
   const int N = rows * cols;
+  const int pair = pair0 + blockIdx.y;
+  const size_t b = (size_t)pair * N;
+  const double* camp = cam_all + 4 * pair;
   Cam cam{camp[0], camp[1], camp[2], camp[3]};
   double T[16];
 #pragma unroll
-  for (int i = 0; i < 16; i++) T[i] = Twc0[i];
+  for (int i = 0; i < 16; i++) T[i] = Twc0_all[16 * pair + i];
+  const double factor = U16 ? factor_all[pair] : 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-    double z = depth[i];
+    double z;
+    if (U16) { z = __dmul_rn((double)d16_all[b + i], factor); depth_all[b + i] = z; }
+    else z = depth_all[b + i];
     double x = nan(""), y = nan(""), zz = nan("");
     if (!(z < 0.01 || z > 100)) {
       backproject(T, cam, z, i / cols, i % cols, x, y, zz);
     }
-    pwx[i] = x; pwy[i] = y; pwz[i] = zz;
+    pwx_all[b + i] = x; pwy_all[b + i] = y; pwz_all[b + i] = zz;
   }
 }
 
@@ -96,12 +109,14 @@ __global__ void k_check_integral(int N, const double* __restrict__ src, uint8_t*
 // ------------------------------------------------------------------------------------------------
 // a2 part 1: in-bounds flag at the prepare pose and per-cell counts of reference intensities
 // (CudaComputeHref.cu:76-131; computeHref types_six_dof_expmap.cpp:655-702)
-__global__ void k_prepare(EvalParams p, int pair, const double* __restrict__ pose16, uint8_t* __restrict__ inb0,
+// Pair pair0 + blockIdx.y at the initial pose poses16[16 * blockIdx.y].
+__global__ void k_prepare(EvalParams p, int pair0, const double* __restrict__ poses16, uint8_t* __restrict__ inb0,
                           unsigned int* __restrict__ cnt) {
+  const int pair = pair0 + blockIdx.y;
   const size_t base = (size_t)pair * p.N;
   const double* cp = p.cam + 4 * pair;
   Cam cam{cp[0], cp[1], cp[2], cp[3]};
-  Pose P = load_pose(pose16);
+  Pose P = load_pose(poses16 + 16 * blockIdx.y);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.N; i += gridDim.x * blockDim.x) {
     int row = i / p.cols, col = i % p.cols;
     uint8_t flag = 0;
@@ -122,9 +137,10 @@ __global__ void k_prepare(EvalParams p, int pair, const double* __restrict__ pos
 }
 
 // a2 part 2: n_c, reference marginal and H_ref per cell (CudaComputeHref.cu:204-221;
-// types_six_dof_expmap.cpp:710-723). One block per cell, one thread per intensity value.
-__global__ void __launch_bounds__(256) k_href(EvalParams p, int pair, const unsigned int* __restrict__ cnt,
+// types_six_dof_expmap.cpp:710-723). One block per (cell, pair pair0 + blockIdx.y), one thread per intensity value.
+__global__ void __launch_bounds__(256) k_href(EvalParams p, int pair0, const unsigned int* __restrict__ cnt,
                                               int* __restrict__ n_c, double* __restrict__ href) {
+  const int pair = pair0 + blockIdx.y;
   extern __shared__ double sm[];
   double* pro = sm;  // [bins]
   __shared__ double s_con[256][4];  // class v's contribution to bins k_r(v) .. k_r(v)+3
@@ -597,10 +613,10 @@ int launch_build_lut(nid_ctx* c) {
   return NID_OK;
 }
 
-int launch_points(nid_ctx* c, int pair) {
-  size_t b = (size_t)pair * c->N;
-  k_points<<<grid_for(c->N, 256, c->sm_count * 8), 256, 0, c->stream>>>(c->rows, c->cols, c->depth + b, c->Twc0 + 16 * pair,
-                                                                       c->cam + 4 * pair, c->pwx + b, c->pwy + b, c->pwz + b);
+int launch_points(nid_ctx* c, int pair0, int n, bool u16) {
+  const dim3 grid(grid_for(c->N, 256, std::max(8, c->sm_count * 8 / n)), n);
+  if (u16) k_points<true><<<grid, 256, 0, c->stream>>>(c->rows, c->cols, pair0, c->depth, c->depth16, c->depth_factor, c->Twc0, c->cam, c->pwx, c->pwy, c->pwz);
+  else k_points<false><<<grid, 256, 0, c->stream>>>(c->rows, c->cols, pair0, c->depth, nullptr, nullptr, c->Twc0, c->cam, c->pwx, c->pwy, c->pwz);
   NID_LAUNCH_CHECK(c, "k_points");
   return NID_OK;
 }
@@ -631,18 +647,19 @@ int launch_check_integral(nid_ctx* c, const double* d_src, uint8_t* d_dst, int i
   return NID_OK;
 }
 
-int launch_prepare(nid_ctx* c, int pair, const double* d_pose16) {
+int launch_prepare(nid_ctx* c, int pair0, int n, const double* d_poses16) {
   EvalParams p = make_params(c, 1);
-  cudaError_t e = cudaMemsetAsync(c->cnt + (size_t)pair * c->ncell * NID_NCLS, 0, sizeof(unsigned int) * c->ncell * NID_NCLS, c->stream);
+  cudaError_t e = cudaMemsetAsync(c->cnt + (size_t)pair0 * c->ncell * NID_NCLS, 0, sizeof(unsigned int) * c->ncell * NID_NCLS * n, c->stream);
   if (e != cudaSuccess) return check_cuda(e, "memset cnt");
-  k_prepare<<<grid_for(c->N, 256, c->sm_count * 8), 256, 0, c->stream>>>(p, pair, d_pose16, c->inb0, c->cnt);
+  const dim3 grid(grid_for(c->N, 256, std::max(8, c->sm_count * 8 / n)), n);
+  k_prepare<<<grid, 256, 0, c->stream>>>(p, pair0, d_poses16, c->inb0, c->cnt);
   NID_LAUNCH_CHECK(c, "k_prepare");
   return NID_OK;
 }
 
-int launch_href(nid_ctx* c, int pair) {
+int launch_href(nid_ctx* c, int pair0, int n) {
   EvalParams p = make_params(c, 1);
-  k_href<<<c->ncell, 256, sizeof(double) * c->bins, c->stream>>>(p, pair, c->cnt, c->n_c, c->href);
+  k_href<<<dim3(c->ncell, n), 256, sizeof(double) * c->bins, c->stream>>>(p, pair0, c->cnt, c->n_c, c->href);
   NID_LAUNCH_CHECK(c, "k_href");
   return NID_OK;
 }

@@ -94,9 +94,10 @@ __device__ __forceinline__ int sell_key(const EvalParams& p, size_t base, int c,
   return p.inb0[i] ? (int)p.im0[i] : 256;
 }
 
-__global__ void __launch_bounds__(256) k_chunk_count(EvalParams p, int pair, int* __restrict__ chunk_cnt) {
+__global__ void __launch_bounds__(256) k_chunk_count(EvalParams p, int pair0, int* __restrict__ chunk_cnt_all) {
   __shared__ int s_cnt[NID_NCLS];
-  const int chunk = blockIdx.x, c = blockIdx.y;
+  const int chunk = blockIdx.x, c = blockIdx.y, pair = pair0 + blockIdx.z;
+  int* chunk_cnt = chunk_cnt_all + (size_t)blockIdx.z * p.ncell * gridDim.x * NID_NCLS;
   for (int k = threadIdx.x; k < NID_NCLS; k += blockDim.x) s_cnt[k] = 0;
   __syncthreads();
   int row, col;
@@ -108,9 +109,10 @@ __global__ void __launch_bounds__(256) k_chunk_count(EvalParams p, int pair, int
 }
 
 // in place: chunk_cnt[cell][chunk][class] -> number of pixels of that class in the earlier chunks of the cell
-__global__ void __launch_bounds__(256) k_chunk_scan(int ncell, int nchunks, int* __restrict__ chunk_cnt) {
+__global__ void __launch_bounds__(256) k_chunk_scan(int ncell, int nchunks, int* __restrict__ chunk_cnt_all) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncell * NID_NCLS) return;
+  int* chunk_cnt = chunk_cnt_all + (size_t)blockIdx.y * ncell * nchunks * NID_NCLS;
   const int c = i / NID_NCLS, k = i - c * NID_NCLS;
   int* q = chunk_cnt + (size_t)c * nchunks * NID_NCLS + k;
   int run = 0, j = 0;
@@ -125,13 +127,16 @@ __global__ void __launch_bounds__(256) k_chunk_scan(int ncell, int nchunks, int*
 }
 
 template <bool PTS>
-__global__ void __launch_bounds__(256) k_scatter_sell(EvalParams p, int pair, int L, const double* __restrict__ depth,
-                                                      const int* __restrict__ task_pos, const int* __restrict__ chunk_off,
+__global__ void __launch_bounds__(256) k_scatter_sell(EvalParams p, int pair0, int L, const double* __restrict__ depth_all,
+                                                      const int* __restrict__ task_pos_all, const int* __restrict__ chunk_off_all,
                                                       double* __restrict__ sd0, double* __restrict__ sd1,
                                                       double* __restrict__ sd2, unsigned* __restrict__ sid) {
   __shared__ int run[NID_NCLS];
   __shared__ int s_cts[NID_NCLS + 1];
-  const int chunk = blockIdx.x, c = blockIdx.y;
+  const int chunk = blockIdx.x, c = blockIdx.y, pair = pair0 + blockIdx.z;
+  const double* depth = depth_all + (size_t)pair * p.N;
+  const int* task_pos = task_pos_all + (size_t)pair * p.max_tasks;
+  const int* chunk_off = chunk_off_all + (size_t)blockIdx.z * p.ncell * gridDim.x * NID_NCLS;
   if (p.n_c[pair * p.ncell + c] < NID_MIN_CELL_POINTS) return;  // inactive cells have no tasks
   const size_t base = (size_t)pair * p.N;
   const int* cts = p.cls_task_start + ((size_t)pair * p.ncell + c) * (NID_NCLS + 1);
@@ -166,12 +171,200 @@ __global__ void __launch_bounds__(256) k_scatter_sell(EvalParams p, int pair, in
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Device-side construction of the task / slice tables of the sliced layout from the (cell, class) counts of
+// k_prepare: no D2H of the counts, no host loops, no H2D of tables, any number of pairs per launch.
+// Per cell the tasks are numbered in class order (class v contributes ceil(cnt_v / L) tasks of L pixels, the last one
+// possibly shorter); slices take the cell's tasks longest first, 32 at a time, ties in task order: every full task (in
+// task order), then the partial tasks by decreasing length (ties by class). A slice is as long as its first task, so
+// all slices that start with a full task hold 32 * L pixel slots and only the last <= 9 slices of a cell need a running sum.
+#define NID_LAYOUT_THREADS 288  // >= NID_NCLS, whole warps
+struct CellLayoutSm {
+  int ts[NID_NCLS + 1];   // first task of every class, cell-local
+  int fs[NID_NCLS + 1];   // full tasks in the classes before
+  int nf[NID_NCLS];       // full tasks of the class
+  int r[NID_NCLS];        // pixels of the class's partial task (0: none)
+  int prank[NID_NCLS];    // rank of that partial task among the cell's partial tasks
+  int sorted_r[NID_NCLS]; // partial-task lengths in rank order
+  int tail_off[NID_NCLS / 32 + 4];  // pixel-slot offset of slice SF + j (the slices that start with a partial task)
+  int wsum[2][NID_LAYOUT_THREADS / 32];
+  int T, F, S, SF, slots;
+};
+
+__device__ __forceinline__ void cell_layout(const unsigned* __restrict__ cnt, int L, CellLayoutSm& s) {
+  const int v = threadIdx.x, lane = v & 31, w = v >> 5;
+  constexpr int NW = NID_LAYOUT_THREADS / 32;
+  const int c = v < NID_NCLS ? (int)cnt[v] : 0;
+  {  // n_c = pixels with a reference sample; cells under 300 get no tasks (computeH.cu:271)
+    int n = v < 256 ? c : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) s.wsum[0][w] = n;
+  }
+  __syncthreads();
+  int n_c = 0;
+#pragma unroll
+  for (int i = 0; i < NW; i++) n_c += s.wsum[0][i];
+  __syncthreads();
+  const int cc = n_c >= NID_MIN_CELL_POINTS ? c : 0;
+  const int nf = cc / L, r = cc - nf * L, nt = nf + (r > 0 ? 1 : 0);
+  int a = nt, b = nf;  // inclusive scans over the classes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b, o);
+    if (lane >= o) { a += x; b += y; }
+  }
+  if (lane == 31) { s.wsum[0][w] = a; s.wsum[1][w] = b; }
+  __syncthreads();
+  int oa = 0, ob = 0;
+  for (int i = 0; i < w; i++) { oa += s.wsum[0][i]; ob += s.wsum[1][i]; }
+  if (v < NID_NCLS) {
+    s.ts[v] = oa + a - nt; s.fs[v] = ob + b - nf;
+    s.nf[v] = nf; s.r[v] = r;
+    if (v == NID_NCLS - 1) { s.ts[NID_NCLS] = oa + a; s.fs[NID_NCLS] = ob + b; }
+  }
+  __syncthreads();
+  if (v < NID_NCLS && r > 0) {  // longest first, ties in class (= task) order
+    int g = 0;
+    for (int q = 0; q < NID_NCLS; q++) {
+      const int rq = s.r[q];
+      g += (rq > r || (rq == r && q < v)) ? 1 : 0;
+    }
+    s.prank[v] = g;
+    s.sorted_r[g] = r;
+  }
+  __syncthreads();
+  if (v == 0) {
+    const int T = s.ts[NID_NCLS], F = s.fs[NID_NCLS];
+    const int S = (T + 31) >> 5, SF = (F + 31) >> 5;
+    int off = SF * 32 * L;
+    s.tail_off[0] = off;
+    for (int j = 0; SF + j < S; j++) {
+      off += ((s.sorted_r[32 * (SF + j) - F] + 3) >> 2) * 128;
+      s.tail_off[j + 1] = off;
+    }
+    s.T = T; s.F = F; s.S = S; s.SF = SF; s.slots = off;
+  }
+  __syncthreads();
+}
+
+// totals per (pair, cell): tasks, slices, pixel slots
+__global__ void __launch_bounds__(NID_LAYOUT_THREADS) k_layout_totals(int pair0, int ncell, int L, const unsigned* __restrict__ cnt,
+                                                                      int* __restrict__ tot) {
+  __shared__ CellLayoutSm s;
+  const int c = blockIdx.x, pair = pair0 + blockIdx.y;
+  cell_layout(cnt + ((size_t)pair * ncell + c) * NID_NCLS, L, s);
+  if (threadIdx.x == 0) {
+    int* o = tot + ((size_t)blockIdx.y * ncell + c) * 3;
+    o[0] = s.T; o[1] = s.S; o[2] = s.slots;
+  }
+}
+
+// exclusive scan of the totals over the cells of a pair -> bases; one CTA per pair
+__global__ void __launch_bounds__(256) k_layout_scan(EvalParams p, int pair0, const int* __restrict__ tot, int* __restrict__ base,
+                                                     int* __restrict__ cell_task_start, int* __restrict__ cell_slice_start,
+                                                     int* __restrict__ ntasks, int* __restrict__ nslices, int* __restrict__ sl_off,
+                                                     int* __restrict__ overflow) {
+  __shared__ int wsum[3][8];
+  __shared__ int carry[3];
+  const int pair = pair0 + blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int* t = tot + (size_t)blockIdx.x * p.ncell * 3;
+  int* bs = base + (size_t)blockIdx.x * p.ncell * 3;
+  if (threadIdx.x < 3) carry[threadIdx.x] = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < p.ncell; c0 += 256) {
+    const int c = c0 + threadIdx.x;
+    int x[3], a[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { x[k] = c < p.ncell ? t[3 * c + k] : 0; a[k] = x[k]; }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int y = __shfl_up_sync(0xffffffffu, a[k], o);
+        if (lane >= o) a[k] += y;
+      }
+    if (lane == 31)
+#pragma unroll
+      for (int k = 0; k < 3; k++) wsum[k][w] = a[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      int o = carry[k];
+      for (int i = 0; i < w; i++) o += wsum[k][i];
+      a[k] += o - x[k];  // exclusive
+    }
+    if (c < p.ncell) {
+      bs[3 * c] = a[0]; bs[3 * c + 1] = a[1]; bs[3 * c + 2] = a[2];
+      cell_task_start[(size_t)pair * (p.ncell + 1) + c] = a[0];
+      cell_slice_start[(size_t)pair * (p.ncell + 1) + c] = a[1];
+    }
+    __syncthreads();
+    if (threadIdx.x == 255)
+#pragma unroll
+      for (int k = 0; k < 3; k++) carry[k] = a[k] + x[k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int nt = carry[0], ns = carry[1], slots = carry[2];
+    cell_task_start[(size_t)pair * (p.ncell + 1) + p.ncell] = nt;
+    cell_slice_start[(size_t)pair * (p.ncell + 1) + p.ncell] = ns;
+    ntasks[pair] = nt;
+    nslices[pair] = ns;
+    sl_off[(size_t)pair * (p.max_slices + 1) + min(ns, p.max_slices)] = slots;
+    if (nt > p.max_tasks || ns > p.max_slices || (size_t)slots > p.sell_cap) atomicExch(overflow, 1);  // (cannot happen by construction)
+  }
+}
+
+// the tables of one (pair, cell)
+__global__ void __launch_bounds__(NID_LAYOUT_THREADS) k_layout_write(EvalParams p, int pair0, int L, const unsigned* __restrict__ cnt,
+                                                                     const int* __restrict__ base, int2* __restrict__ tasks,
+                                                                     int* __restrict__ task_pos, int* __restrict__ sl_task,
+                                                                     int* __restrict__ sl_off, int* __restrict__ sl_cell,
+                                                                     int* __restrict__ cls_task_start) {
+  __shared__ CellLayoutSm s;
+  const int c = blockIdx.x, pair = pair0 + blockIdx.y;
+  cell_layout(cnt + ((size_t)pair * p.ncell + c) * NID_NCLS, L, s);
+  const int* bs = base + ((size_t)blockIdx.y * p.ncell + c) * 3;
+  const int tb = bs[0], sb = bs[1], pb = bs[2];
+  if (tb + s.T > p.max_tasks || sb + s.S > p.max_slices) return;  // flagged by k_layout_scan
+  for (int v = threadIdx.x; v <= NID_NCLS; v += blockDim.x)
+    cls_task_start[((size_t)pair * p.ncell + c) * (NID_NCLS + 1) + v] = tb + s.ts[v];
+  int2* tk = tasks + (size_t)pair * p.max_tasks + tb;
+  int* tp = task_pos + (size_t)pair * p.max_tasks + tb;
+  int* st = sl_task + ((size_t)pair * p.max_slices + sb) * 32;
+  for (int t = threadIdx.x; t < s.T; t += blockDim.x) {
+    int lo = 0, hi = NID_NCLS;  // class of task t: the last v with ts[v] <= t
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s.ts[mid] <= t) lo = mid; else hi = mid;
+    }
+    const int v = lo, i = t - s.ts[v];
+    const bool full = i < s.nf[v];
+    const int len = full ? L : s.r[v];
+    const int rank = full ? s.fs[v] + i : s.F + s.prank[v];
+    const int slice = rank >> 5, ln = rank & 31;
+    const int off = slice < s.SF ? slice * 32 * L : s.tail_off[slice - s.SF];
+    tk[t] = make_int2(i * L, len | (v << 9) | (c << 18));
+    tp[t] = pb + off + 4 * ln;
+    st[rank] = tb + t;
+  }
+  for (int q = s.T + threadIdx.x; q < s.S * 32; q += blockDim.x) st[q] = -1;  // empty lanes of the cell's last slice
+  for (int sl = threadIdx.x; sl < s.S; sl += blockDim.x) {
+    sl_off[(size_t)pair * (p.max_slices + 1) + sb + sl] = pb + (sl < s.SF ? sl * 32 * L : s.tail_off[sl - s.SF]);
+    sl_cell[(size_t)pair * p.max_slices + sb + sl] = c;
+  }
+}
+
 // Packed target texture: texel = I | (Gx+256) << 8 | (Gy+256) << 17 with the central differences
 // Gx = I(x+1,y) - I(x-1,y), Gy = I(x,y+1) - I(x,y-1) (types_six_dof_expmap.cpp:434-435 before the /2);
 // one 2x2 gather then holds everything the bilinear samples of I, dI/du and dI/dv need. Border texels
 // use clamped neighbours and are never consumed (the first row/column takes the literal formula).
-__global__ void k_pack_tex(int rows, int cols, const uint8_t* __restrict__ im, unsigned* __restrict__ out) {
+__global__ void k_pack_tex(int rows, int cols, int pair0, const uint8_t* __restrict__ im_all, unsigned* __restrict__ out_all) {
   const int N = rows * cols;
+  const uint8_t* im = im_all + (size_t)(pair0 + blockIdx.y) * N;
+  unsigned* out = out_all + (size_t)blockIdx.y * N;  // scratch of the batch
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     const int y = i / cols, x = i % cols;
     const int xm = max(x - 1, 0), xp = min(x + 1, cols - 1), ym = max(y - 1, 0), yp = min(y + 1, rows - 1);
@@ -184,8 +377,10 @@ __global__ void k_pack_tex(int rows, int cols, const uint8_t* __restrict__ im, u
 
 // Footprint-packed target image for pass 1: out[y*cols + x] = I(x,y) | I(x+1,y)<<8 | I(x,y+1)<<16 | I(x+1,y+1)<<24
 // (neighbours clamped at the border; in-bounds samples never reach it): one aligned 32-bit load per sample.
-__global__ void k_pack_fp(int rows, int cols, const uint8_t* __restrict__ im, unsigned* __restrict__ out) {
+__global__ void k_pack_fp(int rows, int cols, int pair0, const uint8_t* __restrict__ im_all, unsigned* __restrict__ out_all) {
   const int N = rows * cols;
+  const uint8_t* im = im_all + (size_t)(pair0 + blockIdx.y) * N;
+  unsigned* out = out_all + (size_t)(pair0 + blockIdx.y) * N;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     const int y = i / cols, x = i % cols;
     const int xp = min(x + 1, cols - 1), yp = min(y + 1, rows - 1);
@@ -1069,81 +1264,121 @@ __global__ void __launch_bounds__(256) k_jac_final_sorted(EvalParams p, int n_jo
 
 // ------------------------------------------------------------------------------------------------
 // Kernel 1 on its own, batched over jobs (north_star kernel (1); parity + HBM roofline probe; the evaluation path
-// fuses the same front end into both passes instead of storing its output). One thread per pixel in natural order:
-// depth (8 B, coalesced) -> back-projection and SE3 warp with the job's composed matrix -> packed 2x2 gather ->
-// {I_c, g_x, g_y, valid} as one float4 store (valid: 0 invalid, 1 cost only, 3 cost + Jacobian). The decisions
-// (bounds, truncation, saturation clamp) take the same exact fallbacks as pass 2.
-#ifndef NID_WS_ROWS
-#define NID_WS_ROWS 2  // image rows per thread (pixels in flight per lane)
-#endif
+// fuses the same front end into both passes instead of storing its output). A streaming kernel:
+//   in   the pair's depth plane, 2 B/px as the dataset's raw 16-bit values (metres = raw * factor, exact) or 8 B/px fp64
+//   out  {I_c, g_x, g_y, valid} as one float4 per pixel (16 B/px), valid: 0 invalid, 1 cost only, 3 cost + Jacobian
+// A CTA of 128 threads owns 512 consecutive pixels; thread t takes pixels t, t+128, t+256, t+384 of them, so every
+// warp load is 32 consecutive depths and every warp store 512 contiguous bytes (evict-first: written once, never read
+// here). fp64 is kept for what decides something -- back-projection, SE3 warp, projection, the (int) truncation and
+// the in-bounds tests, with the same exact fall-backs as pass 2 for (u, v) within 2^-24 of an integer, saturated
+// footprints and the first image row / column -- and the three bilinear samples, whose results are stored as
+// floats anyway, are evaluated in fp32 from the fp64 fractions (one packed 2x2 gather serves all three).
+// One Newton step on the reciprocal leaves (u, v) within 2^-36 of their exact values: far inside the 2^-24 guard band.
 #ifndef NID_WS_MINB
-#define NID_WS_MINB 6
+#define NID_WS_MINB 8
 #endif
-template <int NG>
+#define NID_WS_W 4
+template <int NG, bool U16>
 __global__ void __launch_bounds__(128, NID_WS_MINB)
 k_warp_sample_jobs(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt,
-                   const double* __restrict__ depth, float4* __restrict__ out) {
-  constexpr int W = NID_WS_ROWS;
+                   const double* __restrict__ depth64, const uint16_t* __restrict__ depth16,
+                   const double* __restrict__ factor_all, float4* __restrict__ out) {
+  constexpr int W = NID_WS_W;
   const int job = blockIdx.x + p.job0;
   const int pair = p.job_pair[job];
-  const double* g = gt.g[blockIdx.x];
-  const int bpr = (p.cols + 127) >> 7;  // CTAs per band of W image rows
-  const int band = blockIdx.y / bpr, col = (blockIdx.y - band * bpr) * 128 + threadIdx.x;
-  if (col >= p.cols) return;
-  const int row0 = band * W;
-  const double* dp = depth + (size_t)pair * p.N + col;
+  const double* g = gt.g[blockIdx.x];  // pass-1 form: rows 0 and 1 of M pre-multiplied by fx, fy
+  const int i0 = blockIdx.y * (128 * W) + threadIdx.x;
+  const size_t pbase = (size_t)pair * p.N;
+  // depths first: W independent loads in flight
   double z[W];
+  if (U16) {
+    const double factor = factor_all[pair];
+    unsigned raw[W];
 #pragma unroll
-  for (int j = 0; j < W; j++) z[j] = (row0 + j < p.rows) ? dp[(size_t)(row0 + j) * p.cols] : 0.0;
-  Px r[W];
-  uint4 t[W];
+    for (int j = 0; j < W; j++) raw[j] = (i0 + j * 128 < p.N) ? (unsigned)__ldcs(depth16 + pbase + i0 + j * 128) : 0u;
 #pragma unroll
-  for (int j = 0; j < W; j++) {
-    // depth outside [0.01, 100] is a NaN point in the reference (CudaPoints3d.cu:16-19): a padding slot here
-    const bool valid = z[j] >= 0.01 && z[j] <= 100.0;
-    const unsigned id = valid ? (((unsigned)(row0 + j) << 16) | (unsigned)col) : NID_PAD_ID;
-    front<false, false>(g, p.rows, p.cols, valid ? z[j] : 1.0, 0.0, 0.0, id, r[j]);
-    if (!valid) r[j].fix = false;
+    for (int j = 0; j < W; j++) z[j] = __dmul_rn(u2d(raw[j]), factor);  // NID_pose_estimation.cpp:105-106, one rounding
+  } else {
+#pragma unroll
+    for (int j = 0; j < W; j++) z[j] = (i0 + j * 128 < p.N) ? __ldcs(depth64 + pbase + i0 + j * 128) : 0.0;
   }
-#pragma unroll
-  for (int j = 0; j < W; j++) t[j] = gather_u32(p.tex2[pair], r[j].ix, r[j].iy);
+  int row = i0 / p.cols, col = i0 - row * p.cols;
+  int ix[W], iy[W];
+  float dxf[W], dyf[W];
+  unsigned flags[W];  // bit 0 cost-valid, bit 1 Jacobian-valid, bit 2 undecided by the fast path, bits 8.. column | row << 16 kept apart
+  unsigned ids[W];
 #pragma unroll
   for (int j = 0; j < W; j++) {
-    if (row0 + j >= p.rows) continue;
-    const double two52 = 4503599627370496.0;
-    const double i00 = tapd(t[j].w & 0xffu), i01 = tapd(t[j].z & 0xffu), i10 = tapd(t[j].x & 0xffu), i11 = tapd(t[j].y & 0xffu);
-    const double x00 = tapd((t[j].w >> 8) & 0x1ffu), x01 = tapd((t[j].z >> 8) & 0x1ffu);
-    const double x10 = tapd((t[j].x >> 8) & 0x1ffu), x11 = tapd((t[j].y >> 8) & 0x1ffu);
-    const double y00 = tapd(t[j].w >> 17), y01 = tapd(t[j].z >> 17), y10 = tapd(t[j].x >> 17), y11 = tapd(t[j].y >> 17);
-    double ic = bilinear_fast(r[j].dx, r[j].dy, i00 - two52, i01 - i00, i10 - two52, i11 - i10);
-    double gx2 = bilinear_fast(r[j].dx, r[j].dy, x00 - (two52 + 256.0), x01 - x00, x10 - (two52 + 256.0), x11 - x10);
-    double gy2 = bilinear_fast(r[j].dx, r[j].dy, y00 - (two52 + 256.0), y01 - y00, y10 - (two52 + 256.0), y11 - y10);
-    bool vc = r[j].ok, vj = r[j].jac;
+    // depth outside [0.01, 100] is a NaN point in the reference (CudaPoints3d.cu:16-19)
+    const bool valid = z[j] >= 0.01 && z[j] <= 100.0 && (i0 + j * 128 < p.N);
+    ids[j] = ((unsigned)row << 16) | (unsigned)col;
+    const double cxn = fma(u2d((unsigned)col), g[12], g[13]);
+    const double cyn = fma(u2d((unsigned)row), g[14], g[15]);
+    const double d0 = fma(g[0], cxn, fma(g[3], cyn, g[6]));
+    const double d1 = fma(g[1], cxn, fma(g[4], cyn, g[7]));
+    const double d2 = fma(g[2], cxn, fma(g[5], cyn, g[8]));
+    const double zz = valid ? z[j] : 1.0;
+    const double x1 = fma(zz, d0, g[9]), y1 = fma(zz, d1, g[10]), z1 = fma(zz, d2, g[11]);
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z1));
+    y = fma(y, fma(-z1, y, 1.0), y);
+    const double u = fma(x1, y, g[18]), v = fma(y1, y, g[19]);
+    const int jx = __double2int_rz(u), jy = __double2int_rz(v);
+    const double dx = u - u2d((unsigned)jx), dy = v - u2d((unsigned)jy);
+    const bool inr = valid && (unsigned)jx <= (unsigned)(p.cols - 3) && (unsigned)jy <= (unsigned)(p.rows - 3);
+    const bool safe = frac_is_safe(dx) && frac_is_safe(dy);
+    const bool ok = inr && safe && jx <= p.cols - 4 && jy <= p.rows - 4;
+    const bool jac = ok && jx <= p.cols - 5;
+    flags[j] = (ok ? 1u : 0u) | (jac ? 2u : 0u) | ((inr && !safe) ? 4u : 0u);
+    ix[j] = ok ? jx : 0; iy[j] = ok ? jy : 0;
+    dxf[j] = (float)dx; dyf[j] = (float)dy;
+    col += 128;
+    if (col >= p.cols) { col -= p.cols; row++; if (col >= p.cols) { row += col / p.cols; col %= p.cols; } }
+  }
+  uint4 t[W];
+  const cudaTextureObject_t tex = p.tex2[pair];
+#pragma unroll
+  for (int j = 0; j < W; j++) t[j] = gather_u32(tex, ix[j], iy[j]);
+  float4* o = out + (size_t)job * p.N + i0;
+#pragma unroll
+  for (int j = 0; j < W; j++) {
+    if (i0 + j * 128 >= p.N) continue;
+    // texel = I | (Gx+256) << 8 | (Gy+256) << 17; footprint .w (ix,iy) .z (ix+1,iy) .x (ix,iy+1) .y (ix+1,iy+1)
+    const int i00 = t[j].w & 0xffu, i01 = t[j].z & 0xffu, i10 = t[j].x & 0xffu, i11 = t[j].y & 0xffu;
+    const int x00 = (t[j].w >> 8) & 0x1ffu, x01 = (t[j].z >> 8) & 0x1ffu, x10 = (t[j].x >> 8) & 0x1ffu, x11 = (t[j].y >> 8) & 0x1ffu;
+    const int y00 = t[j].w >> 17, y01 = t[j].z >> 17, y10 = t[j].x >> 17, y11 = t[j].y >> 17;
+    const float fx_ = dxf[j], fy_ = dyf[j];
+    // p00 + dx d0 + dy ((p10 + dx d1) - (p00 + dx d0)), small exact integers as floats
+    float a = fmaf(fx_, (float)(i01 - i00), (float)i00), b = fmaf(fx_, (float)(i11 - i10), (float)i10);
+    float ic = fmaf(fy_, b - a, a);
+    a = fmaf(fx_, (float)(x01 - x00), (float)(x00 - 256)); b = fmaf(fx_, (float)(x11 - x10), (float)(x10 - 256));
+    float gx2 = fmaf(fy_, b - a, a);
+    a = fmaf(fx_, (float)(y01 - y00), (float)(y00 - 256)); b = fmaf(fx_, (float)(y11 - y10), (float)(y10 - 256));
+    float gy2 = fmaf(fy_, b - a, a);
+    bool vc = flags[j] & 1u, vj = flags[j] & 2u;
     const bool sat = (t[j].w & t[j].z & t[j].x & t[j].y & 0xffu) == 0xffu;
-    if (r[j].fix || (r[j].ok && (sat || r[j].ix < 1 || r[j].iy < 1))) {
+    if ((flags[j] & 4u) || (vc && (sat || ix[j] < 1 || iy[j] < 1))) {
       // the reference's literal sequence: cost validity and intensity from (u, v), Jacobian validity and gradient
       // from the second projection (types_six_dof_expmap.cpp:562-575, :407-435)
       const double* T1 = p.poses + 16 * job;
       const double* T0 = p.Twc0 + 16 * pair;
       const double* camg = p.cam + 4 * pair;
-      const unsigned id = ((unsigned)(row0 + j) << 16) | (unsigned)col;
       double e[5];
-      exact_uv<false>(T1, T0, camg, z[j], 0.0, 0.0, id, e);
+      exact_uv<false>(T1, T0, camg, z[j], 0.0, 0.0, ids[j], e);
       vc = inb_cost(e[3], e[4], p.rows, p.cols);
       vj = false;
-      ic = 0.0; gx2 = 0.0; gy2 = 0.0;
+      ic = 0.f; gx2 = 0.f; gy2 = 0.f;
       if (vc) {
-        const uint8_t* im1 = p.im1 + (size_t)pair * p.N;
-        ic = clamp_intensity(interp_u8(im1, p.cols, e[3], e[4]));
+        const uint8_t* im1 = p.im1 + pbase;
+        ic = (float)clamp_intensity(interp_u8(im1, p.cols, e[3], e[4]));
         double o6[6];
-        vj = jac_pixel_literal<false>(T1, T0, camg, p.rows, p.cols, im1, z[j], 0.0, 0.0, id, o6);
-        if (vj) { gx2 = o6[4]; gy2 = o6[5]; }
+        vj = jac_pixel_literal<false>(T1, T0, camg, p.rows, p.cols, im1, z[j], 0.0, 0.0, ids[j], o6);
+        if (vj) { gx2 = (float)o6[4]; gy2 = (float)o6[5]; }
       }
     }
-    if (!vc) ic = 0.0;
-    if (!vj) { gx2 = 0.0; gy2 = 0.0; }
-    out[(size_t)job * p.N + (size_t)(row0 + j) * p.cols + col] =
-        make_float4((float)ic, (float)(0.5 * gx2), (float)(0.5 * gy2), (float)((vc ? 1 : 0) + (vj ? 2 : 0)));
+    if (!vc) ic = 0.f;
+    if (!vj) { gx2 = 0.f; gy2 = 0.f; }
+    __stcs(o + j * 128, make_float4(ic, 0.5f * gx2, 0.5f * gy2, (float)((vc ? 1 : 0) + (vj ? 2 : 0))));
   }
 }
 
@@ -1157,48 +1392,48 @@ int launch_count_classes(nid_ctx* c, int pair) {
   return NID_OK;
 }
 
-int launch_scatter(nid_ctx* c, int pair) {
+// pairs [pair0, pair0 + n), n <= c->setup_batch: tables on the device, then the regrouping scatter
+int launch_layout_and_scatter(nid_ctx* c, int pair0, int n) {
   EvalParams p = make_params(c, 1);
-  const size_t sb = (size_t)pair * c->sell_cap;
-  cudaError_t e = cudaMemsetAsync(c->sid + sb, 0xFF, sizeof(unsigned) * c->sell_cap, c->stream);
+  const int L = c->task_px;
+  const dim3 gcell(c->ncell, n);
+  k_layout_totals<<<gcell, NID_LAYOUT_THREADS, 0, c->stream>>>(pair0, c->ncell, L, c->cnt, c->lay_tot);
+  NID_LAUNCH_CHECK(c, "k_layout_totals");
+  k_layout_scan<<<n, 256, 0, c->stream>>>(p, pair0, c->lay_tot, c->lay_base, c->cell_task_start, c->cell_slice_start, c->ntasks,
+                                         c->nslices, c->sl_off, c->d_flag + 1);
+  NID_LAUNCH_CHECK(c, "k_layout_scan");
+  k_layout_write<<<gcell, NID_LAYOUT_THREADS, 0, c->stream>>>(p, pair0, L, c->cnt, c->lay_base, c->tasks, c->task_pos, c->sl_task,
+                                                             c->sl_off, c->sl_cell, c->cls_task_start);
+  NID_LAUNCH_CHECK(c, "k_layout_write");
+  const size_t sb = (size_t)pair0 * c->sell_cap;
+  cudaError_t e = cudaMemsetAsync(c->sid + sb, 0xFF, sizeof(unsigned) * c->sell_cap * n, c->stream);
   if (e != cudaSuccess) return check_cuda(e, "memset sid");
-  e = cudaMemsetAsync(c->sd0 + sb, 0, sizeof(double) * c->sell_cap, c->stream);
+  e = cudaMemsetAsync(c->sd0 + sb, 0, sizeof(double) * c->sell_cap * n, c->stream);
   if (e != cudaSuccess) return check_cuda(e, "memset sd0");
-  const int* tp = c->task_pos + (size_t)pair * c->max_tasks;
-  const double* depth = c->depth + (size_t)pair * c->N;
   const int nchunks = (c->rb * c->cb + 255) / 256;
-  if (!c->chunk_cnt) {
-    e = cudaMalloc((void**)&c->chunk_cnt, sizeof(int) * (size_t)c->ncell * nchunks * NID_NCLS);
-    if (e != cudaSuccess) return check_cuda(e, "cudaMalloc chunk_cnt");
-  }
-  const dim3 grid(nchunks, c->ncell);
-  k_chunk_count<<<grid, 256, 0, c->stream>>>(p, pair, c->chunk_cnt);
+  const dim3 grid(nchunks, c->ncell, n);
+  k_chunk_count<<<grid, 256, 0, c->stream>>>(p, pair0, c->chunk_cnt);
   NID_LAUNCH_CHECK(c, "k_chunk_count");
-  k_chunk_scan<<<(c->ncell * NID_NCLS + 255) / 256, 256, 0, c->stream>>>(c->ncell, nchunks, c->chunk_cnt);
+  k_chunk_scan<<<dim3((c->ncell * NID_NCLS + 255) / 256, n), 256, 0, c->stream>>>(c->ncell, nchunks, c->chunk_cnt);
   NID_LAUNCH_CHECK(c, "k_chunk_scan");
   if (c->sell_points) {
-    cudaMemsetAsync(c->sd1 + sb, 0, sizeof(double) * c->sell_cap, c->stream);
-    cudaMemsetAsync(c->sd2 + sb, 0, sizeof(double) * c->sell_cap, c->stream);
-    k_scatter_sell<true><<<grid, 256, 0, c->stream>>>(p, pair, c->task_px, depth, tp, c->chunk_cnt, c->sd0, c->sd1, c->sd2, c->sid);
+    cudaMemsetAsync(c->sd1 + sb, 0, sizeof(double) * c->sell_cap * n, c->stream);
+    cudaMemsetAsync(c->sd2 + sb, 0, sizeof(double) * c->sell_cap * n, c->stream);
+    k_scatter_sell<true><<<grid, 256, 0, c->stream>>>(p, pair0, L, c->depth, c->task_pos, c->chunk_cnt, c->sd0, c->sd1, c->sd2, c->sid);
   } else {
-    k_scatter_sell<false><<<grid, 256, 0, c->stream>>>(p, pair, c->task_px, depth, tp, c->chunk_cnt, c->sd0, nullptr, nullptr, c->sid);
+    k_scatter_sell<false><<<grid, 256, 0, c->stream>>>(p, pair0, L, c->depth, c->task_pos, c->chunk_cnt, c->sd0, nullptr, nullptr, c->sid);
   }
   NID_LAUNCH_CHECK(c, "k_scatter_sell");
   return NID_OK;
 }
 
-int launch_pack_fp(nid_ctx* c, int pair) {
+// footprint-packed planes and packed gather texels of the targets of pairs [pair0, pair0 + n), n <= c->setup_batch
+int launch_pack(nid_ctx* c, int pair0, int n) {
   int g = (c->N + 255) / 256;
-  if (g > c->sm_count * 8) g = c->sm_count * 8;
-  k_pack_fp<<<g, 256, 0, c->stream>>>(c->rows, c->cols, c->im1 + (size_t)pair * c->N, c->fp1 + (size_t)pair * c->N);
+  g = std::min(g, std::max(8, c->sm_count * 8 / n));
+  k_pack_fp<<<dim3(g, n), 256, 0, c->stream>>>(c->rows, c->cols, pair0, c->im1, c->fp1);
   NID_LAUNCH_CHECK(c, "k_pack_fp");
-  return NID_OK;
-}
-
-int launch_pack_tex(nid_ctx* c, int pair, unsigned* d_out) {
-  int g = (c->N + 255) / 256;
-  if (g > c->sm_count * 8) g = c->sm_count * 8;
-  k_pack_tex<<<g, 256, 0, c->stream>>>(c->rows, c->cols, c->im1 + (size_t)pair * c->N, d_out);
+  k_pack_tex<<<dim3(g, n), 256, 0, c->stream>>>(c->rows, c->cols, pair0, c->im1, c->d_pack);
   NID_LAUNCH_CHECK(c, "k_pack_tex");
   return NID_OK;
 }
@@ -1342,16 +1577,18 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
   return NID_OK;
 }
 
-int launch_warp_sample_jobs(nid_ctx* c, int n_jobs, float4* d_out) {
+// all jobs of a launch must take their depth from the same kind of plane (raw 16-bit or fp64): u16 says which
+int launch_warp_sample_jobs(nid_ctx* c, int n_jobs, float4* d_out, bool u16) {
   EvalParams p = make_params(c, n_jobs);
-  const int bpr = (c->cols + 127) / 128;
+  const int chunks = (c->N + 128 * NID_WS_W - 1) / (128 * NID_WS_W);
   for (int s0 = 0; s0 < n_jobs; s0 += NID_GEO_LARGE) {
     const int n = std::min(NID_GEO_LARGE, n_jobs - s0);
     GeoTable<NID_GEO_LARGE> gt;
-    fill_geo(c, gt, s0, n, false);
+    fill_geo(c, gt, s0, n, true);
     EvalParams q = p;
     q.job0 = s0;
-    k_warp_sample_jobs<NID_GEO_LARGE><<<dim3(n, ((c->rows + NID_WS_ROWS - 1) / NID_WS_ROWS) * bpr), 128, 0, c->stream>>>(q, gt, c->depth, d_out);
+    if (u16) k_warp_sample_jobs<NID_GEO_LARGE, true><<<dim3(n, chunks), 128, 0, c->stream>>>(q, gt, nullptr, c->depth16, c->depth_factor, d_out);
+    else k_warp_sample_jobs<NID_GEO_LARGE, false><<<dim3(n, chunks), 128, 0, c->stream>>>(q, gt, c->depth, nullptr, nullptr, d_out);
     NID_LAUNCH_CHECK(c, "k_warp_sample_jobs");
   }
   return NID_OK;
@@ -1359,7 +1596,7 @@ int launch_warp_sample_jobs(nid_ctx* c, int n_jobs, float4* d_out) {
 
 int sorted_init(nid_ctx* c) {
   cudaError_t e;
-  if (c->bins > NID_SORTED_MAX_BINS || c->bins < 8) return NID_OK;  // natural-order kernels only
+  if (c->bins > NID_SORTED_MAX_BINS || c->bins < NID_SORTED_MIN_BINS) return NID_OK;  // natural-order kernels only
 #define NID_SMEM_ATTR(k, bytes)                                                                     \
   e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));            \
   if (e != cudaSuccess) return check_cuda(e, "smem attr " #k);

@@ -10,7 +10,11 @@
 // calculate_der == false) and forward to the C-ABI. State that the reference recomputed or re-uploaded on
 // every call (points, reference spline weights, images) lives in a process-global context keyed by the
 // caller's `points3d` pointer, which the reference keeps alive for the whole solve
-// (NID_pose_estimation.cpp:240-276). Call nid_shim_reset() when the buffers behind those pointers change.
+// (NID_pose_estimation.cpp:240-276). The images are compared with the copy that was last uploaded on every
+// call (a memcmp of 2.4 MB, far below one evaluation), so refilling im0 / im1 in place with a new frame is seen:
+// a new im1 is uploaded, a new im0 additionally drops the cached prepare. The world points are only re-read
+// after Calculate3Dpoint wrote them through this library; call nid_shim_reset() if they are changed otherwise.
+// On any failure the outputs are set to NaN (the reference's "inactive cell" value), never left as stale zeros.
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -26,10 +30,24 @@ namespace {
 struct ShimCtx {
   nid_ctx* ctx = nullptr;
   int rows = 0, cols = 0, cell = 0, bins = 0;
-  const double* im0 = nullptr;
-  const double* im1 = nullptr;
+  std::vector<double> im0, im1;  // what was last uploaded (content, not pointer identity)
   bool prepared = false;
 };
+
+// Calculate3Dpoint needs no pair geometry: one small context per image size, kept between calls
+struct PointsCtx {
+  nid_ctx* ctx = nullptr;
+  int rows = 0, cols = 0;
+  std::vector<uint8_t> blank;
+};
+PointsCtx g_points;
+
+bool same_image(const std::vector<double>& have, const double* im, size_t n) {
+  return have.size() == n && memcmp(have.data(), im, sizeof(double) * n) == 0;
+}
+void fill_nan(double* p, int n) {
+  if (p) for (int i = 0; i < n; i++) p[i] = NAN;
+}
 
 std::mutex g_mu;
 std::map<const double*, ShimCtx> g_ctx;  // key: points3d
@@ -61,18 +79,24 @@ extern "C" void nid_shim_reset(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& kv : g_ctx) nid_destroy(kv.second.ctx);
   g_ctx.clear();
+  if (g_points.ctx) nid_destroy(g_points.ctx);
+  g_points = PointsCtx();
 }
 
 // CudaPoints3d.cu:35-74. points_3d may be managed, device or host memory.
 void Calculate3Dpoint(double* depth, double* pose_c2w, double* points_3d, double* camera_intrincis, int rows, int cols) {
   std::lock_guard<std::mutex> lk(g_mu);
-  nid_ctx* c = nullptr;
-  if (nid_create(&c, 0, rows, cols, 1, 8, 3, 1, 1) != NID_OK) { warn("Calculate3Dpoint/nid_create"); return; }
-  std::vector<uint8_t> blank((size_t)rows * cols, 0);
-  if (nid_set_pair(c, 0, depth, blank.data(), blank.data(), pose_c2w, camera_intrincis) != NID_OK ||
+  if (!g_points.ctx || g_points.rows != rows || g_points.cols != cols) {
+    if (g_points.ctx) nid_destroy(g_points.ctx);
+    g_points = PointsCtx();
+    if (nid_create(&g_points.ctx, 0, rows, cols, 1, 8, 3, 1, 1) != NID_OK) { warn("Calculate3Dpoint/nid_create"); g_points.ctx = nullptr; return; }
+    g_points.rows = rows; g_points.cols = cols;
+    g_points.blank.assign((size_t)rows * cols, 0);
+  }
+  nid_ctx* c = g_points.ctx;
+  if (nid_set_pair(c, 0, depth, g_points.blank.data(), g_points.blank.data(), pose_c2w, camera_intrincis) != NID_OK ||
       nid_get_points3d(c, 0, points_3d) != NID_OK)
     warn("Calculate3Dpoint");
-  nid_destroy(c);
   // a new set of points invalidates whatever was cached for this buffer
   auto it = g_ctx.find(points_3d);
   if (it != g_ctx.end()) { nid_destroy(it->second.ctx); g_ctx.erase(it); }
@@ -82,15 +106,17 @@ void Calculate3Dpoint(double* depth, double* pose_c2w, double* points_3d, double
 void CudaComputeHref(double* im0, double* points3d, double* pose, double* camera_intrincis, int bin_num, int bs_degree,
                      int cell_num, int rows, int cols, double* bs_value, int* bs_index, int* bs_counter, double* Href) {
   std::lock_guard<std::mutex> lk(g_mu);
-  ShimCtx* s = get_ctx(points3d, rows, cols, cell_num, bin_num, bs_degree, camera_intrincis);
-  if (!s) return;
-  if (nid_set_pair_points(s->ctx, 0, nullptr, im0, nullptr, nullptr) != NID_OK) { warn("CudaComputeHref/im0"); return; }
-  s->im0 = im0;
   const int nc = cell_num * cell_num;
+  const size_t N = (size_t)rows * cols;
+  ShimCtx* s = get_ctx(points3d, rows, cols, cell_num, bin_num, bs_degree, camera_intrincis);
+  if (!s) { fill_nan(Href, nc); return; }
+  s->prepared = false;
+  s->im0.clear();
+  if (nid_set_pair_points(s->ctx, 0, nullptr, im0, nullptr, nullptr) != NID_OK) { warn("CudaComputeHref/im0"); fill_nan(Href, nc); return; }
   std::vector<double> href(nc);
-  if (nid_prepare(s->ctx, 0, pose, bs_counter, href.data()) != NID_OK) { warn("CudaComputeHref/nid_prepare"); return; }
+  if (nid_prepare(s->ctx, 0, pose, bs_counter, href.data()) != NID_OK) { warn("CudaComputeHref/nid_prepare"); fill_nan(Href, nc); return; }
   s->prepared = true;
-  if (nid_get_ref_weights(s->ctx, 0, bs_value, bs_index) != NID_OK) { warn("CudaComputeHref/ref_weights"); return; }
+  if (nid_get_ref_weights(s->ctx, 0, bs_value, bs_index) != NID_OK) { warn("CudaComputeHref/ref_weights"); fill_nan(Href, nc); return; }
   // `Href[i] -= p log2 p` into the caller-zeroed buffer (CudaComputeHref.cu:218); NaN when n_c < 300 (:206-209)
   for (int i = 0; i < nc; i++) Href[i] = isnan(href[i]) ? NAN : Href[i] + href[i];
   // side effect of the reference kernel: im0 is clamped in place where it was used (CudaComputeHref.cu:102-105)
@@ -102,6 +128,7 @@ void CudaComputeHref(double* im0, double* points3d, double* pose, double* camera
         if (im0[i] < 0) im0[i] = 0;
       }
   }
+  s->im0.assign(im0, im0 + N);  // the caller's buffer as it is now (after the in-place clamp)
 }
 
 namespace g2o {
@@ -113,28 +140,37 @@ void CudaComputeH(bool calculate_der, double* im0, double* im1, double* points3d
                   double* Hjoint, double* der) {
   (void)pro_target; (void)pro_joint; (void)bs_index_ref;
   std::lock_guard<std::mutex> lk(g_mu);
+  const int nc = cell_num * cell_num;
+  const size_t N = (size_t)rows * cols;
+  auto fail = [&](const char* where) {
+    warn(where);
+    fill_nan(Htarget, nc); fill_nan(Hjoint, nc);
+    if (calculate_der) fill_nan(der, 6 * nc);
+  };
   ShimCtx* s = get_ctx(points3d, rows, cols, cell_num, bin_num, bs_degree, camera_intrincis);
-  if (!s) return;
-  if (s->im0 != im0) {
+  if (!s) { fail("CudaComputeH/context"); return; }
+  if (!same_image(s->im0, im0, N)) {
     // the clamped value 254.999 written back by CudaComputeHref maps to the same spline weights as 255
-    std::vector<double> tmp(im0, im0 + (size_t)rows * cols);
+    std::vector<double> tmp(im0, im0 + N);
     for (auto& v : tmp) if (v == 254.999) v = 255.0;
-    if (nid_set_pair_points(s->ctx, 0, nullptr, tmp.data(), nullptr, nullptr) != NID_OK) { warn("CudaComputeH/im0"); return; }
-    s->im0 = im0;
+    if (nid_set_pair_points(s->ctx, 0, nullptr, tmp.data(), nullptr, nullptr) != NID_OK) { fail("CudaComputeH/im0"); return; }
+    s->im0.assign(im0, im0 + N);
+    s->prepared = false;  // a new reference image: whatever was prepared belongs to the old one
   }
-  if (s->im1 != im1) {
-    if (nid_set_pair_points(s->ctx, 0, nullptr, nullptr, im1, nullptr) != NID_OK) { warn("CudaComputeH/im1"); return; }
-    s->im1 = im1;
+  if (!same_image(s->im1, im1, N)) {
+    if (nid_set_pair_points(s->ctx, 0, nullptr, nullptr, im1, nullptr) != NID_OK) { fail("CudaComputeH/im1"); return; }
+    s->im1.assign(im1, im1 + N);
+    // (the prepare data -- in-bounds set, n_c, H_ref -- depend on the reference image, the points and the initial
+    // pose only, CudaComputeHref.cu:33-135: a new target keeps them)
   }
   if (!s->prepared) {
-    // CudaComputeHref was not routed through this library: adopt the caller's prepare
-    if (nid_import_prepare(s->ctx, 0, bs_ref, bs_counter, Href) != NID_OK) { warn("CudaComputeH/import_prepare"); return; }
+    // CudaComputeHref was not routed through this library (or im0 changed since): adopt the caller's prepare
+    if (nid_import_prepare(s->ctx, 0, bs_ref, bs_counter, Href) != NID_OK) { fail("CudaComputeH/import_prepare"); return; }
     s->prepared = true;
   }
-  const int nc = cell_num * cell_num;
   std::vector<double> ht(nc), hj(nc), dj(calculate_der ? 6 * nc : 0);
   if (nid_eval(s->ctx, 0, pose, calculate_der ? 1 : 0, ht.data(), hj.data(), calculate_der ? dj.data() : nullptr) != NID_OK) {
-    warn("CudaComputeH/nid_eval");
+    fail("CudaComputeH/nid_eval");
     return;
   }
   for (int i = 0; i < nc; i++) {

@@ -376,10 +376,15 @@ struct orc_problem {
 
 namespace {
 
-// types_six_dof_expmap.h:310-328 (uchar image, (int) truncation)
+// types_six_dof_expmap.h:310-328 (uchar image, (int) truncation). x == -1.0 or y == -1.0 exactly (the gradient
+// taps of a point with u == 0 or v == 0, which the Jacobian bounds test :433 admits) index column / row -1
+// upstream: an out-of-bounds cv::Mat access, undefined. Defined here as the continuous extension of the
+// (-1, 0) interval: index clamped to 0, fraction -1.
 inline double interp(const orc_problem& P, double x, double y) {
   int ix = (int)x;
   int iy = (int)y;
+  if (ix < 0) ix = 0;
+  if (iy < 0) iy = 0;
   double dx = x - ix;
   double dy = y - iy;
   double dxdy = dx * dy;

@@ -1,5 +1,6 @@
 """Runs the reference's own CUDA implementation (oracle/_ref/libnid_ref_gpu.so, compiled unmodified from
-CudaPoints3d.cu and g2o/g2o/core/computeH.cu of the upstream tree by oracle/Makefile). TEST
+CudaPoints3d.cu and g2o/g2o/core/computeH.cu of the upstream tree by oracle/Makefile, plus CudaComputeHref.cu with
+the two-line cudaMemset fix of SURVEY appendix B-2 applied at build time). TEST
 INFRASTRUCTURE ONLY — needs a GPU; used to pin the CPU oracle and to time the "old GPU path".
 
 The reference kernels have no `i < rows*cols` guard: they touch
@@ -36,6 +37,8 @@ def lib():
         L.ref_managed_free.argtypes = [C.c_void_p]
         L.ref_Calculate3Dpoint.argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.c_int]
         L.ref_CudaComputeH.argtypes = [C.c_int, _dp, _dp, _dp, _ip, _dp, _ip, _dp, _dp] + [C.c_int] * 5 + [_dp] * 4
+        if hasattr(L, "ref_CudaComputeHref"):
+            L.ref_CudaComputeHref.argtypes = [_dp, _dp, _dp, _dp] + [C.c_int] * 5 + [_dp, _ip, _ip, _dp]
         _L = L
     return _L
 
@@ -83,6 +86,21 @@ class RefGpu:
 
     def points3d(self):
         return np.array(self.pts.a)
+
+    def compute_href(self, pose16):
+        """The reference's CudaComputeHref (CudaComputeHref.cu:139-223) at the initial pose: returns
+        (bs_counter, bs_value[4N], bs_index[N], Href) as the reference leaves them (NaN weights / index 0 for pixels
+        without a sample, NaN Href for cells under 300 points); im0 is clamped in place like upstream does."""
+        c2 = self.cell * self.cell
+        bs_value = np.zeros(4 * self.n)
+        bs_index = np.zeros(self.n, dtype=np.int32)
+        bs_counter = np.zeros(c2, dtype=np.int32)
+        Href = np.zeros(c2)  # `Href[i] -= ...` into the caller's zeros (NID_pose_estimation.cpp:238)
+        pose = np.ascontiguousarray(pose16, dtype=np.float64)
+        lib().ref_CudaComputeHref(self.im0.p(), self.pts.p(), _d(pose), _d(self.intr), self.bins, 3, self.cell, self.rows,
+                                  self.cols, _d(bs_value), bs_index.ctypes.data_as(_ip), bs_counter.ctypes.data_as(_ip),
+                                  _d(Href))
+        return bs_counter, bs_value, bs_index, Href
 
     def set_prepare(self, bs_counter, bs_value, bs_index, Href):
         self.bs_counter = np.ascontiguousarray(bs_counter, dtype=np.int32)

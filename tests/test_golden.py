@@ -1,6 +1,6 @@
 """The oracle against outputs of the REFERENCE'S OWN CUDA implementation (tests/golden/ref_gpu_*.npz,
 produced on a B200 by oracle/gen_ref_golden.py from the unmodified CudaPoints3d.cu and
-g2o/g2o/core/computeH.cu). This is the pin the oracle stands on: upstream has no tests or vectors.
+g2o/g2o/core/computeH.cu, and from CudaComputeHref.cu with its cudaMemset bug fixed). This is the pin the oracle stands on: upstream has no tests or vectors.
 
 The reference CUDA code differs from its CPU edge in two documented ways (SURVEY B-6/B-7): it warps with the
 4x4 matrix and it uses `u+3<=cols` in the Jacobian bounds test; the oracle is switched to those two
@@ -15,7 +15,7 @@ GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_g
 
 
 def test_golden_vectors_present():
-    assert len(GOLD) >= 5
+    assert len(GOLD) >= 7  # one per knot table of the reference (6, 8, 10, 12, 14 bins) and more cell counts
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(g)[8:-4] for g in GOLD])
@@ -40,6 +40,25 @@ def test_oracle_matches_reference_cuda_outputs(orc, synth, path):
     nc, href = P.prepare(pose0)
     assert np.array_equal(nc, g["n_c"])
     act = nc >= 300
+    # a2: the reference's own CudaComputeHref (CudaComputeHref.cu:33-223, cudaMemset fixed) at the initial pose:
+    # per-cell counts, H_ref, and per pixel the span index and the four reference spline weights
+    assert np.array_equal(nc, g["ref_n_c"])
+    assert np.array_equal(np.isnan(g["ref_href"]), ~act)
+    np.testing.assert_allclose(href[act], g["ref_href"][act], rtol=1e-12)
+    bv, bi = P.ref_weights()
+    bv = bv.reshape(-1, 4)
+    inb = P.pixels(pose0)[:, 5] == 1  # in bounds at the initial pose
+    inb &= np.add.outer(np.arange(rows) < (rows // cell) * cell, np.zeros(cols, dtype=bool)).reshape(-1)
+    inb &= np.add.outer(np.zeros(rows, dtype=bool), np.arange(cols) < (cols // cell) * cell).reshape(-1)
+    assert int(inb.sum()) == int(g["ref_inb_count"]) == int(nc.sum())
+    sub = np.arange(0, rows * cols, 97)
+    rb = g["ref_bs_value_sub"]
+    assert np.array_equal(~np.isnan(rb[:, 0]), inb[sub])          # NaN weights exactly where there is no sample
+    m = inb[sub]
+    np.testing.assert_allclose(bv[sub][m], rb[m], rtol=1e-13, atol=1e-16)
+    assert np.array_equal(bi[sub][m], g["ref_bs_index_sub"][m])
+    assert int(bi[inb].astype(np.int64).sum()) == int(g["ref_bs_index_sum"])
+    np.testing.assert_allclose(bv[inb].sum(axis=0), g["ref_bs_value_colsum"], rtol=1e-11)
     for k, xi in enumerate(g["xis"]):
         pose = orc.se3_mul(orc.se3_exp(xi), pose0)
         np.testing.assert_array_equal(orc.se3_to_mat16(pose), g["poses"][k])

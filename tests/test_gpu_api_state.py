@@ -1,0 +1,174 @@
+"""State and memory-safety properties of the C-ABI that the round-1 review asked for: the asynchronous staged API
+never reuses a pinned staging slot while a copy from it is pending, staged jobs survive a nid_prepare of another
+pair, nid_eval_staged refuses more jobs than were staged, forced strip counts cannot overflow the partial buffers,
+and the gradient taps of points with u == 0 / v == 0 exactly never read outside the image."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NATURAL, SORTED = 1, 2
+
+
+def _two_pairs(nid, orc, make_pair, path, max_jobs=8, rows=120, cols=160):
+    pa, pb = make_pair(1000, rows, cols), make_pair(1001, rows, cols)
+    ctx = nid.Context(rows, cols, 4, 16, n_pairs=2, max_jobs=max_jobs)
+    ctx.set_option("path", path)
+    pose0 = []
+    for i, p in enumerate((pa, pb)):
+        ctx.set_pair(i, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+        pose0.append(orc.reference_perturbation(p.T_wc1))
+        ctx.prepare(i, orc.se3_to_mat16(pose0[i]))
+    return ctx, pose0
+
+
+@pytest.mark.parametrize("path", [NATURAL, SORTED])
+def test_pipelined_stage_eval_without_sync(nid, orc, make_pair, path):
+    """stage A, eval, stage B (no synchronisation in between): the evaluation of A must see A's poses on the device
+    (the natural-order kernels read them for every pixel, the sorted ones on their exact paths)."""
+    ctx, pose0 = _two_pairs(nid, orc, make_pair, path)
+    rng = np.random.default_rng(11)
+    jp = np.array([0, 1, 1, 0, 0, 1, 0, 1], dtype=np.int32)
+
+    def batch():
+        return np.stack([orc.se3_to_mat16(orc.se3_mul(orc.se3_exp(rng.normal(size=6) * 3e-3), pose0[j])) for j in jp])
+    for _ in range(12):
+        A, B = batch(), batch()
+        ref = ctx.eval_jobs(A, jp, True)
+        ctx.stage_jobs(A, jp)
+        ctx.eval_staged(len(jp), True)
+        ctx.stage_jobs(B, jp)          # must not disturb the evaluation of A that is still in flight
+        got = ctx.fetch_results(len(jp), True)
+        for x, y in zip(got, ref):
+            if path == SORTED:
+                assert np.array_equal(x, y)
+            else:
+                np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-12)
+    # many steps in flight (more than the staging ring holds): the last one is still right
+    steps = [batch() for _ in range(9)]
+    for S in steps:
+        ctx.stage_jobs(S, jp)
+        ctx.eval_staged(len(jp), True)
+    got = ctx.fetch_results(len(jp), True)
+    ref = ctx.eval_jobs(steps[-1], jp, True)
+    for x, y in zip(got, ref):
+        np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-12)
+
+
+def test_staged_jobs_survive_prepare_and_kernel1_calls(nid, orc, make_pair):
+    ctx, pose0 = _two_pairs(nid, orc, make_pair, SORTED)
+    M0, M1 = orc.se3_to_mat16(pose0[0]), orc.se3_to_mat16(pose0[1])
+    ref = ctx.eval_jobs(np.stack([M0]), np.array([0], dtype=np.int32), True)
+    ctx.stage_jobs(np.stack([M0]), np.array([0], dtype=np.int32))
+    ctx.prepare(1, M1)                # another pair, another pose: takes its own pose scratch
+    ctx.warp_sample_f64(1, M1)
+    ctx.eval_staged(1, True)
+    got = ctx.fetch_results(1, True)
+    for x, y in zip(got, ref):
+        assert np.array_equal(x, y)
+    with pytest.raises(nid.NidError, match="staged"):
+        ctx.eval_staged(2, True)      # only one job was staged
+    ctx.hard_eval_jobs(np.stack([M0, M1]), np.array([0, 1], dtype=np.int32))
+    with pytest.raises(nid.NidError, match="staged"):
+        ctx.eval_staged(1, True)      # hard-binned jobs are not evaluation jobs
+
+
+def test_forced_strips_cannot_overflow_partials(nid, orc, make_pair):
+    p = make_pair(1000, 120, 160)
+    n_jobs = 96
+    ctx = nid.Context(p.rows, p.cols, 2, 16, n_pairs=1, max_jobs=n_jobs)
+    ctx.set_option("path", NATURAL)
+    ctx.set_pair(0, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+    pose0 = orc.reference_perturbation(p.T_wc1)
+    ctx.prepare(0, orc.se3_to_mat16(pose0))
+    rng = np.random.default_rng(2)
+    poses = np.stack([orc.se3_to_mat16(orc.se3_mul(orc.se3_exp(rng.normal(size=6) * 2e-3), pose0)) for _ in range(n_jobs)])
+    jp = np.zeros(n_jobs, dtype=np.int32)
+    ref = ctx.eval_jobs(poses, jp, True)
+    ctx.set_option("force_strips", 32)  # 96 x 32 (job, strip) slots would not fit: clamped by the library
+    got = ctx.eval_jobs(poses, jp, True)
+    for x, y in zip(got, ref):
+        np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-12)
+    with pytest.raises(nid.NidError):
+        ctx.set_option("force_strips", -1)
+
+
+@pytest.mark.parametrize("path", [NATURAL, SORTED])
+def test_first_row_and_column_points_at_identity(nid, orc, make_pair, synth, path):
+    """T_cw1 = T_wc0^-1 with valid depth in the first image row and column: those points have u == 0 or v == 0, the
+    Jacobian bounds test admits them (types_six_dof_expmap.cpp:433) and their gradient taps sit at -1.0 exactly.
+    Upstream that indexes the image at -1 (undefined); here and in the oracle it is the continuous extension
+    (nid_device.cuh interp_u8). Two pair slots hold different images: slot 1 must not see slot 0's bytes."""
+    pa = make_pair(1000, 120, 160)
+    pb = make_pair(1001, 120, 160)
+    pa = dataclasses.replace(pa, im1=pa.im0.copy())
+    pb = dataclasses.replace(pb, im1=pb.im0.copy())
+    ctx = nid.Context(pa.rows, pa.cols, 2, 16, n_pairs=2, max_jobs=2)
+    ctx.set_option("path", path)
+    for slot, p in enumerate((pa, pb)):
+        pose_id = orc.se3_from_mat16(synth.mat16_inverse(p.T_wc0))
+        P = orc.Problem(p.im0, p.depth0, p.im1, p.T_wc0, p.intr, 2, 16, threads=4)
+        P.set_quirks(0, 1)
+        ctx.set_pair(slot, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+        M = orc.se3_to_mat16(pose_id)
+        nc, href = ctx.prepare(slot, M)
+        nco, hrefo = P.prepare(pose_id)
+        assert np.array_equal(nc, nco)
+        px = P.pixels(pose_id)
+        assert np.sum((px[:, 0] == 0.0) & (px[:, 6] == 1)) > 20 and np.sum((px[:, 1] == 0.0) & (px[:, 6] == 1)) > 20
+        Ht, Hj, J = ctx.eval(slot, M, True)
+        Hto, Hjo, erro, Jo = P.eval(pose_id, True)
+        np.testing.assert_allclose(Ht, Hto, rtol=1e-11)
+        np.testing.assert_allclose(Hj, Hjo, rtol=1e-11)
+        scale = np.abs(Jo).max(axis=1, keepdims=True)
+        assert np.max(np.abs(J - Jo) / scale) < 1e-8
+        got = ctx.warp_sample_f64(slot, M)
+        m = ~np.isnan(px[:, 0])
+        np.testing.assert_allclose(got[m, 2:5], px[m, 2:5], rtol=1e-12, atol=1e-10)
+
+
+@pytest.mark.parametrize("cell,bins", [(4, 16), (8, 10)])
+def test_batched_u16_setup_equals_single_pair_setup(nid, orc, make_pair, cell, bins):
+    """nid_set_pairs_u16 + nid_prepare_pairs (raw 16-bit depth, task tables built on the device, several pairs per
+    launch, more pairs than one set-up batch) against nid_set_pair + nid_prepare pair by pair: same n_c and H_ref, and
+    bit-identical evaluations."""
+    n = 37  # > one set-up batch of 32
+    pairs = [make_pair(1000 + (i % 5), 120, 160, invalid_depth_frac=0.02 * (i % 3)) for i in range(n)]
+    pose0 = [orc.reference_perturbation(p.T_wc1) for p in pairs]
+    rng = np.random.default_rng(4)
+    init = np.stack([orc.se3_to_mat16(orc.se3_mul(orc.se3_exp(rng.normal(size=6) * 2e-3), pose0[i])) for i in range(n)])
+    A = nid.Context(120, 160, cell, bins, n_pairs=n, max_jobs=n)
+    keep = A.set_pairs_u16(0, np.stack([p.depth0_u16 for p in pairs]), np.stack([p.im0 for p in pairs]),
+                           np.stack([p.im1 for p in pairs]), np.stack([p.T_wc0 for p in pairs]),
+                           np.stack([p.intr for p in pairs]))
+    ncA, hrefA = A.prepare_pairs(0, init)
+    del keep
+    Bc = nid.Context(120, 160, cell, bins, n_pairs=n, max_jobs=n)
+    for i, p in enumerate(pairs):
+        Bc.set_pair(i, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+        nc, href = Bc.prepare(i, init[i])
+        assert np.array_equal(nc, ncA[i]) and np.array_equal(href, hrefA[i], equal_nan=True)
+    assert np.array_equal(A.points3d(3), Bc.points3d(3), equal_nan=True)
+    jp = np.arange(n, dtype=np.int32)
+    ra = A.eval_jobs(init, jp, True)
+    rb = Bc.eval_jobs(init, jp, True)
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x, y, equal_nan=True)
+    # against the oracle for one pair of the second batch
+    i = 34
+    P = orc.Problem(pairs[i].im0, pairs[i].depth0, pairs[i].im1, pairs[i].T_wc0, pairs[i].intr, cell, bins, threads=4)
+    P.set_quirks(0, 1)
+    pose_i = orc.se3_from_mat16(init[i])
+    nco, hrefo = P.prepare(pose_i)
+    assert np.array_equal(ncA[i], nco)
+    Hto, Hjo, _, Jo = P.eval(pose_i, True)
+    act = ~np.isnan(hrefo)
+    np.testing.assert_allclose(ra[0][i][act], Hto[act], rtol=1e-11)
+    np.testing.assert_allclose(ra[1][i][act], Hjo[act], rtol=1e-11)
+    # a re-prepare of a sub-range at other poses only touches that range
+    A.prepare_pairs(5, init[5:9] )
+    rc = A.eval_jobs(init, jp, True)
+    for x, y in zip(ra, rc):
+        assert np.array_equal(x, y, equal_nan=True)

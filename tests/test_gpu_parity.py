@@ -311,10 +311,7 @@ def test_warp_sample_jobs_batched_kernel1(nid, orc, make_pair, synth, kind):
         pa, pb = _saturate(pa), _saturate(pb)
     poses = []
     if kind == "integer_aligned":
-        depth = pb.depth0.copy()
-        depth[0, :] = 0.0
-        depth[:, 0] = 0.0
-        pb = dataclasses.replace(pb, im1=pb.im0.copy(), depth0=depth)
+        pb = dataclasses.replace(pb, im1=pb.im0.copy())  # (first row / column keep their depth: taps at -1.0 are defined)
     ctx = nid.Context(pa.rows, pa.cols, 4, 16, n_pairs=2, max_jobs=4)
     probs = []
     for i, p in enumerate((pa, pb)):
@@ -365,12 +362,9 @@ def test_integer_aligned_warp(nid, orc, make_pair, synth, path):
     decisions must be the reference's."""
     p = make_pair(1000, 120, 160)
     import dataclasses
-    depth = p.depth0.copy()
-    # u == 0 or v == 0 exactly makes the reference's gradient read column / row -1 (outside the image,
-    # types_six_dof_expmap.h:310-328 with ix = -1): undefined upstream, so keep those pixels out
-    depth[0, :] = 0.0
-    depth[:, 0] = 0.0
-    p = dataclasses.replace(p, im1=p.im0.copy(), depth0=depth)
+    # (points with u == 0 or v == 0 exactly, whose gradient taps index column / row -1 upstream, are covered by
+    # tests/test_gpu_api_state.py::test_first_row_and_column_points_at_identity)
+    p = dataclasses.replace(p, im1=p.im0.copy())
     pose_id = orc.se3_from_mat16(synth.mat16_inverse(p.T_wc0))
     P = orc.Problem(p.im0, p.depth0, p.im1, p.T_wc0, p.intr, 2, 16, threads=4)
     P.set_quirks(0, 1)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 
-@pytest.mark.parametrize("bins", [8, 10, 16, 32])
+@pytest.mark.parametrize("bins", [6, 8, 10, 12, 14, 16, 32])
 def test_bspline_partition_of_unity(orc, bins):
     for I in np.concatenate([np.linspace(0, 254.999, 301), [0, 51, 102, 254.999]]):
         u = I * (bins - 3) / 255.0
@@ -176,7 +176,7 @@ def test_lm_decreases_cost(orc, make_pair):
     assert np.all(np.diff(trace[:, 0]) <= 1e-12)  # accepted steps only ever lower the robust cost
 
 
-@pytest.mark.parametrize("bins", [8, 10, 14, 16, 32, 40])
+@pytest.mark.parametrize("bins", [6, 7, 8, 10, 12, 14, 16, 32, 40])
 def test_uniform_basis_fold_equals_clamped_basis(orc, bins):
     """the sorted kernels evaluate the *uniform* cubic B-spline per pixel and fold a 3x3 block at either
     end once per task row (values) / class table (derivatives). Check the identity N = A U and N' = A U' against the
