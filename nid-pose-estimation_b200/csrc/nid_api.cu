@@ -70,7 +70,7 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start; p.cell_slice_start = c->cell_slice_start;
   p.cls_task_start = c->cls_task_start; p.span_start = c->span_start; p.wv = c->wv;
   p.max_tasks = c->max_tasks; p.g_stride = (int)c->g_stride;
-  p.G = c->G; p.fp1 = c->fp1; p.tex2 = c->d_tex2;
+  p.G = c->G; p.fp1 = c->fp1; p.tex2 = c->d_tex2; p.k1tex = c->d_k1tex;
   return p;
 }
 
@@ -119,6 +119,7 @@ int ensure_job_buffers(nid_ctx* c) {
 
 // footprint-packed plane and gather texture of the targets of pairs [pair0, pair0 + n)
 static int update_textures(nid_ctx* c, int pair0, int n) {
+  for (int i = 0; i < n; i++) c->k1_ready[pair0 + i] = 0;  // kernel 1's planes follow the target image (rebuilt on next use)
   for (int p0 = pair0; p0 < pair0 + n; p0 += c->setup_batch) {
     const int nb = std::min(c->setup_batch, pair0 + n - p0);
     OKR(launch_pack(c, p0, nb));
@@ -299,6 +300,11 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
       return NID_ERR_CUDA;
     }
     OKR(dalloc(&c->d_tex2, P, "d_tex2"));
+    OKR(dalloc(&c->d_k1tex, P, "d_k1tex"));
+    CU(cudaMemset(c->d_k1tex, 0, sizeof(cudaTextureObject_t) * P), "memset k1tex");
+    c->k1_arrays.assign(P, nullptr);
+    c->h_k1tex.assign(P, 0);
+    c->k1_ready.assign(P, 0);
     CU(cudaMemcpy(c->d_tex2, c->h_tex2.data(), sizeof(cudaTextureObject_t) * P, cudaMemcpyHostToDevice), "H2D tex2 handles");
     c->setup_batch = (int)std::min<size_t>(P, 32);
     OKR(dalloc(&c->d_pack, N * (size_t)c->setup_batch, "d_pack"));
@@ -350,6 +356,10 @@ int nid_destroy(nid_ctx* c) {
                   c->job_pair, c->aux_pose, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
                   c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sl_off, c->sl_task, c->sl_cell, c->nslices, c->task_pos,
                   c->lay_tot, c->lay_base, c->prep_poses, c->depth16, c->depth_factor, c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->fp1, c->cls_task_start, c->span_start, c->wv};
+  for (auto t : c->h_k1tex) if (t) cudaDestroyTextureObject(t);
+  for (auto arr : c->k1_arrays) if (arr) cudaFreeArray(arr);
+  if (c->d_k1tex) cudaFree(c->d_k1tex);
+  if (c->d_k1pack) cudaFree(c->d_k1pack);
   for (auto t : c->h_tex2) if (t) cudaDestroyTextureObject(t);
   for (auto arr : c->tex2_arrays) if (arr) cudaFreeArray(arr);
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -911,19 +921,49 @@ int nid_warp_sample(nid_ctx* c, int pair, const double T_cw1[16], float* out) {
   return NID_OK;
 }
 
+// Kernel 1's target texture of one pair: three stacked fp16 planes (I, Gx/2, Gy/2) in a gather-able CUDA array, created
+// and filled the first time the pair is used by nid_warp_sample_jobs after its target image changed.
+static int ensure_k1_texture(nid_ctx* c, int pair) {
+  if (c->k1_ready[pair]) return NID_OK;
+  if (!c->k1_arrays[pair]) {
+    cudaChannelFormatDesc cd = cudaCreateChannelDescHalf();
+    CU(cudaMallocArray(&c->k1_arrays[pair], &cd, c->cols, 3 * c->rows, cudaArrayTextureGather), "cudaMallocArray (kernel-1 planes)");
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = c->k1_arrays[pair];
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    CU(cudaCreateTextureObject(&c->h_k1tex[pair], &rd, &td, nullptr), "cudaCreateTextureObject (kernel-1 planes)");
+    CU(cudaMemcpyAsync(c->d_k1tex + pair, &c->h_k1tex[pair], sizeof(cudaTextureObject_t), cudaMemcpyHostToDevice, c->stream), "H2D k1 texture handle");
+  }
+  if (!c->d_k1pack) OKR(dalloc(&c->d_k1pack, (size_t)3 * c->N, "d_k1pack"));
+  OKR(launch_pack_k1(c, pair, c->d_k1pack));
+  CU(cudaMemcpy2DToArrayAsync(c->k1_arrays[pair], 0, 0, c->d_k1pack, sizeof(unsigned short) * c->cols, sizeof(unsigned short) * c->cols,
+                              3 * c->rows, cudaMemcpyDeviceToDevice, c->stream), "fp16 planes -> texture array");
+  c->k1_ready[pair] = 1;
+  return NID_OK;
+}
+
 int nid_warp_sample_jobs(nid_ctx* c, int n_jobs, const int* job_pair, const double* poses, float* out) {
   if (!c || !poses) { set_error("bad argument"); return NID_ERR_ARG; }
   CU(cudaSetDevice(c->device), "cudaSetDevice");
   if (n_jobs < 1 || n_jobs > c->max_jobs) { set_error("n_jobs out of range"); return NID_ERR_ARG; }
   if (c->sell_points) { set_error("nid_warp_sample_jobs needs depth pairs (nid_set_pair), not caller-supplied points"); return NID_ERR_UNSUPPORTED; }
-  if (!c->d_tex2) { set_error("nid_warp_sample_jobs needs the packed target textures (6 to 40 bins)"); return NID_ERR_UNSUPPORTED; }
   if (!c->d_pix4_jobs) OKR(dalloc(&c->d_pix4_jobs, (size_t)4 * c->N * c->max_jobs, "d_pix4_jobs"));
   OKR(stage_jobs(c, n_jobs, job_pair, poses, 1));
   c->staged_jobs = 0;  // (not evaluation jobs: the pairs need not be prepared)
   // pairs uploaded as raw 16-bit depth are read as such (2 B/px); a mixed batch falls back to the fp64 planes, which
   // every pair has
   bool u16 = true;
-  for (int j = 0; j < n_jobs; j++) u16 = u16 && c->pair_u16[c->h_job_pair[j]];
+  for (int j = 0; j < n_jobs; j++) {
+    u16 = u16 && c->pair_u16[c->h_job_pair[j]];
+    OKR(ensure_k1_texture(c, c->h_job_pair[j]));
+  }
   OKR(launch_warp_sample_jobs(c, n_jobs, (float4*)c->d_pix4_jobs, u16));
   if (out) CU(cudaMemcpyAsync(out, c->d_pix4_jobs, sizeof(float) * 4 * c->N * (size_t)n_jobs, cudaMemcpyDefault, c->stream), "D2H pix4 jobs");
   CU(cudaStreamSynchronize(c->stream), "sync warp_sample_jobs");

@@ -72,6 +72,7 @@ struct EvalParams {
   double* G;            // [jobs][g_stride][bins]
   const unsigned* fp1;              // [n_pairs][N] footprint-packed target image (pass 1), see k_pack_fp
   const cudaTextureObject_t* tex2;  // [n_pairs] packed I | Gx | Gy 32-bit texture (k_pack_tex)
+  const cudaTextureObject_t* k1tex; // [n_pairs] kernel 1: fp16 planes I, Gx/2, Gy/2 stacked (k_pack_k1); built on first use
 };
 
 }  // namespace nid
@@ -133,6 +134,12 @@ struct nid_ctx {
   std::vector<cudaArray_t> tex2_arrays;
   std::vector<cudaTextureObject_t> h_tex2;
   cudaTextureObject_t* d_tex2 = nullptr;
+  // kernel 1 (nid_warp_sample_jobs): fp16 target planes, created and filled on first use per pair
+  std::vector<cudaArray_t> k1_arrays;
+  std::vector<cudaTextureObject_t> h_k1tex;
+  cudaTextureObject_t* d_k1tex = nullptr;
+  std::vector<char> k1_ready;
+  unsigned short* d_k1pack = nullptr;  // [3N] scratch
   unsigned* fp1 = nullptr;     // [n_pairs][N]
   std::vector<double> h_Twc0, h_cam;  // host copies per pair (geometry tables are built on the host)
   unsigned* d_pack = nullptr;  // [setup_batch][N] scratch for the packed textures
@@ -213,6 +220,7 @@ int sorted_init(nid_ctx* c);
 int launch_count_classes(nid_ctx* c, int pair);
 int launch_layout_and_scatter(nid_ctx* c, int pair0, int n);
 int launch_pack(nid_ctx* c, int pair0, int n);
+int launch_pack_k1(nid_ctx* c, int pair, unsigned short* d_out);
 int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int want_jac);
 int launch_href(nid_ctx* c, int pair0, int n);
 

@@ -37,6 +37,7 @@
 // Memory-system details that were measured to matter: the pixel store is read with evict-first
 // loads and prefetched into L2 two groups ahead, so that L1 stays with the target-image gathers; CTAs are small
 // (128 / 64 threads) at the same number of resident warps; the shared-memory carve-out is requested per kernel.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include <algorithm>
@@ -1262,6 +1263,22 @@ __global__ void __launch_bounds__(256) k_jac_final_sorted(EvalParams p, int n_jo
   }
 }
 
+// Kernel-1 target texture: three stacked planes of 16-bit floats, rows [0,R) I, [R,2R) Gx/2, [2R,3R) Gy/2 with the
+// central differences Gx = I(x+1,y) - I(x-1,y), Gy = I(x,y+1) - I(x,y-1) (types_six_dof_expmap.cpp:434-435); border
+// texels use clamped neighbours and are never consumed (the first row / column takes the literal formula).
+__global__ void k_pack_k1(int rows, int cols, const uint8_t* __restrict__ im, unsigned short* __restrict__ out) {
+  const int N = rows * cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const int y = i / cols, x = i % cols;
+    const int xm = max(x - 1, 0), xp = min(x + 1, cols - 1), ym = max(y - 1, 0), yp = min(y + 1, rows - 1);
+    const int gx = (int)im[y * cols + xp] - (int)im[y * cols + xm];
+    const int gy = (int)im[yp * cols + x] - (int)im[ym * cols + x];
+    out[i] = __half_as_ushort(__float2half_rn((float)im[i]));
+    out[N + i] = __half_as_ushort(__float2half_rn(0.5f * (float)gx));
+    out[2 * N + i] = __half_as_ushort(__float2half_rn(0.5f * (float)gy));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Kernel 1 on its own, batched over jobs (north_star kernel (1); parity + HBM roofline probe; the evaluation path
 // fuses the same front end into both passes instead of storing its output). A streaming kernel:
@@ -1269,25 +1286,72 @@ __global__ void __launch_bounds__(256) k_jac_final_sorted(EvalParams p, int n_jo
 //   out  {I_c, g_x, g_y, valid} as one float4 per pixel (16 B/px), valid: 0 invalid, 1 cost only, 3 cost + Jacobian
 // A CTA of 128 threads owns 512 consecutive pixels; thread t takes pixels t, t+128, t+256, t+384 of them, so every
 // warp load is 32 consecutive depths and every warp store 512 contiguous bytes (evict-first: written once, never read
-// here). fp64 is kept for what decides something -- back-projection, SE3 warp, projection, the (int) truncation and
-// the in-bounds tests, with the same exact fall-backs as pass 2 for (u, v) within 2^-24 of an integer, saturated
-// footprints and the first image row / column -- and the three bilinear samples, whose results are stored as
-// floats anyway, are evaluated in fp32 from the fp64 fractions (one packed 2x2 gather serves all three).
-// One Newton step on the reciprocal leaves (u, v) within 2^-36 of their exact values: far inside the 2^-24 guard band.
+// here). The first version of this kernel was issue-bound at 217 instructions per pixel (profiles/r02_k1_*): two
+// thirds of them unpacking and converting the twelve integer taps and re-deriving the viewing ray. Now:
+//  * the target lives in a 16-bit-float gather texture of three stacked planes {I, Gx/2, Gy/2} (small integers and
+//    half-integers: exact in fp16), so one gather per channel delivers four ready-made floats: no unpacking, no
+//    integer-to-float conversion, and the /2 of the central differences is already in the texels;
+//  * the ray d = M (cxn, cyn, 1) is affine in (col, row): it is evaluated once per thread and stepped by 128 columns
+//    (three DADDs per pixel instead of ten fp64 operations and two conversions);
+//  * the validity logic is branch-free bit arithmetic and full chunks skip the per-pixel range checks.
+// fp64 is kept for what decides something -- SE3 warp, projection, the (int) truncation and the in-bounds tests,
+// with the same exact fall-backs as pass 2 for (u, v) within 2^-24 of an integer, saturated footprints and the first
+// image row / column -- and the three bilinear samples, whose results are stored as floats anyway, are evaluated in
+// fp32 from the fp64 fractions. One Newton step on the reciprocal leaves (u, v) within 2^-36 of their exact values:
+// far inside the 2^-24 guard band.
 #ifndef NID_WS_MINB
 #define NID_WS_MINB 8
 #endif
+// Kernel-1 pixel i by the reference's literal sequence (rare path; re-reads its depth): cost validity and intensity
+// from (u, v), Jacobian validity and gradient from the second projection (types_six_dof_expmap.cpp:562-575, :407-435).
+// out3 = {I_c, 2 g_x, 2 g_y}; returns valid bits (1 cost, 2 Jacobian).
+template <bool U16>
+__device__ __noinline__ unsigned warp_sample_literal(const EvalParams& p, int job, int pair, int i, const double* __restrict__ depth64,
+                                                     const uint16_t* __restrict__ depth16, const double* __restrict__ factor_all,
+                                                     float* out3) {
+  const size_t pbase = (size_t)pair * p.N;
+  const double z = U16 ? __dmul_rn((double)depth16[pbase + i], factor_all[pair]) : depth64[pbase + i];
+  const int row = i / p.cols, col = i - row * p.cols;
+  const unsigned id = ((unsigned)row << 16) | (unsigned)col;
+  const double* T1 = p.poses + 16 * job;
+  const double* T0 = p.Twc0 + 16 * pair;
+  const double* camg = p.cam + 4 * pair;
+  double e[5];
+  exact_uv<false>(T1, T0, camg, z, 0.0, 0.0, id, e);
+  out3[0] = 0.f; out3[1] = 0.f; out3[2] = 0.f;
+  if (!inb_cost(e[3], e[4], p.rows, p.cols)) return 0u;
+  const uint8_t* im1 = p.im1 + pbase;
+  out3[0] = (float)clamp_intensity(interp_u8(im1, p.cols, e[3], e[4]));
+  double o6[6];
+  if (!jac_pixel_literal<false>(T1, T0, camg, p.rows, p.cols, im1, z, 0.0, 0.0, id, o6)) return 1u;
+  out3[1] = (float)o6[4]; out3[2] = (float)o6[5];
+  return 3u;
+}
+#ifndef NID_WS_W
 #define NID_WS_W 4
+#endif
+#ifndef NID_WS_ORDER
+#define NID_WS_ORDER 0
+#endif
+// Geometry entries of this kernel (fill_geo_k1): [0..2] A, [3..5] B, [6..8] C with the ray d = A col + B row + C
+// (rows 0 and 1 pre-multiplied by fx, fy), [9..11] translation (same scaling), [12..14] 128 A, [15..17] B - cols A
+// (the step into the next image row), [18] cx, [19] cy.
 template <int NG, bool U16>
 __global__ void __launch_bounds__(128, NID_WS_MINB)
 k_warp_sample_jobs(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt,
                    const double* __restrict__ depth64, const uint16_t* __restrict__ depth16,
                    const double* __restrict__ factor_all, float4* __restrict__ out) {
   constexpr int W = NID_WS_W;
-  const int job = blockIdx.x + p.job0;
+#if NID_WS_ORDER
+  const int jb = blockIdx.y, cb_ = blockIdx.x;  // chunk index fast: neighbouring CTAs stream one pair
+#else
+  const int jb = blockIdx.x, cb_ = blockIdx.y;  // job index fast
+#endif
+  const int job = jb + p.job0;
   const int pair = p.job_pair[job];
-  const double* g = gt.g[blockIdx.x];  // pass-1 form: rows 0 and 1 of M pre-multiplied by fx, fy
-  const int i0 = blockIdx.y * (128 * W) + threadIdx.x;
+  const double* g = gt.g[jb];
+  const int i0 = cb_ * (128 * W) + threadIdx.x;
+  const bool full = (cb_ + 1) * (128 * W) <= p.N;  // (uniform per CTA)
   const size_t pbase = (size_t)pair * p.N;
   // depths first: W independent loads in flight
   double z[W];
@@ -1295,90 +1359,97 @@ k_warp_sample_jobs(const __grid_constant__ EvalParams p, const __grid_constant__
     const double factor = factor_all[pair];
     unsigned raw[W];
 #pragma unroll
-    for (int j = 0; j < W; j++) raw[j] = (i0 + j * 128 < p.N) ? (unsigned)__ldcs(depth16 + pbase + i0 + j * 128) : 0u;
+    for (int j = 0; j < W; j++) raw[j] = (full || i0 + j * 128 < p.N) ? (unsigned)__ldcs(depth16 + pbase + i0 + j * 128) : 0u;
 #pragma unroll
     for (int j = 0; j < W; j++) z[j] = __dmul_rn(u2d(raw[j]), factor);  // NID_pose_estimation.cpp:105-106, one rounding
   } else {
 #pragma unroll
-    for (int j = 0; j < W; j++) z[j] = (i0 + j * 128 < p.N) ? __ldcs(depth64 + pbase + i0 + j * 128) : 0.0;
+    for (int j = 0; j < W; j++) z[j] = (full || i0 + j * 128 < p.N) ? __ldcs(depth64 + pbase + i0 + j * 128) : 0.0;
   }
   int row = i0 / p.cols, col = i0 - row * p.cols;
-  int ix[W], iy[W];
+  double d0, d1, d2;
+  {
+    const double fc = u2d((unsigned)col), fr = u2d((unsigned)row);
+    d0 = fma(g[0], fc, fma(g[3], fr, g[6]));
+    d1 = fma(g[1], fc, fma(g[4], fr, g[7]));
+    d2 = fma(g[2], fc, fma(g[5], fr, g[8]));
+  }
+  // what survives the front end, per pixel: the footprint corner, the two fractions as floats, three flag bits
+  // (1 cost-valid, 2 Jacobian-valid, 4 take the literal path); the rare paths re-read everything else
+  int jxs[W], jys[W];
+  unsigned flags = 0;
   float dxf[W], dyf[W];
-  unsigned flags[W];  // bit 0 cost-valid, bit 1 Jacobian-valid, bit 2 undecided by the fast path, bits 8.. column | row << 16 kept apart
-  unsigned ids[W];
+  const int c3 = p.cols - 3, r3 = p.rows - 3;
 #pragma unroll
   for (int j = 0; j < W; j++) {
     // depth outside [0.01, 100] is a NaN point in the reference (CudaPoints3d.cu:16-19)
-    const bool valid = z[j] >= 0.01 && z[j] <= 100.0 && (i0 + j * 128 < p.N);
-    ids[j] = ((unsigned)row << 16) | (unsigned)col;
-    const double cxn = fma(u2d((unsigned)col), g[12], g[13]);
-    const double cyn = fma(u2d((unsigned)row), g[14], g[15]);
-    const double d0 = fma(g[0], cxn, fma(g[3], cyn, g[6]));
-    const double d1 = fma(g[1], cxn, fma(g[4], cyn, g[7]));
-    const double d2 = fma(g[2], cxn, fma(g[5], cyn, g[8]));
-    const double zz = valid ? z[j] : 1.0;
-    const double x1 = fma(zz, d0, g[9]), y1 = fma(zz, d1, g[10]), z1 = fma(zz, d2, g[11]);
+    const unsigned valid = (z[j] >= 0.01) & (z[j] <= 100.0);
+    const double x1 = fma(z[j], d0, g[9]), y1 = fma(z[j], d1, g[10]), z1 = fma(z[j], d2, g[11]);
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z1));
     y = fma(y, fma(-z1, y, 1.0), y);
     const double u = fma(x1, y, g[18]), v = fma(y1, y, g[19]);
-    const int jx = __double2int_rz(u), jy = __double2int_rz(v);
+    const int jx = __double2int_rz(u), jy = __double2int_rz(v);  // NaN -> 0, saturating
     const double dx = u - u2d((unsigned)jx), dy = v - u2d((unsigned)jy);
-    const bool inr = valid && (unsigned)jx <= (unsigned)(p.cols - 3) && (unsigned)jy <= (unsigned)(p.rows - 3);
-    const bool safe = frac_is_safe(dx) && frac_is_safe(dy);
-    const bool ok = inr && safe && jx <= p.cols - 4 && jy <= p.rows - 4;
-    const bool jac = ok && jx <= p.cols - 5;
-    flags[j] = (ok ? 1u : 0u) | (jac ? 2u : 0u) | ((inr && !safe) ? 4u : 0u);
-    ix[j] = ok ? jx : 0; iy[j] = ok ? jy : 0;
+    // with u, v not within 2^-24 of an integer the integer comparisons decide exactly like
+    // `u>=0 && u+3<=cols && v>=0 && v+3<=rows` (types_six_dof_expmap.cpp:565; :433 with cols-1)
+    const unsigned band = valid & ((unsigned)jx <= (unsigned)c3) & ((unsigned)jy <= (unsigned)r3);
+    const unsigned safe = (unsigned)frac_is_safe(dx) & (unsigned)frac_is_safe(dy);
+    const unsigned ok = band & safe & (jx < c3) & (jy < r3);
+    const unsigned jac = ok & (jx < c3 - 1);
+    const unsigned lit = (band & (safe ^ 1u)) | (ok & ((jx < 1) | (jy < 1)));  // undecided, or first row / column
+    flags |= (ok | (jac << 1) | (lit << 2)) << (4 * j);
+    jxs[j] = ok ? jx : 0; jys[j] = ok ? jy : 0;
     dxf[j] = (float)dx; dyf[j] = (float)dy;
-    col += 128;
-    if (col >= p.cols) { col -= p.cols; row++; if (col >= p.cols) { row += col / p.cols; col %= p.cols; } }
+    if (j + 1 < W) {
+      col += 128;
+      d0 += g[12]; d1 += g[13]; d2 += g[14];
+      while (col >= p.cols) { col -= p.cols; d0 += g[15]; d1 += g[16]; d2 += g[17]; }
+    }
   }
-  uint4 t[W];
-  const cudaTextureObject_t tex = p.tex2[pair];
-#pragma unroll
-  for (int j = 0; j < W; j++) t[j] = gather_u32(tex, ix[j], iy[j]);
+  const cudaTextureObject_t tex = p.k1tex[pair];
   float4* o = out + (size_t)job * p.N + i0;
 #pragma unroll
   for (int j = 0; j < W; j++) {
-    if (i0 + j * 128 >= p.N) continue;
-    // texel = I | (Gx+256) << 8 | (Gy+256) << 17; footprint .w (ix,iy) .z (ix+1,iy) .x (ix,iy+1) .y (ix+1,iy+1)
-    const int i00 = t[j].w & 0xffu, i01 = t[j].z & 0xffu, i10 = t[j].x & 0xffu, i11 = t[j].y & 0xffu;
-    const int x00 = (t[j].w >> 8) & 0x1ffu, x01 = (t[j].z >> 8) & 0x1ffu, x10 = (t[j].x >> 8) & 0x1ffu, x11 = (t[j].y >> 8) & 0x1ffu;
-    const int y00 = t[j].w >> 17, y01 = t[j].z >> 17, y10 = t[j].x >> 17, y11 = t[j].y >> 17;
+    // one gather per plane: .w (ix,iy) .z (ix+1,iy) .x (ix,iy+1) .y (ix+1,iy+1)
+    const float gxc = (float)(jxs[j] + 1), gyc = (float)(jys[j] + 1);
+#ifdef NID_WS_NOGATHER
+    const float4 I = make_float4(gxc, gyc, 3.f, 4.f), X = I, Y = I;
+#else
+    const float4 I = tex2Dgather<float4>(tex, gxc, gyc, 0);
+#if defined(NID_WS_G1)
+    const float4 X = make_float4(I.y, I.x, I.w, I.z), Y = make_float4(I.z, I.w, I.x, I.y);
+#elif defined(NID_WS_G2)
+    const float4 X = tex2Dgather<float4>(tex, gxc, gyc + (float)p.rows, 0);
+    const float4 Y = make_float4(I.z + X.x, I.w, I.x, I.y);
+#else
+    const float4 X = tex2Dgather<float4>(tex, gxc, gyc + (float)p.rows, 0);
+    const float4 Y = tex2Dgather<float4>(tex, gxc, gyc + (float)(2 * p.rows), 0);
+#endif
+#endif
     const float fx_ = dxf[j], fy_ = dyf[j];
-    // p00 + dx d0 + dy ((p10 + dx d1) - (p00 + dx d0)), small exact integers as floats
-    float a = fmaf(fx_, (float)(i01 - i00), (float)i00), b = fmaf(fx_, (float)(i11 - i10), (float)i10);
-    float ic = fmaf(fy_, b - a, a);
-    a = fmaf(fx_, (float)(x01 - x00), (float)(x00 - 256)); b = fmaf(fx_, (float)(x11 - x10), (float)(x10 - 256));
-    float gx2 = fmaf(fy_, b - a, a);
-    a = fmaf(fx_, (float)(y01 - y00), (float)(y00 - 256)); b = fmaf(fx_, (float)(y11 - y10), (float)(y10 - 256));
-    float gy2 = fmaf(fy_, b - a, a);
-    bool vc = flags[j] & 1u, vj = flags[j] & 2u;
-    const bool sat = (t[j].w & t[j].z & t[j].x & t[j].y & 0xffu) == 0xffu;
-    if ((flags[j] & 4u) || (vc && (sat || ix[j] < 1 || iy[j] < 1))) {
-      // the reference's literal sequence: cost validity and intensity from (u, v), Jacobian validity and gradient
-      // from the second projection (types_six_dof_expmap.cpp:562-575, :407-435)
-      const double* T1 = p.poses + 16 * job;
-      const double* T0 = p.Twc0 + 16 * pair;
-      const double* camg = p.cam + 4 * pair;
-      double e[5];
-      exact_uv<false>(T1, T0, camg, z[j], 0.0, 0.0, ids[j], e);
-      vc = inb_cost(e[3], e[4], p.rows, p.cols);
-      vj = false;
-      ic = 0.f; gx2 = 0.f; gy2 = 0.f;
-      if (vc) {
-        const uint8_t* im1 = p.im1 + pbase;
-        ic = (float)clamp_intensity(interp_u8(im1, p.cols, e[3], e[4]));
-        double o6[6];
-        vj = jac_pixel_literal<false>(T1, T0, camg, p.rows, p.cols, im1, z[j], 0.0, 0.0, ids[j], o6);
-        if (vj) { gx2 = (float)o6[4]; gy2 = (float)o6[5]; }
+    const float w11 = fx_ * fy_, w01 = fx_ - w11, w10 = fy_ - w11, w00 = (1.0f - fx_) - w10;
+    float ic = fmaf(w11, I.y, fmaf(w10, I.x, fmaf(w01, I.z, w00 * I.w)));
+    float gx = fmaf(w11, X.y, fmaf(w10, X.x, fmaf(w01, X.z, w00 * X.w)));
+    float gy = fmaf(w11, Y.y, fmaf(w10, Y.x, fmaf(w01, Y.z, w00 * Y.w)));
+    const unsigned f = flags >> (4 * j);
+    unsigned vc = f & 1u, vj = (f >> 1) & 1u;
+    const unsigned sat = fminf(fminf(I.x, I.y), fminf(I.z, I.w)) == 255.0f;
+    if (((f >> 2) | (vc & sat)) & 1u) {
+      if (full || i0 + j * 128 < p.N) {
+        float r3_[3];
+        const unsigned vv = warp_sample_literal<U16>(p, job, pair, i0 + j * 128, depth64, depth16, factor_all, r3_);
+        vc = vv & 1u; vj = (vv >> 1) & 1u;
+        ic = r3_[0]; gx = 0.5f * r3_[1]; gy = 0.5f * r3_[2];
       }
     }
-    if (!vc) ic = 0.f;
-    if (!vj) { gx2 = 0.f; gy2 = 0.f; }
-    __stcs(o + j * 128, make_float4(ic, 0.5f * gx2, 0.5f * gy2, (float)((vc ? 1 : 0) + (vj ? 2 : 0))));
+    ic = vc ? ic : 0.f;
+    gx = vj ? gx : 0.f; gy = vj ? gy : 0.f;
+    const float fl = vc ? (vj ? 3.f : 1.f) : 0.f;
+#ifdef NID_WS_NOSTORE
+    if (ic == 123.456f)
+#endif
+    if (full || i0 + j * 128 < p.N) __stcs(o + j * 128, make_float4(ic, gx, gy, fl));
   }
 }
 
@@ -1577,6 +1648,37 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
   return NID_OK;
 }
 
+// Geometry table of kernel 1 (see k_warp_sample_jobs): the ray of pixel (col, row) is affine in (col, row)
+template <int NG>
+static void fill_geo_k1(const nid_ctx* c, GeoTable<NG>& gt, int first, int n) {
+  fill_geo(c, gt, first, n, true);  // [0..11] M with rows 0/1 scaled by fx, fy; [12] 1/fx [13] -cx/fx [14] 1/fy [15] -cy/fy
+  for (int i = 0; i < n; i++) {
+    double* g = gt.g[i];
+    const double ifx = g[12], cxo = g[13], ify = g[14], cyo = g[15], cx = g[18], cy = g[19];
+    double A[3], B[3], C[3];
+    for (int r = 0; r < 3; r++) {
+      A[r] = g[r] * ifx;
+      B[r] = g[3 + r] * ify;
+      C[r] = g[r] * cxo + g[3 + r] * cyo + g[6 + r];
+    }
+    for (int r = 0; r < 3; r++) {
+      g[r] = A[r]; g[3 + r] = B[r]; g[6 + r] = C[r];
+      g[12 + r] = 128.0 * A[r];
+      g[15 + r] = B[r] - (double)c->cols * A[r];
+    }
+    g[18] = cx; g[19] = cy;
+  }
+}
+
+// target planes of kernel 1 for one pair (built on first use; the evaluation path does not need them)
+int launch_pack_k1(nid_ctx* c, int pair, unsigned short* d_out) {
+  int g = (c->N + 255) / 256;
+  if (g > c->sm_count * 8) g = c->sm_count * 8;
+  k_pack_k1<<<g, 256, 0, c->stream>>>(c->rows, c->cols, c->im1 + (size_t)pair * c->N, d_out);
+  NID_LAUNCH_CHECK(c, "k_pack_k1");
+  return NID_OK;
+}
+
 // all jobs of a launch must take their depth from the same kind of plane (raw 16-bit or fp64): u16 says which
 int launch_warp_sample_jobs(nid_ctx* c, int n_jobs, float4* d_out, bool u16) {
   EvalParams p = make_params(c, n_jobs);
@@ -1584,11 +1686,12 @@ int launch_warp_sample_jobs(nid_ctx* c, int n_jobs, float4* d_out, bool u16) {
   for (int s0 = 0; s0 < n_jobs; s0 += NID_GEO_LARGE) {
     const int n = std::min(NID_GEO_LARGE, n_jobs - s0);
     GeoTable<NID_GEO_LARGE> gt;
-    fill_geo(c, gt, s0, n, true);
+    fill_geo_k1(c, gt, s0, n);
     EvalParams q = p;
     q.job0 = s0;
-    if (u16) k_warp_sample_jobs<NID_GEO_LARGE, true><<<dim3(n, chunks), 128, 0, c->stream>>>(q, gt, nullptr, c->depth16, c->depth_factor, d_out);
-    else k_warp_sample_jobs<NID_GEO_LARGE, false><<<dim3(n, chunks), 128, 0, c->stream>>>(q, gt, c->depth, nullptr, nullptr, d_out);
+    const dim3 grid = NID_WS_ORDER ? dim3(chunks, n) : dim3(n, chunks);
+    if (u16) k_warp_sample_jobs<NID_GEO_LARGE, true><<<grid, 128, 0, c->stream>>>(q, gt, nullptr, c->depth16, c->depth_factor, d_out);
+    else k_warp_sample_jobs<NID_GEO_LARGE, false><<<grid, 128, 0, c->stream>>>(q, gt, c->depth, nullptr, nullptr, d_out);
     NID_LAUNCH_CHECK(c, "k_warp_sample_jobs");
   }
   return NID_OK;

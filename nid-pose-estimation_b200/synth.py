@@ -133,6 +133,44 @@ def make_pair(seed: int = 1000, rows: int = 480, cols: int = 640, gamma: float =
                 intr=intr, rows=rows, cols=cols)
 
 
+def make_sequence(seed: int, n: int, rows: int = 480, cols: int = 640) -> list:
+    """n distinct pairs that share one rendered scene (two ray-cast frames, ~1.5 s at 640x480) and differ in what a
+    tracking sequence varies cheaply: pair k sees its own exposure of the reference frame (gain/bias before the 8-bit
+    quantisation), its own gamma/affine illumination change of the target frame, so every pair has its own im0 (and
+    with it its own reference classes), its own im1 and its own solution; depth and ground-truth poses are the
+    scene's. Pair 0 is make_pair(seed) itself. Used for BASELINE config 4 (1024 pairs = 16 scenes x 64 pairs)."""
+    rng = np.random.default_rng(seed)
+    scale = cols / 640.0
+    intr4 = (FX * scale, FY * scale, (CX + 0.5) * scale - 0.5, (CY + 0.5) * scale - 0.5)
+    scene = _Scene(rng)
+    T0 = np.eye(4)
+    T0[:3, :3] = _rot(*rng.uniform(-0.02, 0.02, size=3))
+    T0[:3, 3] = rng.uniform(-0.05, 0.05, size=3)
+    dT = np.eye(4)
+    dT[:3, :3] = _rot(*rng.uniform(-0.01, 0.01, size=3))
+    dT[:3, 3] = rng.uniform(-0.02, 0.02, size=3)
+    T1 = T0 @ dT
+    tex0, z0 = scene.render(T0, rows, cols, intr4)
+    tex1, _ = scene.render(T1, rows, cols, intr4)
+    d16 = np.clip(np.rint(z0 * 5000.0), 0, 65535).astype(np.uint16)
+    depth = d16.astype(np.float64) * DEPTH_FACTOR
+    intr = np.array([*intr4, DEPTH_FACTOR], dtype=np.float64)
+    vr = np.random.default_rng(seed * 7919 + 13)
+    out = []
+    for k in range(n):
+        if k == 0:
+            a0, b0, gamma, gain, bias = 1.0, 0.0, 0.6, 0.8, 0.1
+        else:
+            a0, b0 = vr.uniform(0.85, 1.0), vr.uniform(0.0, 0.08)
+            gamma, gain, bias = vr.uniform(0.45, 1.2), vr.uniform(0.7, 0.95), vr.uniform(0.0, 0.12)
+        im0 = np.clip(np.rint(255.0 * (a0 * tex0 + b0)), 0, 255).astype(np.uint8)
+        im1 = np.clip(np.rint(255.0 * (gain * np.power(tex1, gamma) + bias)), 0, 255).astype(np.uint8)
+        out.append(Pair(im0=im0, im1=im1, depth0=depth, depth0_u16=d16,
+                        T_wc0=np.ascontiguousarray(T0.T).reshape(16).copy(),
+                        T_wc1=np.ascontiguousarray(T1.T).reshape(16).copy(), intr=intr, rows=rows, cols=cols))
+    return out
+
+
 def mat16_inverse(m16: np.ndarray) -> np.ndarray:
     """Rigid inverse of a column-major 4x4."""
     M = m16.reshape(4, 4).T

@@ -172,3 +172,32 @@ def test_batched_u16_setup_equals_single_pair_setup(nid, orc, make_pair, cell, b
     rc = A.eval_jobs(init, jp, True)
     for x, y in zip(ra, rc):
         assert np.array_equal(x, y, equal_nan=True)
+
+
+def test_kernel1_from_raw_u16_depth(nid, orc, make_pair):
+    """nid_warp_sample_jobs on pairs uploaded as raw 16-bit depth (2 B/px in) against the oracle's per-pixel record and
+    against the same pairs uploaded as fp64 depth: flags identical, values to float precision."""
+    pairs = [make_pair(1003, 120, 160, invalid_depth_frac=0.03), make_pair(1004, 120, 160)]
+    A = nid.Context(120, 160, 4, 16, n_pairs=2, max_jobs=4)
+    keep = A.set_pairs_u16(0, np.stack([p.depth0_u16 for p in pairs]), np.stack([p.im0 for p in pairs]),
+                           np.stack([p.im1 for p in pairs]), np.stack([p.T_wc0 for p in pairs]), np.stack([p.intr for p in pairs]))
+    A.sync()
+    B = nid.Context(120, 160, 4, 16, n_pairs=2, max_jobs=4)
+    for i, p in enumerate(pairs):
+        B.set_pair(i, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+    base = [orc.reference_perturbation(p.T_wc1) for p in pairs]
+    xi = np.array([0.002, -0.001, 0.0015, 0.004, -0.003, 0.002])
+    jp = [0, 1, 1, 0]
+    poses = [base[0], base[1], orc.se3_mul(orc.se3_exp(xi), base[1]), orc.se3_mul(orc.se3_exp(-xi), base[0])]
+    M = np.stack([orc.se3_to_mat16(q) for q in poses])
+    ga, gb = A.warp_sample_jobs(M, jp), B.warp_sample_jobs(M, jp)
+    assert np.array_equal(ga, gb)  # same arithmetic once the depth is in a register
+    for j, (pr, pose) in enumerate(zip(jp, poses)):
+        P = orc.Problem(pairs[pr].im0, pairs[pr].depth0, pairs[pr].im1, pairs[pr].T_wc0, pairs[pr].intr, 4, 16, threads=4)
+        P.set_quirks(0, 1)
+        exp = P.pixels(pose)
+        m = ~np.isnan(exp[:, 0])
+        assert np.array_equal(ga[j, m, 3], exp[m, 5] + 2 * exp[m, 6])
+        np.testing.assert_allclose(ga[j, m, 0], exp[m, 2], rtol=1e-6, atol=1e-5)
+        np.testing.assert_allclose(ga[j, m, 1:3], exp[m, 3:5], rtol=1e-6, atol=1e-5)
+        assert np.all(ga[j, ~m] == 0)
