@@ -366,6 +366,8 @@ int nid_destroy(nid_ctx* c) {
   if (c->h_poses_ring) cudaFreeHost(c->h_poses_ring);
   if (c->h_job_pair_ring) cudaFreeHost(c->h_job_pair_ring);
   if (c->h_aux_pose) cudaFreeHost(c->h_aux_pose);
+  if (c->h_lm_lists) cudaFreeHost(c->h_lm_lists);
+  if (c->d_lm_lists) cudaFree(c->d_lm_lists);
   for (int i = 0; i < NID_STAGE_RING; i++) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->h_arena) cudaFreeHost(c->h_arena);
@@ -724,6 +726,7 @@ struct LM {
   int phase = 0;  // 0 need jac, 1 need trial, 2 done
   int jac_evals = 0, cost_evals = 0;
   int pair = 0;
+  bool slot_holds_est = false;  // the problem's job slot holds the evaluation (histograms, err, tables) of `est`
 };
 
 void lm_start_trial(LM& s) {
@@ -779,6 +782,7 @@ static void lm_absorb(nid_ctx* c, LM& s, const double* g, int n, int max_iters) 
     s.lambda *= s.ni;
     s.ni *= 2;
     s.est = s.backup;  // pop
+    s.slot_holds_est = false;
   }
   s.rho = rho;
   s.qmax++;
@@ -805,6 +809,15 @@ static void lm_absorb(nid_ctx* c, LM& s, const double* g, int n, int max_iters) 
 // Lock-step LM over n problems. The problems are cut into two halves that ping-pong: while the device evaluates the
 // jobs of one half (its own stream and its own range of job slots), the host absorbs the results of the other half,
 // solves the 6x6 systems and stages the next poses. Each problem sees exactly the schedule of a solo solve.
+//
+// Every problem keeps ONE job slot for the whole solve, and every round hands the kernels two lists of slots: list 1
+// gets pass 1 + assembly (histograms, entropies, err, chi2 and the scaled log tables), list 2 gets pass 2 + the
+// Gauss-Newton block. A trial pose is on list 1 only. A cost+Jacobian job is on list 2 and -- this is the point --
+// on list 1 only when its slot does not already hold the evaluation of that very pose: after an accepted trial the
+// next outer iteration linearises at the pose the trial was evaluated at (optimization_algorithm_levenberg.cpp:173-199
+// then :98), and the sorted kernels are deterministic, so the histograms, err and tables in the slot are bit for bit
+// what a recomputation would produce. The reference evaluates them again (CudaComputeH(true) repeats the cost half);
+// skipping that repeats nothing observable and saves a third of the device work of a solve (option "lm_reuse").
 int nid_solve_jobs(nid_ctx* c, int n, const int* job_pair, double* poses7, int max_iters, double delta, int* stats) {
   if (!c || n < 1 || n > c->max_jobs || !poses7) { set_error("bad argument"); return NID_ERR_ARG; }
   CU(cudaSetDevice(c->device), "cudaSetDevice");
@@ -820,50 +833,109 @@ int nid_solve_jobs(nid_ctx* c, int n, const int* job_pair, double* poses7, int m
   }
   OKR(ensure_job_buffers(c));
   c->staged_jobs = 0;  // the solver rewrites the staged poses and job table
+  const bool sorted = use_sorted(c);
+  const bool reuse = sorted && c->opt_lm_reuse;
   // (the natural-order kernels size their per-job partial buffers by the job count of a launch: one range there)
-  const int nh = (n >= 8 && use_sorted(c)) ? 2 : 1;
+  const int nh = (n >= 8 && sorted) ? 2 : 1;
   if (nh == 2 && !c->stream2) {
     CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking), "cudaStreamCreate (LM)");
   }
+  if (!c->h_lm_lists) {
+    CU(cudaMallocHost((void**)&c->h_lm_lists, sizeof(int) * 2 * (size_t)c->max_jobs), "pinned LM lists");
+    OKR(dalloc(&c->d_lm_lists, 2 * (size_t)c->max_jobs, "LM lists"));
+  }
   CU(cudaStreamSynchronize(c->stream), "sync before LM");
-  struct Half { int lo, hi, base, na; std::vector<int> order; cudaStream_t stream; };
+  // slot of problem j = j; half h owns the slots [lo, hi) and the list storage [2 lo, 2 hi): list 1 then list 2
+  struct Half { int lo, hi, n1, n2, na; cudaStream_t stream; };
   Half H[2];
-  H[0] = {0, nh == 2 ? n / 2 : n, 0, 0, {}, c->stream};
-  H[1] = {n / 2, n, n / 2, 0, {}, c->stream2};
+  H[0] = {0, nh == 2 ? n / 2 : n, 0, 0, 0, c->stream};
+  H[1] = {n / 2, n, 0, 0, 0, c->stream2};
   cudaStream_t const main_stream = c->stream;
+  for (int j = 0; j < n; j++) c->h_job_pair[j] = st[j].pair;
+  CU(cudaMemcpyAsync(c->job_pair, c->h_job_pair, sizeof(int) * n, cudaMemcpyHostToDevice, main_stream), "H2D job_pair");
+  CU(cudaStreamSynchronize(main_stream), "sync job_pair");
   int rc = NID_OK;
-  // stage and launch the jobs of half h: first every problem that needs cost+Jacobian, then every trial pose
   auto issue = [&](Half& h) -> int {
-    h.order.clear();
-    int nj = 0;
-    for (int j = h.lo; j < h.hi; j++) if (st[j].phase == 0) { h.order.push_back(j); nj++; }
-    for (int j = h.lo; j < h.hi; j++) if (st[j].phase == 1) h.order.push_back(j);
-    h.na = (int)h.order.size();
-    if (h.na == 0) return NID_OK;
-    for (int k = 0; k < h.na; k++) {
-      nidhost::pose_to_mat16(st[h.order[k]].est, c->h_poses + 16 * (size_t)(h.base + k));
-      c->h_job_pair[h.base + k] = st[h.order[k]].pair;
+    int* l1 = c->h_lm_lists + 2 * (size_t)h.lo;
+    int* l2 = l1 + (h.hi - h.lo);
+    h.n1 = h.n2 = h.na = 0;
+    for (int j = h.lo; j < h.hi; j++) {
+      LM& s = st[j];
+      if (s.phase == 2) continue;
+      h.na++;
+      nidhost::pose_to_mat16(s.est, c->h_poses + 16 * (size_t)j);
+      if (s.phase == 0) {
+        l2[h.n2++] = j;
+        if (!(reuse && s.slot_holds_est)) l1[h.n1++] = j;
+      } else {
+        l1[h.n1++] = j;
+      }
+      s.slot_holds_est = true;  // after this round the slot holds the evaluation of s.est (a rejection resets it)
     }
-    CU(cudaMemcpyAsync(c->poses + 16 * (size_t)h.base, c->h_poses + 16 * (size_t)h.base, sizeof(double) * 16 * h.na,
-                       cudaMemcpyHostToDevice, h.stream), "H2D poses");
-    CU(cudaMemcpyAsync(c->job_pair + h.base, c->h_job_pair + h.base, sizeof(int) * h.na, cudaMemcpyHostToDevice, h.stream),
-       "H2D job_pair");
+    if (h.na == 0) return NID_OK;
+    const int cnt = h.hi - h.lo;
+    CU(cudaMemcpyAsync(c->poses + 16 * (size_t)h.lo, c->h_poses + 16 * (size_t)h.lo, sizeof(double) * 16 * cnt, cudaMemcpyHostToDevice, h.stream),
+       "H2D poses");
+    int* d1 = c->d_lm_lists + 2 * (size_t)h.lo;
+    int* d2 = d1 + cnt;
+    CU(cudaMemcpyAsync(d1, l1, sizeof(int) * 2 * cnt, cudaMemcpyHostToDevice, h.stream), "H2D job lists");
     c->stream = h.stream;  // the launchers issue on the context's current stream
-    const int r = launch_eval_mixed(c, h.base, nj, h.na - nj, delta);
+    int r = NID_OK;
+    if (sorted) {
+      if (h.n1 > 0) r = launch_sorted_pass1(c, d1, l1, 0, h.n1, 1);
+      if (r == NID_OK && h.n2 > 0) r = launch_sorted_pass2(c, d2, l2, 0, h.n2);
+      if (r == NID_OK && h.n2 > 0) r = launch_gn_list(c, d2, 0, h.n2, delta, 1);
+      if (r == NID_OK && h.n1 > 0) r = launch_gn_list(c, d1, 0, h.n1, delta, 0);  // chi2 of the trial poses (and, harmlessly, again of full jobs)
+    } else {
+      // natural-order kernels: contiguous ranges, everything recomputed -- jobs are compacted into the slots [lo, lo + na)
+      r = NID_ERR_STATE;
+    }
     c->stream = main_stream;
     if (r != NID_OK) return r;
-    CU(cudaMemcpyAsync(c->h_out + 44 * (size_t)h.base, c->gn + 44 * (size_t)h.base, sizeof(double) * 44 * h.na,
-                       cudaMemcpyDeviceToHost, h.stream), "D2H gn");
+    CU(cudaMemcpyAsync(c->h_out + 44 * (size_t)h.lo, c->gn + 44 * (size_t)h.lo, sizeof(double) * 44 * cnt, cudaMemcpyDeviceToHost, h.stream),
+       "D2H gn");
     return NID_OK;
   };
-  for (int i = 0; i < nh && rc == NID_OK; i++) rc = issue(H[i]);
-  while (rc == NID_OK && (H[0].na > 0 || (nh == 2 && H[1].na > 0))) {
-    for (int i = 0; i < nh && rc == NID_OK; i++) {
-      Half& h = H[i];
-      if (h.na == 0) continue;
+  // natural-order path: the round-1 scheme (compacted contiguous ranges, full evaluations)
+  std::vector<int> order;
+  auto issue_natural = [&](Half& h) -> int {
+    order.clear();
+    int nj = 0;
+    for (int j = h.lo; j < h.hi; j++) if (st[j].phase == 0) { order.push_back(j); nj++; }
+    for (int j = h.lo; j < h.hi; j++) if (st[j].phase == 1) order.push_back(j);
+    h.na = (int)order.size();
+    if (h.na == 0) return NID_OK;
+    for (int k = 0; k < h.na; k++) {
+      nidhost::pose_to_mat16(st[order[k]].est, c->h_poses + 16 * (size_t)k);
+      c->h_job_pair[k] = st[order[k]].pair;
+    }
+    CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16 * h.na, cudaMemcpyHostToDevice, h.stream), "H2D poses");
+    CU(cudaMemcpyAsync(c->job_pair, c->h_job_pair, sizeof(int) * h.na, cudaMemcpyHostToDevice, h.stream), "H2D job_pair");
+    const int r = launch_eval_mixed(c, 0, nj, h.na - nj, delta);
+    if (r != NID_OK) return r;
+    CU(cudaMemcpyAsync(c->h_out, c->gn, sizeof(double) * 44 * h.na, cudaMemcpyDeviceToHost, h.stream), "D2H gn");
+    return NID_OK;
+  };
+  if (!sorted) {
+    Half& h = H[0];
+    rc = issue_natural(h);
+    while (rc == NID_OK && h.na > 0) {
       if (cudaStreamSynchronize(h.stream) != cudaSuccess) { rc = check_cuda(cudaGetLastError(), "sync lm"); break; }
-      for (int k = 0; k < h.na; k++) lm_absorb(c, st[h.order[k]], c->h_out + 44 * (size_t)(h.base + k), n, max_iters);
-      rc = issue(h);
+      const std::vector<int> done = order;
+      for (int k = 0; k < (int)done.size(); k++) lm_absorb(c, st[done[k]], c->h_out + 44 * (size_t)k, n, max_iters);
+      rc = issue_natural(h);
+    }
+  } else {
+    for (int i = 0; i < nh && rc == NID_OK; i++) rc = issue(H[i]);
+    while (rc == NID_OK && (H[0].na > 0 || (nh == 2 && H[1].na > 0))) {
+      for (int i = 0; i < nh && rc == NID_OK; i++) {
+        Half& h = H[i];
+        if (h.na == 0) continue;
+        if (cudaStreamSynchronize(h.stream) != cudaSuccess) { rc = check_cuda(cudaGetLastError(), "sync lm"); break; }
+        for (int j = h.lo; j < h.hi; j++)
+          if (st[j].phase != 2) lm_absorb(c, st[j], c->h_out + 44 * (size_t)j, n, max_iters);
+        rc = issue(h);
+      }
     }
   }
   c->stream = main_stream;
@@ -1028,6 +1100,7 @@ int nid_set_option(nid_ctx* c, const char* key, int value) {
     return NID_OK;
   }
   if (!strcmp(key, "keep_hist")) { c->opt_keep_hist = value; return NID_OK; }
+  if (!strcmp(key, "lm_reuse")) { c->opt_lm_reuse = value ? 1 : 0; return NID_OK; }
   if (!strcmp(key, "task_px")) {
     if (value < 16 || value > NID_TASK_PX_MAX || (value & 3)) { set_error("task_px must be a multiple of 4 in [16, 256]"); return NID_ERR_ARG; }
     if (value != c->task_px) {

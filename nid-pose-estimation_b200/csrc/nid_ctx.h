@@ -18,7 +18,8 @@ namespace nid {
 // Everything the evaluation kernels need; passed by value (fits the 4 KB parameter space easily).
 struct EvalParams {
   int rows, cols, cell, bins, rb, cb, N, ncell;  // ncell = cell*cell
-  int job0;        // first job handled by this launch
+  int job0;        // first job handled by this launch (index into job_list when that is set)
+  const int* job_list;  // optional indirection: the i-th job of the launch is job_list[job0 + i] (LM driver: fixed slots)
   int S;           // strips per cell (CTAs per cell and job)
   int strip_rows;  // rows of a cell handled by one strip
   int hist_stride; // bins*bins + bins
@@ -182,6 +183,10 @@ struct nid_ctx {
   double* aux_pose = nullptr;     // device [16]
   double* h_out = nullptr;     // [max_jobs][ncell*8 + 44]
   int opt_force_strips = 0;
+  // LM driver: per half-batch job lists (pinned mirror + device copy), [2 halves][2 lists][max_jobs]
+  int* h_lm_lists = nullptr;
+  int* d_lm_lists = nullptr;
+  int opt_lm_reuse = 1;        // a cost+Jacobian job at the pose of the accepted trial reuses that trial's histograms and tables
   double* lm_trace = nullptr;  // set by nid_solve for the duration of one call
   int lm_trace_cap = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -192,6 +197,8 @@ struct nid_ctx {
 };
 
 namespace nid {
+// the i-th job of a launch
+__host__ __device__ inline int job_at(const EvalParams& p, int i) { return p.job_list ? p.job_list[p.job0 + i] : p.job0 + i; }
 void set_error(const std::string& s);
 int check_cuda(cudaError_t e, const char* what);
 EvalParams make_params(nid_ctx* c, int n_jobs);
@@ -222,6 +229,10 @@ int launch_layout_and_scatter(nid_ctx* c, int pair0, int n);
 int launch_pack(nid_ctx* c, int pair0, int n);
 int launch_pack_k1(nid_ctx* c, int pair, unsigned short* d_out);
 int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int want_jac);
+// the two halves of an evaluation on explicit job lists (d_list / h_list: device and host copies, entries [first, first + n))
+int launch_sorted_pass1(nid_ctx* c, const int* d_list, const int* h_list, int first, int n, int tables);
+int launch_sorted_pass2(nid_ctx* c, const int* d_list, const int* h_list, int first, int n);
+int launch_gn_list(nid_ctx* c, const int* d_list, int first, int n, double delta, int want_jac);
 int launch_href(nid_ctx* c, int pair0, int n);
 
 // kernel launchers (nid_kernels.cu)

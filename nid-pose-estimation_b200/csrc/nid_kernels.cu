@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) k_hist(EvalParams p) {
   const int B = p.bins;
   double* Pj = sm;           // [B*B]
   double* Pt = sm + B * B;   // [B]
-  const int strip = blockIdx.x, c = blockIdx.y, job = blockIdx.z + p.job0;
+  const int strip = blockIdx.x, c = blockIdx.y, job = job_at(p, blockIdx.z);
   const int pair = p.job_pair[job];
   double* out = p.part + (((size_t)job * p.ncell + c) * p.S + strip) * p.hist_stride;
   if (p.n_c[pair * p.ncell + c] < NID_MIN_CELL_POINTS) return;
@@ -297,7 +297,7 @@ __device__ __forceinline__ void merge_entropy(const EvalParams& p, int job, int 
 __global__ void __launch_bounds__(256) k_entropy(EvalParams p) {
   extern __shared__ double sm[];
   __shared__ double scratch[8];
-  const int c = blockIdx.x, job = blockIdx.y + p.job0;
+  const int c = blockIdx.x, job = job_at(p, blockIdx.y);
   const int pair = p.job_pair[job];
   const int nc = p.n_c[pair * p.ncell + c];
   const size_t o = (size_t)job * p.ncell + c;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256) k_jac(EvalParams p) {
   __shared__ double scratch[8];
   __shared__ double red[8][6];
   const int B = p.bins;
-  const int strip = blockIdx.x, c = blockIdx.y, job = blockIdx.z + p.job0;
+  const int strip = blockIdx.x, c = blockIdx.y, job = job_at(p, blockIdx.z);
   const int pair = p.job_pair[job];
   const int nc = p.n_c[pair * p.ncell + c];
   const size_t o = (size_t)job * p.ncell + c;
@@ -437,10 +437,10 @@ __global__ void k_jac_final(EvalParams p, int n_jobs) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int total = n_jobs * p.ncell * 6;
   if (idx >= total) return;
-  idx += p.job0 * p.ncell * 6;
   int k = idx % 6;
-  size_t o = idx / 6;
-  int job = (int)(o / p.ncell), c = (int)(o % p.ncell);
+  const int job = job_at(p, (idx / 6) / p.ncell), c = (idx / 6) % p.ncell;
+  size_t o = (size_t)job * p.ncell + c;
+  idx = (int)(o * 6 + k);
   int pair = p.job_pair[job];
   if (p.n_c[pair * p.ncell + c] < NID_MIN_CELL_POINTS) { p.der[idx] = nan(""); return; }
   double t = 0.0;
@@ -454,8 +454,8 @@ __global__ void k_jac_final(EvalParams p, int n_jobs) {
 __global__ void k_gn(EvalParams p, int n_jobs, int want_jac) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_jobs * 44) return;
-  idx += p.job0 * 44;
-  int job = idx / 44, ent = idx % 44;
+  const int job = job_at(p, idx / 44), ent = idx % 44;
+  idx = job * 44 + ent;
   if (!want_jac && ent >= 1 && ent <= 42) return;
   double acc = 0.0;
   const double* e = p.err + (size_t)job * p.ncell;
@@ -746,6 +746,17 @@ int launch_eval_mixed(nid_ctx* c, int base, int nj, int nt, double delta) {
     k_gn<<<(nt * 44 + 127) / 128, 128, 0, c->stream>>>(q, nt, 0);
     NID_LAUNCH_CHECK(c, "k_gn(chi2)");
   }
+  return NID_OK;
+}
+
+int launch_gn_list(nid_ctx* c, const int* d_list, int first, int n, double delta, int want_jac) {
+  EvalParams p = make_params(c, n);
+  p.huber_delta = delta;
+  p.huber_dsqr = (double)(float)(delta * delta);  // `float dsqr`, robust_kernel_impl.h:84
+  p.job0 = first;
+  p.job_list = d_list;
+  k_gn<<<(n * 44 + 127) / 128, 128, 0, c->stream>>>(p, n, want_jac);
+  NID_LAUNCH_CHECK(c, want_jac ? "k_gn" : "k_gn(chi2)");
   return NID_OK;
 }
 

@@ -731,7 +731,7 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
   extern __shared__ double sm[];
   const int B = p.bins, NS = B - 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int job = NID_BLK_JOB + p.job0;
+  const int job = job_at(p, NID_BLK_JOB);
   const int pair = p.job_pair[job];
   const double* g = gt.g[NID_BLK_JOB];
   const int slice = NID_BLK_CHUNK * (T >> 5) + warp;
@@ -859,7 +859,7 @@ __device__ __forceinline__ void assemble_body(const EvalParams& p, int want_jac)
   double* hvs = red + NT;  // [NID_NCLS][B] per-class soft histograms
   double* part = hvs + NID_NCLS * B;    // [4][BB] per-span partial sums of P_j
   double* wl = part + 4 * BB;           // [256][4] reference weights (up to 20 bins)
-  const int c = blockIdx.x, job = blockIdx.y + p.job0;
+  const int c = blockIdx.x, job = job_at(p, blockIdx.y);
   const int pair = p.job_pair[job];
   const int nc = p.n_c[pair * p.ncell + c];
   const size_t o = (size_t)job * p.ncell + c;
@@ -1123,7 +1123,7 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   extern __shared__ double sm[];
   const int B = p.bins, NS = B - 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int job = NID_BLK_JOB + p.job0;
+  const int job = job_at(p, NID_BLK_JOB);
   const int pair = p.job_pair[job];
   const double* g = gt.g[NID_BLK_JOB];
   // shared: the lanes' class tables W^v [B][T] | per-warp log tables W|V (prologue only)
@@ -1239,7 +1239,7 @@ __global__ void __launch_bounds__(256) k_jac_final_sorted(EvalParams p, int n_jo
   const int lane = threadIdx.x & 31;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wid >= n_jobs * p.ncell) return;
-  const int job = p.job0 + wid / p.ncell, c = wid % p.ncell;
+  const int job = job_at(p, wid / p.ncell), c = wid % p.ncell;
   const int pair = p.job_pair[job];
   double* der = p.der + ((size_t)job * p.ncell + c) * 6;
   if (p.n_c[pair * p.ncell + c] < NID_MIN_CELL_POINTS) {
@@ -1347,7 +1347,7 @@ k_warp_sample_jobs(const __grid_constant__ EvalParams p, const __grid_constant__
 #else
   const int jb = blockIdx.x, cb_ = blockIdx.y;  // job index fast
 #endif
-  const int job = jb + p.job0;
+  const int job = job_at(p, jb);
   const int pair = p.job_pair[job];
   const double* g = gt.g[jb];
   const int i0 = cb_ * (128 * W) + threadIdx.x;
@@ -1534,10 +1534,11 @@ size_t assemble_smem(const nid_ctx* c) {
 // Host side of the geometry table: job (first + i) -> gt.g[i] from the staged poses (pinned mirror), the pair's
 // T_wc0 and intrinsics. pass1: rows 0 and 1 of M pre-multiplied by fx, fy.
 template <int NG>
-static void fill_geo(const nid_ctx* c, GeoTable<NG>& gt, int first, int n, bool pass1) {
+static void fill_geo(const nid_ctx* c, GeoTable<NG>& gt, int first, int n, bool pass1, const int* h_list = nullptr) {
   for (int i = 0; i < n; i++) {
-    const double* T1 = c->h_poses + 16 * (size_t)(first + i);
-    const int pair = c->h_job_pair[first + i];
+    const int job = h_list ? h_list[first + i] : first + i;
+    const double* T1 = c->h_poses + 16 * (size_t)job;
+    const int pair = c->h_job_pair[job];
     const double* T0 = c->h_Twc0.data() + 16 * (size_t)pair;
     const double* cam = c->h_cam.data() + 4 * (size_t)pair;
     double* g = gt.g[i];
@@ -1558,13 +1559,13 @@ static void fill_geo(const nid_ctx* c, GeoTable<NG>& gt, int first, int n, bool 
 }
 
 template <bool PTS, int NG>
-static void launch_hist_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
+static void launch_hist_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs, const int* h_list) {
   const int T = pick_block(c, ns, n_jobs, NID_HIST_TMAX);
   const size_t sm = hist_sell_smem(c, T);
   for (int s0 = 0; s0 < n_jobs; s0 += NG) {
     const int n = std::min(NG, n_jobs - s0);
     GeoTable<NG> gt;
-    fill_geo(c, gt, job0 + s0, n, true);
+    fill_geo(c, gt, job0 + s0, n, true, h_list);
     EvalParams q = p;
     q.job0 = job0 + s0;
     const dim3 grid = NID_GRID(n, (ns + T / 32 - 1) / (T / 32));
@@ -1578,13 +1579,13 @@ static void launch_hist_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0
   }
 }
 template <bool PTS, int NG>
-static void launch_jac_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
+static void launch_jac_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs, const int* h_list) {
   const int T = pick_block(c, ns, n_jobs, NID_JAC_TMAX);
   const size_t sm = jac_sell_smem(c, T);
   for (int s0 = 0; s0 < n_jobs; s0 += NG) {
     const int n = std::min(NG, n_jobs - s0);
     GeoTable<NG> gt;
-    fill_geo(c, gt, job0 + s0, n, false);
+    fill_geo(c, gt, job0 + s0, n, false, h_list);
     EvalParams q = p;
     q.job0 = job0 + s0;
     const dim3 grid = NID_GRID(n, (ns + T / 32 - 1) / (T / 32));
@@ -1598,47 +1599,68 @@ static void launch_jac_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0,
 }
 #define NID_GEO_SMALL 8
 #define NID_GEO_LARGE 96
-static void launch_hist_w(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
+static void launch_hist_w(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs, const int* h_list) {
   if (c->sell_points) {
-    if (n_jobs <= NID_GEO_SMALL) launch_hist_chunks<true, NID_GEO_SMALL>(c, p, ns, job0, n_jobs);
-    else launch_hist_chunks<true, NID_GEO_LARGE>(c, p, ns, job0, n_jobs);
+    if (n_jobs <= NID_GEO_SMALL) launch_hist_chunks<true, NID_GEO_SMALL>(c, p, ns, job0, n_jobs, h_list);
+    else launch_hist_chunks<true, NID_GEO_LARGE>(c, p, ns, job0, n_jobs, h_list);
   } else {
-    if (n_jobs <= NID_GEO_SMALL) launch_hist_chunks<false, NID_GEO_SMALL>(c, p, ns, job0, n_jobs);
-    else launch_hist_chunks<false, NID_GEO_LARGE>(c, p, ns, job0, n_jobs);
+    if (n_jobs <= NID_GEO_SMALL) launch_hist_chunks<false, NID_GEO_SMALL>(c, p, ns, job0, n_jobs, h_list);
+    else launch_hist_chunks<false, NID_GEO_LARGE>(c, p, ns, job0, n_jobs, h_list);
   }
 }
-static void launch_jac_w(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs) {
+static void launch_jac_w(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs, const int* h_list) {
   if (c->sell_points) {
-    if (n_jobs <= NID_GEO_SMALL) launch_jac_chunks<true, NID_GEO_SMALL>(c, p, ns, job0, n_jobs);
-    else launch_jac_chunks<true, NID_GEO_LARGE>(c, p, ns, job0, n_jobs);
+    if (n_jobs <= NID_GEO_SMALL) launch_jac_chunks<true, NID_GEO_SMALL>(c, p, ns, job0, n_jobs, h_list);
+    else launch_jac_chunks<true, NID_GEO_LARGE>(c, p, ns, job0, n_jobs, h_list);
   } else {
-    if (n_jobs <= NID_GEO_SMALL) launch_jac_chunks<false, NID_GEO_SMALL>(c, p, ns, job0, n_jobs);
-    else launch_jac_chunks<false, NID_GEO_LARGE>(c, p, ns, job0, n_jobs);
+    if (n_jobs <= NID_GEO_SMALL) launch_jac_chunks<false, NID_GEO_SMALL>(c, p, ns, job0, n_jobs, h_list);
+    else launch_jac_chunks<false, NID_GEO_LARGE>(c, p, ns, job0, n_jobs, h_list);
   }
 }
 
-int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int want_jac) {
-  EvalParams p = make_params(c, n_jobs_total);
-  p.job0 = job0;
+// Pass 1 + assembly (histograms, entropies, err; with `tables` also the scaled log tables pass 2 needs) of the n jobs
+// d_list[first .. first + n) (d_list == nullptr: jobs first .. first + n - 1); h_list is the host copy of d_list.
+int launch_sorted_pass1(nid_ctx* c, const int* d_list, const int* h_list, int first, int n, int tables) {
+  EvalParams p = make_params(c, n);
+  p.job0 = first;
+  p.job_list = d_list;
   const int ns = c->max_nslices_prepared;
   ktime_mark(c, 0);
-  launch_hist_w(c, p, ns, job0, n_jobs);
+  launch_hist_w(c, p, ns, first, n, h_list);
   c->launches--;
   NID_LAUNCH_CHECK(c, "k_hist_sell");
   ktime_mark(c, 1);
-  if (assemble_small(c)) k_assemble_small<<<dim3(c->ncell, n_jobs), NID_ASM_SMALL, assemble_smem(c), c->stream>>>(p, want_jac);
-  else k_assemble<<<dim3(c->ncell, n_jobs), NID_ASM_THREADS, assemble_smem(c), c->stream>>>(p, want_jac);
+  if (assemble_small(c)) k_assemble_small<<<dim3(c->ncell, n), NID_ASM_SMALL, assemble_smem(c), c->stream>>>(p, tables);
+  else k_assemble<<<dim3(c->ncell, n), NID_ASM_THREADS, assemble_smem(c), c->stream>>>(p, tables);
   NID_LAUNCH_CHECK(c, "k_assemble");
   ktime_mark(c, 2);
+  return NID_OK;
+}
+
+// Pass 2 + Jacobian tail of the same kind of job list; the jobs' tables must be those of their current poses.
+int launch_sorted_pass2(nid_ctx* c, const int* d_list, const int* h_list, int first, int n) {
+  EvalParams p = make_params(c, n);
+  p.job0 = first;
+  p.job_list = d_list;
+  const int ns = c->max_nslices_prepared;
+  launch_jac_w(c, p, ns, first, n, h_list);
+  c->launches--;
+  NID_LAUNCH_CHECK(c, "k_jac_sell");
+  ktime_mark(c, 3);
+  const int warps = n * c->ncell;
+  k_jac_final_sorted<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(p, n);
+  NID_LAUNCH_CHECK(c, "k_jac_final_sorted");
+  ktime_mark(c, 4);
+  return NID_OK;
+}
+
+int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int want_jac) {
+  (void)n_jobs_total;
+  int r = launch_sorted_pass1(c, nullptr, nullptr, job0, n_jobs, want_jac);
+  if (r != NID_OK) return r;
   if (want_jac) {
-    launch_jac_w(c, p, ns, job0, n_jobs);
-    c->launches--;
-    NID_LAUNCH_CHECK(c, "k_jac_sell");
-    ktime_mark(c, 3);
-    const int warps = n_jobs * c->ncell;
-    k_jac_final_sorted<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(p, n_jobs);
-    NID_LAUNCH_CHECK(c, "k_jac_final_sorted");
-    ktime_mark(c, 4);
+    r = launch_sorted_pass2(c, nullptr, nullptr, job0, n_jobs);
+    if (r != NID_OK) return r;
     const int slot[4] = {0, 3, 1, 2};
     ktime_collect(c, 4, slot);
   } else {

@@ -201,3 +201,37 @@ def test_kernel1_from_raw_u16_depth(nid, orc, make_pair):
         np.testing.assert_allclose(ga[j, m, 0], exp[m, 2], rtol=1e-6, atol=1e-5)
         np.testing.assert_allclose(ga[j, m, 1:3], exp[m, 3:5], rtol=1e-6, atol=1e-5)
         assert np.all(ga[j, ~m] == 0)
+
+
+@pytest.mark.parametrize("cell,bins", [(4, 16), (8, 10)])
+def test_lm_reuse_of_the_accepted_trial_is_bit_identical(nid, orc, make_pair, cell, bins):
+    """nid_solve_jobs linearises at the pose of the accepted trial without recomputing that pose's histograms (option
+    lm_reuse, default on): poses, iteration counts and the LM trace must equal a solve that recomputes everything,
+    bit for bit; solo and batched, and against the oracle's LM run."""
+    pairs = [make_pair(1000 + i, 120, 160) for i in range(9)]
+    n = len(pairs)
+    ctx = nid.Context(120, 160, cell, bins, n_pairs=n, max_jobs=n)
+    pose0 = []
+    for i, p in enumerate(pairs):
+        ctx.set_pair(i, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+        pose0.append(orc.reference_perturbation(p.T_wc1))
+        ctx.prepare(i, orc.se3_to_mat16(pose0[i]))
+    pose0 = np.stack(pose0)
+    jp = np.arange(n, dtype=np.int32)
+    out1, st1 = ctx.solve_jobs(pose0, jp)
+    solo1 = [ctx.solve(i, pose0[i]) for i in range(n)]
+    ctx.set_option("lm_reuse", 0)
+    out0, st0 = ctx.solve_jobs(pose0, jp)
+    solo0 = [ctx.solve(i, pose0[i]) for i in range(n)]
+    assert np.array_equal(out1, out0) and np.array_equal(st1, st0)
+    for i in range(n):
+        assert np.array_equal(solo1[i][0], solo0[i][0]) and np.array_equal(solo1[i][1], solo0[i][1])
+        assert np.array_equal(solo1[i][0], out1[i]) and np.array_equal(solo1[i][2], st1[i])
+    assert st1[:, 2].sum() > st1[:, 1].sum()  # some rejected trials happened (cost evaluations exceed Jacobian ones)
+    P = orc.Problem(pairs[2].im0, pairs[2].depth0, pairs[2].im1, pairs[2].T_wc0, pairs[2].intr, cell, bins, threads=4)
+    P.set_quirks(0, 1)
+    P.prepare(pose0[2])
+    poseo, its, traceo, counts = P.optimize(pose0[2], 10)
+    assert st1[2, 0] == its
+    np.testing.assert_allclose(solo1[2][1][:, 0], traceo[:, 0], rtol=1e-7)
+    assert np.max(np.abs(out1[2] - poseo)) < 1e-7
