@@ -160,10 +160,18 @@ __device__ __forceinline__ void bspline4(double ub, int k, int bins, double w[4]
 
 // ---- fast variants used by the sorted kernels -----------------------------------------------------
 // exact small-integer -> double without the (slow) I2F.F64 path: bits(2^52 + v) - 2^52
+#ifndef NID_U2D_MODE
+#define NID_U2D_MODE 0  // 0: magic constant (one move + one DADD); 1: I2F.F64 (one XU-pipe instruction)
+#endif
+#if NID_U2D_MODE == 1
+__device__ __forceinline__ double u2d(unsigned v) { return __uint2double_rn(v); }
+__device__ __forceinline__ double i2d_small(int v) { return __int2double_rn(v); }
+#else
 __device__ __forceinline__ double u2d(unsigned v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
 __device__ __forceinline__ double i2d_small(int v) {  // |v| < 2^20
   return __hiloint2double(0x43300000, v + 1048576) - (4503599627370496.0 + 1048576.0);
 }
+#endif
 
 // Centre sample and central-difference gradient (types_six_dof_expmap.cpp:434-435 via .h:310-328) from
 // 12 taps instead of 5 x 4: for u,v >= 1 the five bilinear samples share their fractional weights.
