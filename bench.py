@@ -330,10 +330,9 @@ def leg_c4(args, nid, synth, orc, shard, torch, dist, rank, world, local_rank, b
     pairs = [seqs[int(p) // per_scene][int(p) % per_scene] for p in mine]
     gen_s = time.perf_counter() - t0
     keep, dn, an, bn, T, K = pinned_pairs(torch, pairs)
-    rng = np.random.default_rng(4000 + rank)
     pose0 = []
-    for i, p in enumerate(pairs):  # the reference perturbation plus a small seeded offset per pair
-        xi = rng.uniform(-1, 1, size=6) * np.array([1e-3, 1e-3, 1e-3, 2e-3, 2e-3, 2e-3])
+    for gp, p in zip(mine, pairs):  # the reference perturbation plus a small offset seeded by the GLOBAL pair index
+        xi = np.random.default_rng(4000 + int(gp)).uniform(-1, 1, size=6) * np.array([1e-3, 1e-3, 1e-3, 2e-3, 2e-3, 2e-3])
         pose0.append(orc.se3_mul(orc.se3_exp(xi), orc.reference_perturbation(p.T_wc1)))
     pose0 = np.stack(pose0)
     init = np.stack([orc.se3_to_mat16(q) for q in pose0])

@@ -95,7 +95,7 @@ static int dalloc(T** p, size_t n, const char* what) {
 
 // per-job scratch of the active path, allocated on first use / grown when a pair with more tasks is prepared
 int ensure_job_buffers(nid_ctx* c) {
-  const size_t J = c->max_jobs, NC = c->ncell;
+  const size_t J = c->job_cap, NC = c->ncell;
   const size_t hs = (size_t)c->bins * c->bins + c->bins;
   if (c->opt_keep_hist && !c->hist) OKR(dalloc(&c->hist, J * NC * hs, "hist"));
   if (use_sorted(c)) {
@@ -173,8 +173,8 @@ static int stage_jobs(nid_ctx* c, int n_jobs, const int* job_pair, const double*
   const int slot = (c->stage_slot + 1) % NID_STAGE_RING;
   CU(cudaEventSynchronize(c->stage_ev[slot]), "wait for the staging slot");  // (returns at once for an unrecorded event)
   c->stage_slot = slot;
-  c->h_poses = c->h_poses_ring + (size_t)slot * 16 * c->max_jobs;
-  c->h_job_pair = c->h_job_pair_ring + (size_t)slot * c->max_jobs;
+  c->h_poses = c->h_poses_ring + (size_t)slot * 16 * c->job_cap;
+  c->h_job_pair = c->h_job_pair_ring + (size_t)slot * c->job_cap;
   for (int j = 0; j < n_jobs; j++) c->h_job_pair[j] = job_pair ? job_pair[j] : 0;
   memcpy(c->h_poses, poses, sizeof(double) * 16 * n_jobs);
   CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16 * n_jobs, cudaMemcpyHostToDevice, c->stream), "H2D poses");
@@ -229,11 +229,12 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   c->device = device; c->rows = rows; c->cols = cols; c->cell = cell; c->bins = bins; c->degree = degree;
   c->N = rows * cols; c->ncell = cell * cell; c->rb = rows / cell; c->cb = cols / cell;
   c->n_pairs = n_pairs; c->max_jobs = max_jobs;
+  c->job_cap = std::max(max_jobs, NID_MIN_JOB_SLOTS);
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
   c->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
-  const size_t N = c->N, P = n_pairs, J = max_jobs, NC = c->ncell;
+  const size_t N = c->N, P = n_pairs, J = c->job_cap, NC = c->ncell;
   const size_t hs = (size_t)bins * bins + bins;
   OKR(dalloc(&c->pwx, P * N, "pwx")); OKR(dalloc(&c->pwy, P * N, "pwy")); OKR(dalloc(&c->pwz, P * N, "pwz"));
   OKR(dalloc(&c->im0, P * N, "im0")); OKR(dalloc(&c->im1, P * N, "im1")); OKR(dalloc(&c->inb0, P * N, "inb0"));
@@ -806,6 +807,85 @@ static void lm_absorb(nid_ctx* c, LM& s, const double* g, int n, int max_iters) 
   }
 }
 
+// Latency mode of the LM driver (a handful of problems, the reference's own use: one pair per process,
+// NID_pose_estimation.cpp:350). With one job in flight the device is nearly idle and a solve is a chain of ~34
+// dependent rounds (10 linearisations + ~24 trial poses), each a few small kernels and a host round trip. The trial
+// poses of an outer iteration are known in advance: after a rejection the schedule retries with lambda * ni, ni * 2
+// (optimization_algorithm_levenberg.cpp:186-199). So every round evaluates, per problem, the next K trial poses of that
+// sequence at once and completely (histograms, err, chi2 AND Jacobian / Gauss-Newton block); the host then walks the
+// unchanged state machine over the cached results: the first accepted trial ends the iteration and its Gauss-Newton
+// block is already there for the next one. Same decisions, same numbers (the kernels are deterministic), about one
+// round per outer iteration instead of three and a half.
+static int solve_speculative(nid_ctx* c, std::vector<LM>& st, int n, int max_iters, double delta, int K) {
+  struct Cand { nidhost::Pose7 pose; double gn[44]; bool valid; };
+  std::vector<Cand> cache((size_t)n * K);
+  for (auto& q : cache) q.valid = false;
+  if (!c->h_lm_lists) {
+    CU(cudaMallocHost((void**)&c->h_lm_lists, sizeof(int) * 2 * (size_t)c->job_cap), "pinned LM lists");
+    OKR(dalloc(&c->d_lm_lists, 2 * (size_t)c->job_cap, "LM lists"));
+  }
+  CU(cudaStreamSynchronize(c->stream), "sync before LM");
+  auto same_pose = [](const nidhost::Pose7& a, const nidhost::Pose7& b) {
+    return memcmp(a.t, b.t, sizeof(a.t)) == 0 && memcmp(a.q, b.q, sizeof(a.q)) == 0;
+  };
+  for (;;) {
+    // 1. let every problem consume what the cache already holds
+    bool progress = true;
+    while (progress) {
+      progress = false;
+      for (int j = 0; j < n; j++) {
+        LM& s = st[j];
+        if (s.phase == 2) continue;
+        for (int k = 0; k < K; k++) {
+          Cand& q = cache[(size_t)j * K + k];
+          if (q.valid && same_pose(q.pose, s.est)) {
+            lm_absorb(c, s, q.gn, n, max_iters);  // phase 0 reads chi2/H/b, phase 1 reads chi2: both are in the block
+            progress = true;
+            break;
+          }
+        }
+      }
+    }
+    // 2. the next round: per unfinished problem the pose it waits for and the trials that would follow rejections
+    int nj = 0;
+    int* list = c->h_lm_lists;
+    for (int j = 0; j < n; j++) {
+      LM& s = st[j];
+      for (int k = 0; k < K; k++) cache[(size_t)j * K + k].valid = false;
+      if (s.phase == 2) continue;
+      LM sim = s;
+      for (int k = 0; k < K; k++) {
+        const int slot = j * K + k;
+        Cand& q = cache[slot];
+        q.pose = sim.est;
+        q.valid = true;
+        nidhost::pose_to_mat16(sim.est, c->h_poses + 16 * (size_t)slot);
+        c->h_job_pair[slot] = s.pair;
+        list[nj++] = slot;
+        if (sim.phase != 1 || sim.qmax + 1 >= 10) break;  // only trial poses have successors; maxTrials = 10
+        // the trial after a rejection of this one (lm_absorb's else branch, then lm_start_trial)
+        sim.lambda *= sim.ni;
+        sim.ni *= 2;
+        sim.est = sim.backup;
+        sim.qmax++;
+        lm_start_trial(sim);
+      }
+    }
+    if (nj == 0) break;
+    const int nslots = n * K;
+    CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16 * nslots, cudaMemcpyHostToDevice, c->stream), "H2D poses");
+    CU(cudaMemcpyAsync(c->job_pair, c->h_job_pair, sizeof(int) * nslots, cudaMemcpyHostToDevice, c->stream), "H2D job_pair");
+    CU(cudaMemcpyAsync(c->d_lm_lists, list, sizeof(int) * nj, cudaMemcpyHostToDevice, c->stream), "H2D job list");
+    OKR(launch_sorted_pass1(c, c->d_lm_lists, list, 0, nj, 1));
+    OKR(launch_sorted_pass2(c, c->d_lm_lists, list, 0, nj));
+    OKR(launch_gn_list(c, c->d_lm_lists, 0, nj, delta, 1));
+    CU(cudaMemcpyAsync(c->h_out, c->gn, sizeof(double) * 44 * nslots, cudaMemcpyDeviceToHost, c->stream), "D2H gn");
+    CU(cudaStreamSynchronize(c->stream), "sync lm");
+    for (int i = 0; i < nj; i++) memcpy(cache[list[i]].gn, c->h_out + 44 * (size_t)list[i], sizeof(double) * 44);
+  }
+  return NID_OK;
+}
+
 // Lock-step LM over n problems. The problems are cut into two halves that ping-pong: while the device evaluates the
 // jobs of one half (its own stream and its own range of job slots), the host absorbs the results of the other half,
 // solves the 6x6 systems and stages the next poses. Each problem sees exactly the schedule of a solo solve.
@@ -835,14 +915,28 @@ int nid_solve_jobs(nid_ctx* c, int n, const int* job_pair, double* poses7, int m
   c->staged_jobs = 0;  // the solver rewrites the staged poses and job table
   const bool sorted = use_sorted(c);
   const bool reuse = sorted && c->opt_lm_reuse;
+  if (sorted && n <= 4 && c->opt_lm_spec >= 2) {
+    const int K = std::min(c->opt_lm_spec, c->job_cap / n);
+    if (K >= 2) {
+      for (int j = 0; j < n; j++) c->h_job_pair[j] = st[j].pair;
+      int r = solve_speculative(c, st, n, max_iters, delta, K);
+      if (r != NID_OK) return r;
+      for (int j = 0; j < n; j++) {
+        memcpy(poses7 + 7 * j, st[j].est.t, sizeof(double) * 3);
+        memcpy(poses7 + 7 * j + 3, st[j].est.q, sizeof(double) * 4);
+        if (stats) { stats[3 * j] = st[j].it; stats[3 * j + 1] = st[j].jac_evals; stats[3 * j + 2] = st[j].cost_evals; }
+      }
+      return NID_OK;
+    }
+  }
   // (the natural-order kernels size their per-job partial buffers by the job count of a launch: one range there)
   const int nh = (n >= 8 && sorted) ? 2 : 1;
   if (nh == 2 && !c->stream2) {
     CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking), "cudaStreamCreate (LM)");
   }
   if (!c->h_lm_lists) {
-    CU(cudaMallocHost((void**)&c->h_lm_lists, sizeof(int) * 2 * (size_t)c->max_jobs), "pinned LM lists");
-    OKR(dalloc(&c->d_lm_lists, 2 * (size_t)c->max_jobs, "LM lists"));
+    CU(cudaMallocHost((void**)&c->h_lm_lists, sizeof(int) * 2 * (size_t)c->job_cap), "pinned LM lists");
+    OKR(dalloc(&c->d_lm_lists, 2 * (size_t)c->job_cap, "LM lists"));
   }
   CU(cudaStreamSynchronize(c->stream), "sync before LM");
   // slot of problem j = j; half h owns the slots [lo, hi) and the list storage [2 lo, 2 hi): list 1 then list 2
@@ -1101,6 +1195,11 @@ int nid_set_option(nid_ctx* c, const char* key, int value) {
   }
   if (!strcmp(key, "keep_hist")) { c->opt_keep_hist = value; return NID_OK; }
   if (!strcmp(key, "lm_reuse")) { c->opt_lm_reuse = value ? 1 : 0; return NID_OK; }
+  if (!strcmp(key, "lm_speculate")) {
+    if (value < 0 || value > 8) { set_error("lm_speculate must be 0 (off) .. 8 trial poses per round"); return NID_ERR_ARG; }
+    c->opt_lm_spec = value;
+    return NID_OK;
+  }
   if (!strcmp(key, "task_px")) {
     if (value < 16 || value > NID_TASK_PX_MAX || (value & 3)) { set_error("task_px must be a multiple of 4 in [16, 256]"); return NID_ERR_ARG; }
     if (value != c->task_px) {

@@ -11,6 +11,7 @@
 #define NID_SORTED_MIN_BINS 6  /* the two 3x3 end blocks of the basis fold must not overlap */
 #define NID_SORTED_MAX_BINS 40 /* k_assemble keeps 5*B^2 + 257*B doubles in shared memory */
 #define NID_STAGE_RING 4
+#define NID_MIN_JOB_SLOTS 8
 #define NID_TASK_PX_MAX 256 /* upper bound of the pixels per task of the sorted path (option "task_px") */
 
 namespace nid {
@@ -83,6 +84,7 @@ struct nid_ctx {
   int rows = 0, cols = 0, cell = 0, bins = 0, degree = 3;
   int N = 0, ncell = 0, rb = 0, cb = 0;
   int n_pairs = 0, max_jobs = 0;
+  int job_cap = 0;             // job slots actually allocated: max(max_jobs, NID_MIN_JOB_SLOTS) (speculative LM trials need a few)
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   int* chunk_cnt = nullptr;    // [setup_batch][ncell][chunks of 256 px][NID_NCLS] scratch of the regrouping scatter
@@ -186,6 +188,7 @@ struct nid_ctx {
   // LM driver: per half-batch job lists (pinned mirror + device copy), [2 halves][2 lists][max_jobs]
   int* h_lm_lists = nullptr;
   int* d_lm_lists = nullptr;
+  int opt_lm_spec = 4;         // latency mode of nid_solve_jobs (few problems): trial poses evaluated per round and problem
   int opt_lm_reuse = 1;        // a cost+Jacobian job at the pose of the accepted trial reuses that trial's histograms and tables
   double* lm_trace = nullptr;  // set by nid_solve for the duration of one call
   int lm_trace_cap = 0;

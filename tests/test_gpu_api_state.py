@@ -228,6 +228,15 @@ def test_lm_reuse_of_the_accepted_trial_is_bit_identical(nid, orc, make_pair, ce
         assert np.array_equal(solo1[i][0], solo0[i][0]) and np.array_equal(solo1[i][1], solo0[i][1])
         assert np.array_equal(solo1[i][0], out1[i]) and np.array_equal(solo1[i][2], st1[i])
     assert st1[:, 2].sum() > st1[:, 1].sum()  # some rejected trials happened (cost evaluations exceed Jacobian ones)
+    # latency mode (speculative trial poses, default for up to four problems) against the plain state machine
+    ctx.set_option("lm_reuse", 1)
+    ctx.set_option("lm_speculate", 0)
+    for i in (0, 3, 8):
+        pose, trace, st = ctx.solve(i, pose0[i])
+        assert np.array_equal(pose, solo1[i][0]) and np.array_equal(trace, solo1[i][1]) and np.array_equal(st, solo1[i][2])
+    ctx.set_option("lm_speculate", 4)
+    out2, st2 = ctx.solve_jobs(pose0[:2], jp[:2])
+    assert np.array_equal(out2, out1[:2]) and np.array_equal(st2, st1[:2])
     P = orc.Problem(pairs[2].im0, pairs[2].depth0, pairs[2].im1, pairs[2].T_wc0, pairs[2].intr, cell, bins, threads=4)
     P.set_quirks(0, 1)
     P.prepare(pose0[2])
