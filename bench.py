@@ -337,20 +337,37 @@ def leg_c4(args, nid, synth, orc, shard, torch, dist, rank, world, local_rank, b
     pose0 = np.stack(pose0)
     init = np.stack([orc.se3_to_mat16(q) for q in pose0])
     n = len(pairs)
-    chunk = min(n, 128)
-    ctx = nid.Context(ROWS, COLS, CELL, BINS, n_pairs=n, max_jobs=chunk, device=local_rank)
+    chunk = min(n, 128)          # problems per nid_solve_jobs call
+    block = min(n, 256)          # pairs per set-up submission
+    # two contexts ping-pong: while one solves its block of pairs, the other one's block is uploaded and prepared
+    # (set-up runs on its own host thread and its own stream; the ctypes calls release the GIL)
+    ctxs = [nid.Context(ROWS, COLS, CELL, BINS, n_pairs=block, max_jobs=chunk, device=local_rank) for _ in range(2 if n > block else 1)]
+    blocks = [(b0, min(n, b0 + block)) for b0 in range(0, n, block)]
+
+    def setup(k):
+        b0, b1 = blocks[k]
+        cx = ctxs[k % len(ctxs)]
+        cx.set_pairs_u16(0, dn[b0:b1], an[b0:b1], bn[b0:b1], T[b0:b1], K[b0:b1])
+        cx.prepare_pairs(0, init[b0:b1])
 
     def run_once():
-        ctx.set_pairs_u16(0, dn, an, bn, T, K)
-        ctx.prepare_pairs(0, init)
-        t_setup = time.perf_counter()
         rows = np.zeros((n, 10))
-        for c0 in range(0, n, chunk):
-            c1 = min(n, c0 + chunk)
-            out, st = ctx.solve_jobs(pose0[c0:c1], np.arange(c0, c1, dtype=np.int32))
-            rows[c0:c1, :7] = out
-            rows[c0:c1, 7:] = st
-        return rows, t_setup
+        t_first = None
+        with ThreadPoolExecutor(max_workers=1) as ex:
+            fut = ex.submit(setup, 0)
+            for k, (b0, b1) in enumerate(blocks):
+                fut.result()
+                if t_first is None:
+                    t_first = time.perf_counter()
+                if k + 1 < len(blocks):
+                    fut = ex.submit(setup, k + 1)
+                cx = ctxs[k % len(ctxs)]
+                for c0 in range(b0, b1, chunk):
+                    c1 = min(b1, c0 + chunk)
+                    out, st = cx.solve_jobs(pose0[c0:c1], np.arange(c0 - b0, c1 - b0, dtype=np.int32))
+                    rows[c0:c1, :7] = out
+                    rows[c0:c1, 7:] = st
+        return rows, t_first
 
     run_once()  # warm (allocations, first-touch)
     barrier()
@@ -364,10 +381,12 @@ def leg_c4(args, nid, synth, orc, shard, torch, dist, rank, world, local_rank, b
         t = torch.tensor([el, setup_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         el, setup_s = t.tolist()
-    ctx.close()
+    for cx in ctxs:
+        cx.close()
     assert np.all(np.isfinite(table)), "c4: non-finite rows in the gathered table"
     res = {"value": n_total / el, "unit": "pairs/s", "pairs": n_total, "pairs_per_rank": int(n), "seconds": el,
-           "setup_seconds": setup_s, "solve_and_gather_seconds": el - setup_s, "scaling": "strong", "sharding": "block (shard.py)",
+           "first_block_setup_seconds": setup_s, "scaling": "strong", "sharding": "block (shard.py)",
+           "overlap": "two contexts ping-pong: the set-up of the next block of 256 pairs overlaps the solves of the current one",
            "gather": "NCCL all_gather of {pose7, outer_iters, jac_evals, cost_evals} per pair" if world > 1 else "single rank",
            "mean_outer_iters": float(table[:, 7].mean()), "mean_jac_evals": float(table[:, 8].mean()),
            "mean_cost_evals": float(table[:, 9].mean()), "host_generation_seconds_untimed": gen_s,
@@ -488,6 +507,58 @@ def leg_old_gpu(nid, synth, orc, torch):
         out[f"cell{cell}_bins{bins}"] = {"reference_cuda": ref_rate, "ours_batched": ours, "ours_one_call_at_a_time": ours1,
                                          "ratio_batched": ours / ref_rate, "ratio_one_at_a_time": ours1 / ref_rate}
     return out
+
+
+def leg_shim(nid, synth, orc, torch):
+    """The reference-API drop-in path: the exact-signature entry points (Calculate3Dpoint, CudaComputeHref,
+    g2o::CudaComputeH; csrc/ref_shims.cu) driven like NID_pose_estimation.cpp:253-276 and the LM loop drive them,
+    one blocking call at a time with the reference's fp64 host buffers, at the reference's default geometry."""
+    import ctypes as C
+    _dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L = nid.lib()
+    p = synth.make_pair(1000, ROWS, COLS)
+    cell, bins, N = 16, 10, ROWS * COLS
+    d = lambda a: a.ctypes.data_as(_dp)
+    depth = p.depth0.reshape(-1).copy()
+    Twc0, intr = p.T_wc0.copy(), p.intr.copy()
+    points = np.zeros(3 * N)
+    im0 = p.im0.astype(np.float64).reshape(-1).copy()
+    im1 = p.im1.astype(np.float64).reshape(-1).copy()
+    pose0 = orc.reference_perturbation(p.T_wc1)
+    M0 = orc.se3_to_mat16(pose0)
+    t0 = time.perf_counter()
+    L.nid_shim_Calculate3Dpoint(d(depth), d(Twc0), d(points), d(intr), ROWS, COLS)
+    bs_value = np.zeros(4 * N)
+    bs_index = np.zeros(N, dtype=np.int32)
+    bs_counter = np.zeros(cell * cell, dtype=np.int32)
+    Href = np.zeros(cell * cell)
+    L.nid_shim_CudaComputeHref(d(im0), d(points), d(M0), d(intr), bins, 3, cell, ROWS, COLS, d(bs_value),
+                               bs_index.ctypes.data_as(_ip), bs_counter.ctypes.data_as(_ip), d(Href))
+    setup_s = time.perf_counter() - t0
+    rng = np.random.default_rng(9)
+    poses = [orc.se3_to_mat16(orc.se3_mul(orc.se3_exp(rng.uniform(-1, 1, 6) * 2e-3), pose0)) for _ in range(40)]
+    Ht, Hj, der = np.zeros(cell * cell), np.zeros(cell * cell), np.zeros(6 * cell * cell)
+
+    def call(M, jac):
+        Ht[:] = 0
+        Hj[:] = 0
+        L.nid_shim_CudaComputeH(jac, d(im0), d(im1), d(points), bs_counter.ctypes.data_as(_ip), d(bs_value),
+                                bs_index.ctypes.data_as(_ip), d(M), d(intr), bins, 3, cell, ROWS, COLS, d(Href), None, None,
+                                d(Ht), d(Hj), d(der))
+    call(poses[0], 1)
+    t0 = time.perf_counter()
+    for M in poses:
+        call(M, 1)
+    rate_j = len(poses) / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for M in poses:
+        call(M, 0)
+    rate_c = len(poses) / (time.perf_counter() - t0)
+    L.nid_shim_reset()
+    return {"geometry": f"{ROWS}x{COLS}, 16x16 cells, 10 bins (NID_pose_estimation.cpp:26-28)", "cost_jacobian_calls_per_s": rate_j,
+            "cost_only_calls_per_s": rate_c, "setup_ms": 1e3 * setup_s,
+            "call": "g2o::CudaComputeH(calculate_der, ...) with the reference's signature and fp64 host / managed buffers, blocking, one "
+                    "evaluation per call (each call compares the two images with the uploaded copies: 4.9 MB of memcmp)"}
 
 
 def main():
@@ -648,11 +719,16 @@ def main():
             c5, c5_pair, c5_all = leg_c5(args, nid, synth, orc, shard, torch, dist, rank, world, local_rank, barrier)
     except Exception as e:  # noqa: BLE001
         c5 = {"error": repr(e)}
+    shim = None
     if rank == 0 and world == 1 and args.old_gpu:
         try:
             old = leg_old_gpu(nid, synth, orc, torch)
         except Exception as e:  # noqa: BLE001
             old = {"error": repr(e)}
+        try:
+            shim = leg_shim(nid, synth, orc, torch)
+        except Exception as e:  # noqa: BLE001
+            shim = {"error": repr(e)}
 
     if rank == 0:
         evals = args.steps * n_slots * world
@@ -746,6 +822,8 @@ def main():
             line["c5"] = c5
         if old is not None:
             line["old_gpu_path"] = old
+        if shim is not None:
+            line["reference_api_shim"] = shim
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

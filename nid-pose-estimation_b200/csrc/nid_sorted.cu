@@ -972,6 +972,7 @@ __device__ __forceinline__ void assemble_body(const EvalParams& p, int want_jac)
   __shared__ double scratch[NT / 32];
   __shared__ int s_cts[NID_NCLS + 1];
   __shared__ int s_bnd[NT / 4 + 2];
+  __shared__ int s_span[NID_SORTED_MAX_BINS];  // first class of every span (+ end)
   const int B = p.bins, BB = B * B, NS = B - 3;
   double* Pall = sm;                    // [BB + B]
   double* red = sm + BB + B;            // [NT] partial sums of P_t
@@ -993,6 +994,7 @@ __device__ __forceinline__ void assemble_body(const EvalParams& p, int want_jac)
   {
     const int* cts = p.cls_task_start + ((size_t)pair * p.ncell + c) * (NID_NCLS + 1);
     for (int i = threadIdx.x; i <= NID_NCLS; i += blockDim.x) s_cts[i] = cts[i];
+    for (int i = threadIdx.x; i <= NS; i += blockDim.x) s_span[i] = p.span_start[i];
     if (NID_FEW_BINS(B)) for (int i = threadIdx.x; i < 1024; i += blockDim.x) wl[i] = p.lut_w[i];
     __syncthreads();
     // many bins: a thread owns two adjacent bins of a row (one 16-byte load; rows are 16-byte aligned when B is even),
@@ -1063,21 +1065,31 @@ __device__ __forceinline__ void assemble_body(const EvalParams& p, int want_jac)
     }
   }
   __syncthreads();
-  // ---- P_j: item (kk, r, t) sums the classes of span r-kk
-  for (int it = threadIdx.x; it < 4 * BB; it += blockDim.x) {
-    const int kk = it / BB, idx = it % BB;
-    const int r = idx / B, tt = idx % B;
-    const int k = r - kk;
-    double a = 0.0;
-    if (k >= 0 && k < NS) {
-      const int vlo = p.span_start[k], vhi = p.span_start[k + 1];
-      if (NID_FEW_BINS(B)) {
-        for (int v = vlo; v < vhi; v++) a += wl[4 * v + kk] * hvs[v * B + tt];
-      } else {  // many bins: the 8 KB copy of the weight table would cost a resident CTA per SM
-        for (int v = vlo; v < vhi; v++) a += __ldg(p.lut_w + 4 * v + kk) * hvs[v * B + tt];
+  // ---- P_j: item (kk, r, t) sums the classes of span r-kk (in class order: the summation order is part of the result)
+  {
+    const unsigned mdiv = (1048576u + (unsigned)B - 1u) / (unsigned)B;  // idx / B == (idx * mdiv) >> 20 for idx < 2^20 / B
+    for (int kk = 0; kk < 4; kk++)
+      for (int idx = threadIdx.x; idx < BB; idx += blockDim.x) {
+        const int r = (int)(((unsigned)idx * mdiv) >> 20), tt = idx - r * B;
+        const int k = r - kk;
+        double a = 0.0;
+        if (k >= 0 && k < NS) {
+          const int vlo = s_span[k], vhi = s_span[k + 1];
+          const double* ph = hvs + vlo * B + tt;
+          int n = vhi - vlo;
+          if (NID_FEW_BINS(B)) {
+            const double* pw = wl + 4 * vlo + kk;
+            for (; n >= 4; n -= 4, pw += 16, ph += 4 * B) {
+              a = fma(pw[0], ph[0], a); a = fma(pw[4], ph[B], a); a = fma(pw[8], ph[2 * B], a); a = fma(pw[12], ph[3 * B], a);
+            }
+            for (; n > 0; n--, pw += 4, ph += B) a = fma(pw[0], ph[0], a);
+          } else {  // many bins: the 8 KB copy of the weight table would cost a resident CTA per SM
+            const double* pw = p.lut_w + 4 * vlo + kk;
+            for (; n > 0; n--, pw += 4, ph += B) a = fma(__ldg(pw), ph[0], a);
+          }
+        }
+        part[kk * BB + idx] = a;
       }
-    }
-    part[it] = a;
   }
   // ---- P_t: thread (g, tt) sums classes g, g+ng, ... ; groups are then added in order
   {
