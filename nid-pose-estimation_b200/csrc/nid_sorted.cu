@@ -1147,6 +1147,111 @@ __global__ void __launch_bounds__(NID_ASM_SMALL, 2 * NID_ASM_MINB) k_assemble_sm
   assemble_body<NID_ASM_SMALL>(p, want_jac);
 }
 
+// Assembly for small cells (the reference's default 16x16 cells hold ~1200 pixels, i.e. ~130 task rows and at most a
+// handful of pixels per class): one WARP per (cell, job) and no block barrier. Lane t owns bin t of P_t and column t of
+// P_j; the warp streams the cell's task rows in task order, eight in flight, and a row of class v adds
+// w_ref,v[m] * row[t] to P_j[k_r(v)+m][t] (types_six_dof_expmap.cpp:598-601 summed per task instead of per pixel).
+// Same outputs as assemble_body (entropies, err, scaled log tables); the CTA-per-cell version spends its time on the
+// 257-class bookkeeping and six barriers, which only pays off when a cell has thousands of task rows.
+// Fixed per geometry (cells under NID_ASM_SMALL_PX pixels and at most 32 bins), so results never depend on the batch.
+#define NID_ASMW_WARPS 8
+#ifndef NID_ASMW_BATCH
+#define NID_ASMW_BATCH 8  // task rows a lane keeps in flight (16 and 24 cost resident warps: measured slower)
+#endif
+#ifndef NID_ASMW_MINB
+#define NID_ASMW_MINB 4
+#endif
+// Lanes are (g, t) = (lane / B, lane % B): NG = 32 / B sub-groups each stream every NG-th task row of the cell into
+// their own copy of P_j / P_t (rows are B doubles, so one load instruction fetches NG whole rows); the copies are
+// added in sub-group order at the end. Task order within a sub-group and sub-group order are fixed: deterministic.
+__global__ void __launch_bounds__(NID_ASMW_WARPS * 32, NID_ASMW_MINB) k_assemble_warp(EvalParams p, int want_jac, int n_jobs) {
+  extern __shared__ double sm[];  // per warp: NG copies of P_j as [B][B] (+ one row of P_t each)
+  const int B = p.bins, BB = B * B;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int unit = blockIdx.x * NID_ASMW_WARPS + warp;
+  if (unit >= n_jobs * p.ncell) return;
+  const int c = unit % p.ncell, job = job_at(p, unit / p.ncell);
+  const int pair = p.job_pair[job];
+  const int nc = p.n_c[pair * p.ncell + c];
+  const size_t o = (size_t)job * p.ncell + c;
+  if (nc < NID_MIN_CELL_POINTS) {
+    if (lane == 0) { p.ht[o] = nan(""); p.hj[o] = nan(""); p.err[o] = nan(""); }
+    return;
+  }
+  const int NG = 32 / B;                 // sub-groups (1 for more than 16 bins)
+  const int g = lane / B, t = lane - g * B;
+  const bool mine = g < NG;              // lanes beyond NG * B idle
+  const int stride = BB + B;             // one copy: P_j [B][B] | P_t [B]
+  double* cp = sm + (size_t)warp * NG * stride;
+  for (int i = lane; i < NG * stride; i += 32) cp[i] = 0.0;
+  __syncwarp();
+  double* Pj = cp + (mine ? g : 0) * stride + t;  // Pj[r * B]: column t of the sub-group's copy
+  double pt = 0.0;
+  const int t0 = p.cell_task_start[pair * (p.ncell + 1) + c], t1 = p.cell_task_start[pair * (p.ncell + 1) + c + 1];
+  const int2* tk = p.tasks + (size_t)pair * p.max_tasks;
+  const double* G = p.G + (size_t)job * p.g_stride * B + t;
+  for (int tb = t0; tb < t1; tb += NID_ASMW_BATCH * NG) {
+    double x[NID_ASMW_BATCH];
+    int cls[NID_ASMW_BATCH];
+#pragma unroll
+    for (int i = 0; i < NID_ASMW_BATCH; i++) {
+      const int tt = tb + i * NG + g;
+      const bool in = mine && tt < t1;
+      x[i] = in ? NID_ASM_LD(G + (size_t)tt * B) : 0.0;
+      cls[i] = in ? ((tk[tt].y >> 9) & 0x1ff) : 256;
+    }
+#pragma unroll
+    for (int i = 0; i < NID_ASMW_BATCH; i++) {
+      pt += x[i];
+      if (cls[i] < 256) {  // (class 256: valid points without a reference sample count in P_t only)
+        double* q = Pj + __ldg(p.lut_k + cls[i]) * B;
+        const double* w = p.lut_w + 4 * cls[i];
+#pragma unroll
+        for (int m = 0; m < 4; m++) q[m * B] = fma(__ldg(w + m), x[i], q[m * B]);
+      }
+    }
+  }
+  if (mine) cp[g * stride + BB + t] = pt;
+  __syncwarp();
+  // add the copies in sub-group order: lane (r-chunk) ... every lane sums whole entries
+  for (int i = lane; i < stride; i += 32) {
+    double a = cp[i];
+    for (int k = 1; k < NG; k++) a += cp[k * stride + i];
+    cp[i] = a;
+  }
+  __syncwarp();
+  // normalise, entropies (computeH.cu:261-300); the table 1 + log2 P replaces P in place
+  double ej = 0.0, et = 0.0;
+  const double dn = (double)nc;
+  double* hist = p.hist ? p.hist + o * (size_t)(BB + B) : nullptr;
+  for (int i = lane; i < stride; i += 32) {
+    const double q = cp[i] / dn;
+    const double lg = (q < kSigma) ? 0.0 : log2(q);
+    if (i < BB) ej -= q * lg; else et -= q * lg;
+    cp[i] = (q < kSigma) ? 0.0 : 1.0 + lg;
+    if (hist) hist[i] = q;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    ej += __shfl_xor_sync(0xffffffffu, ej, off);
+    et += __shfl_xor_sync(0xffffffffu, et, off);
+  }
+  const double Hj = ej, Ht = et;
+  const double Href = p.href[pair * p.ncell + c];
+  if (lane == 0) {
+    p.ht[o] = Ht; p.hj[o] = Hj;
+    p.err[o] = (2 * Hj - Href - Ht) / Hj;
+  }
+  __syncwarp();
+  if (want_jac) {
+    const double s_over = ((double)(B - 3) / 255.0) / ((double)nc * Hj * Hj);
+    const double coefJ = -s_over * (Ht + Href);
+    const double coefT = s_over * Hj;
+    double* wv = p.wv + o * (size_t)(BB + B);
+    for (int i = lane; i < stride; i += 32) wv[i] = cp[i] * (i < BB ? coefJ : coefT);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Pass 2: per task the partial of  J[a] = sum_i g_i[a] * c_i,  c_i = q0 + f_i (q1 + f_i q2) with the
 // quadratic of the pixel's (class, span); c_i = 0 at ub == 0 exactly (the reference's BsplineDer quirk).
@@ -1681,9 +1786,16 @@ static int pick_block(const nid_ctx* c, int ns, int n_jobs, int tmax) {
 }
 // cells of fewer than 4096 pixels take the 128-thread assembly
 #ifndef NID_ASM_SMALL_PX
-#define NID_ASM_SMALL_PX 4096
+#define NID_ASM_SMALL_PX 8192
 #endif
 static bool assemble_small(const nid_ctx* c) { return (long long)c->rb * c->cb < NID_ASM_SMALL_PX; }
+#ifndef NID_ASM_WARP
+#define NID_ASM_WARP 1
+#endif
+static bool assemble_warp(const nid_ctx* c) { return NID_ASM_WARP && assemble_small(c) && c->bins <= 32; }
+static size_t assemble_warp_smem(const nid_ctx* c) {
+  return sizeof(double) * (size_t)NID_ASMW_WARPS * (32 / c->bins) * ((size_t)c->bins * c->bins + c->bins);
+}
 size_t assemble_smem(const nid_ctx* c) {
   return sizeof(double) * ((size_t)5 * c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins + (NID_FEW_BINS(c->bins) ? 1024 : 0));
 }
@@ -1787,7 +1899,10 @@ int launch_sorted_pass1(nid_ctx* c, const int* d_list, const int* h_list, int fi
   c->launches--;
   NID_LAUNCH_CHECK(c, "k_hist_sell");
   ktime_mark(c, 1);
-  if (assemble_small(c)) k_assemble_small<<<dim3(c->ncell, n), NID_ASM_SMALL, assemble_smem(c), c->stream>>>(p, tables);
+  if (assemble_warp(c)) {
+    const int units = c->ncell * n;
+    k_assemble_warp<<<(units + NID_ASMW_WARPS - 1) / NID_ASMW_WARPS, NID_ASMW_WARPS * 32, assemble_warp_smem(c), c->stream>>>(p, tables, n);
+  } else if (assemble_small(c)) k_assemble_small<<<dim3(c->ncell, n), NID_ASM_SMALL, assemble_smem(c), c->stream>>>(p, tables);
   else k_assemble<<<dim3(c->ncell, n), NID_ASM_THREADS, assemble_smem(c), c->stream>>>(p, tables);
   NID_LAUNCH_CHECK(c, "k_assemble");
   ktime_mark(c, 2);
@@ -1912,6 +2027,7 @@ int sorted_init(nid_ctx* c) {
 #undef NID_SMEM_ATTR_PX
   NID_SMEM_ATTR(k_assemble, assemble_smem(c));
   NID_SMEM_ATTR(k_assemble_small, assemble_smem(c));
+  if (c->bins <= 32) { NID_SMEM_ATTR(k_assemble_warp, assemble_warp_smem(c)); }
 #undef NID_SMEM_ATTR
   return NID_OK;
 }

@@ -1,0 +1,6 @@
+#!/bin/bash
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+for v in base asmw0; do
+  if [ "$v" = base ]; then unset NID_B200_LIB; else export NID_B200_LIB=$PWD/build/libvar_$v.so; fi
+  for g in "480 640 16 10" "480 640 8 10" "480 640 8 8" "240 320 4 16"; do echo "== $v: $(timeout 300 python tools/time_config.py $g 96 10 2>&1 | grep 'sorted want_jac=1')"; done
+done

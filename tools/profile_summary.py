@@ -25,7 +25,7 @@ for r in rows:
 step = {k: sum(v) / len(v) for k, v in agg.items() if k[0] in EVAL}
 tot = sum(step.values())
 with open(os.path.join(pr, f"{tag}_launches.txt"), "w") as f:
-    f.write(f"ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --pairs {pairs} --steps 3 --warmup 3 --cpu-budget 0.2 --solves 0\n")
+    f.write(f"ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --pairs {pairs} --steps 3 --warmup 3 --cpu-budget 0.2 --solves 0 --c4-pairs 0 --c5 0 --old-gpu 0   (tools/gpu_prof.sh)\n")
     f.write("per-launch times are cold-cache and serialised under ncu: the SHARE of the step is what bench.py's live CUDA-event timing must agree with\n")
     f.write(f"{'kernel':24s} {'grid':16s} {'block':14s} {'launches':>8s} {'avg us':>10s} {'share of one evaluation step':>30s}\n")
     for k, v in agg.items():
@@ -57,7 +57,7 @@ keys = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
 traffic = {}
 pipes = {}
 with open(os.path.join(pr, f"{tag}_ncu_full.txt"), "w") as f:
-    f.write(f"ncu --set full --clock-control none --import-source on -k regex:'k_hist_sell|k_jac_sell|k_assemble|k_jac_final' -s 8 -c 4 python bench.py --pairs {pairs} --steps 3 --warmup 3\n")
+    f.write(f"ncu --set full --clock-control none --import-source on -k regex:'k_hist_sell|k_jac_sell|k_assemble|k_jac_final' -s 8 -c 4 python bench.py --pairs {pairs} --steps 3 --warmup 3 ...   (tools/gpu_prof.sh)\n")
     f.write(f"one launch = {pairs} cost+Jacobian evaluations of 640x480 pairs (4x4 cells, 16 bins)\n")
     for r in rr[2:]:
         name = short(r[hdr.index('Kernel Name')])
@@ -77,8 +77,31 @@ with open(os.path.join(pr, f"{tag}_ncu_full.txt"), "w") as f:
                        "issue_active_pct": val('smsp__issue_active.avg.pct_of_peak_sustained_active'),
                        "warps_active_pct": val('sm__warps_active.avg.pct_of_peak_sustained_active'),
                        "registers_per_thread": val('launch__registers_per_thread')}
-json.dump({"source": f"profiles/{tag}_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch / {pairs} evaluations)",
-           "dram_bytes_per_eval": traffic, "pipes": pipes}, open(os.path.join(pr, "traffic.json"), "w"), indent=1)
+# fp64 warp instructions per evaluation: executed counts of the D* opcodes on the source page of the same capture
+fp64 = {}
+for name in EVAL:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{name}"], capture_output=True, text=True).stdout
+    rows_s = list(csv.reader(out.splitlines()))
+    try:
+        h = next(r for r in rows_s if r and r[0] == "Address")
+    except StopIteration:
+        continue
+    data = [r for r in rows_s if len(r) == len(h) and r[0] != "Address"]
+    first = data[0][0]
+    for i in range(1, len(data)):
+        if data[i][0] == first:
+            data = data[:i]  # the dump concatenates the captured launches: keep the first
+            break
+    iS, iI = h.index("Source"), h.index("Instructions Executed")
+    tot = 0
+    for r in data:
+        txt = r[iS].strip()
+        op = (txt.split()[1] if txt.startswith("@") else txt.split()[0]) if txt else ""
+        if op[:1] == "D" and op.split(".")[0] in ("DFMA", "DADD", "DMUL", "DSETP", "DMNMX"):
+            tot += int(r[iI])
+    fp64[name] = tot / pairs
+json.dump({"source": f"profiles/{tag}_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch / {pairs} evaluations; fp64 = executed DFMA/DADD/DMUL/DSETP warp instructions, ncu source page)",
+           "dram_bytes_per_eval": traffic, "pipes": pipes, "fp64_warp_inst_per_eval": fp64}, open(os.path.join(pr, "traffic.json"), "w"), indent=1)
 lines = []
 for fn in (f"{tag}_bench_ref.json", f"{tag}_bench.json"):
     p = os.path.join(go, fn)
