@@ -92,6 +92,7 @@ __device__ __forceinline__ int sell_key(const EvalParams& p, size_t base, int c,
   col = (c % p.cell) * p.cb + t % p.cb;
   const size_t i = base + (size_t)row * p.cols + col;
   if (isnan(p.pwx[i])) return -1;
+  if (p.span_mode) return p.inb0[i] ? __ldg(p.lut_k + p.im0[i]) : p.bins - 3;  // reference span; NS = no reference sample
   return p.inb0[i] ? (int)p.im0[i] : 256;
 }
 
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(256) k_scatter_sell(EvalParams p, int pair0, i
     if (PTS) { sd0[dst] = p.pwx[i]; sd1[dst] = p.pwy[i]; sd2[dst] = p.pwz[i]; }
     else sd0[dst] = depth[(size_t)row * p.cols + col];
     sid[dst] = ((unsigned)row << 16) | (unsigned)col;
+    if (p.span_mode) p.sv[dst] = p.im0[i];
   }
 }
 
@@ -193,12 +195,15 @@ struct CellLayoutSm {
   int T, F, S, SF, slots;
 };
 
-__device__ __forceinline__ void cell_layout(const unsigned* __restrict__ cnt, int L, CellLayoutSm& s) {
+// span: lut_k (reference span of every intensity) when the tasks are per span, else nullptr; NS = bins - 3
+__device__ __forceinline__ void cell_layout(const unsigned* __restrict__ cnt, int L, CellLayoutSm& s,
+                                            const int* __restrict__ span = nullptr, int NS = 0) {
   const int v = threadIdx.x, lane = v & 31, w = v >> 5;
   constexpr int NW = NID_LAYOUT_THREADS / 32;
-  const int c = v < NID_NCLS ? (int)cnt[v] : 0;
+  int c = v < NID_NCLS ? (int)cnt[v] : 0;
+  const int c_px = c;  // pixels of reference intensity v (n_c below counts these whatever the task kind)
   {  // n_c = pixels with a reference sample; cells under 300 get no tasks (computeH.cu:271)
-    int n = v < 256 ? c : 0;
+    int n = v < 256 ? c_px : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     if (lane == 0) s.wsum[0][w] = n;
@@ -208,6 +213,15 @@ __device__ __forceinline__ void cell_layout(const unsigned* __restrict__ cnt, in
 #pragma unroll
   for (int i = 0; i < NW; i++) n_c += s.wsum[0][i];
   __syncthreads();
+  if (span) {  // "class" k = reference span k (k < NS), NS = pixels without a reference sample; integer sums: any order
+    if (v < NID_NCLS) s.r[v] = 0;
+    __syncthreads();
+    if (v < 256) { if (c) atomicAdd(&s.r[span[v]], c); }
+    else if (v == 256) s.r[NS] = c;  // (nothing else lands on index NS: span[v] < NS)
+    __syncthreads();
+    c = v < NID_NCLS ? s.r[v] : 0;
+    __syncthreads();
+  }
   const int cc = n_c >= NID_MIN_CELL_POINTS ? c : 0;
   const int nf = cc / L, r = cc - nf * L, nt = nf + (r > 0 ? 1 : 0);
   int a = nt, b = nf;  // inclusive scans over the classes
@@ -252,10 +266,10 @@ __device__ __forceinline__ void cell_layout(const unsigned* __restrict__ cnt, in
 
 // totals per (pair, cell): tasks, slices, pixel slots
 __global__ void __launch_bounds__(NID_LAYOUT_THREADS) k_layout_totals(int pair0, int ncell, int L, const unsigned* __restrict__ cnt,
-                                                                      int* __restrict__ tot) {
+                                                                      int* __restrict__ tot, const int* __restrict__ span, int NS) {
   __shared__ CellLayoutSm s;
   const int c = blockIdx.x, pair = pair0 + blockIdx.y;
-  cell_layout(cnt + ((size_t)pair * ncell + c) * NID_NCLS, L, s);
+  cell_layout(cnt + ((size_t)pair * ncell + c) * NID_NCLS, L, s, span, NS);
   if (threadIdx.x == 0) {
     int* o = tot + ((size_t)blockIdx.y * ncell + c) * 3;
     o[0] = s.T; o[1] = s.S; o[2] = s.slots;
@@ -326,7 +340,7 @@ __global__ void __launch_bounds__(NID_LAYOUT_THREADS) k_layout_write(EvalParams 
                                                                      int* __restrict__ cls_task_start) {
   __shared__ CellLayoutSm s;
   const int c = blockIdx.x, pair = pair0 + blockIdx.y;
-  cell_layout(cnt + ((size_t)pair * p.ncell + c) * NID_NCLS, L, s);
+  cell_layout(cnt + ((size_t)pair * p.ncell + c) * NID_NCLS, L, s, p.span_mode ? p.lut_k : nullptr, p.bins - 3);
   const int* bs = base + ((size_t)blockIdx.y * p.ncell + c) * 3;
   const int tb = bs[0], sb = bs[1], pb = bs[2];
   if (tb + s.T > p.max_tasks || sb + s.S > p.max_slices) return;  // flagged by k_layout_scan
@@ -726,11 +740,16 @@ __device__ __forceinline__ void make_exact(const ExactSrc& xs, int rows, int col
 // weights, then the accumulations in pixel order into the lane's private row h[b * T] (T = threads per CTA).
 // fp: the pair's footprint-packed target image, fp[y*cols + x] = I(x,y) | I(x+1,y)<<8 | I(x,y+1)<<16 | I(x+1,y+1)<<24.
 // n0 counts the lane's pixels with u == 0 exactly (see bspline4_uniform).
-template <bool PTS, int W, int T>
+// MODE 1 (span tasks, small cells): the lane's task holds pixels of one reference SPAN but of any reference intensity;
+// the lane accumulates the four joint-histogram rows of that span, h[(m * B + b) * T] += w_ref,v[m] * w_t[n], with the
+// pixel's reference weights looked up from its intensity byte (vv: the group's four bytes; noref: pixels without a
+// reference sample, weight row (1, 0, 0, 0)); n0m[m]: the reference weights of the pixels with u == 0 exactly.
+template <bool PTS, int W, int T, int MODE = 0>
 __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const ExactSrc& xs, int rows, int cols,
                                             const Group<PTS>& G, int j0, const GroupAddr& ga,
                                             const unsigned* __restrict__ fp, double s, int NS, double* __restrict__ h,
-                                            int& n0) {
+                                            int& n0, const double* __restrict__ lutw = nullptr, unsigned vv = 0u,
+                                            bool noref = false, double* n0m = nullptr) {
   Px r[W];
   bool anyexact = false;
 #pragma unroll
@@ -784,15 +803,86 @@ __device__ __forceinline__ void hist_pixels(const double* __restrict__ g, const 
     bspline4_uniform(ub - u2d((unsigned)kt[j]), wt[j]);
     const bool zero = ub == 0.0;
     acc[j] = r[j].ok && !zero;
-    n0 += (r[j].ok && zero) ? 1 : 0;
+    if (MODE == 0) n0 += (r[j].ok && zero) ? 1 : 0;
+    else if (r[j].ok && zero) {
+      const unsigned v = (vv >> (8 * (j0 + j))) & 0xffu;
+#pragma unroll
+      for (int m = 0; m < 4; m++) n0m[m] += noref ? (m == 0 ? 1.0 : 0.0) : __ldg(lutw + 4 * v + m);
+    }
   }
 #pragma unroll
   for (int j = 0; j < W; j++) {
     if (!acc[j]) continue;
-    double* hk = h + kt[j] * T;
+    if (MODE == 0) {
+      double* hk = h + kt[j] * T;
 #pragma unroll
-    for (int n = 0; n < 4; n++) hk[n * T] += wt[j][n];
+      for (int n = 0; n < 4; n++) hk[n * T] += wt[j][n];
+    } else {
+      const int B = NS + 3;
+      const unsigned v = (vv >> (8 * (j0 + j))) & 0xffu;
+      if (noref) {
+        double* hk = h + kt[j] * T;
+#pragma unroll
+        for (int n = 0; n < 4; n++) hk[n * T] += wt[j][n];
+      } else {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const double wr = __ldg(lutw + 4 * v + m);
+          double* hk = h + (m * B + kt[j]) * T;
+#pragma unroll
+          for (int n = 0; n < 4; n++) hk[n * T] = fma(wr, wt[j][n], hk[n * T]);
+        }
+      }
+    }
   }
+}
+
+// Epilogue of pass 1: the warp's 32 rows go out as whole 8 B x B lines. Lane l first rotates its row inside the warp's
+// own columns of the shared array -- value (l, b) to column (l + b) mod 32 of plane b -- so that the lanes which then
+// write one task's row read B different banks; each store instruction covers 32/B' complete rows (B' = B rounded up
+// to a power of two) instead of 32 partial sectors of 32 different rows.
+// hw: plane b of this warp at hw[b * T + 0..31]; the row of task tk goes to Gj[tk * gstride + 0..B-1].
+template <int T>
+__device__ __forceinline__ void store_task_rows(double* hw, int B, int lane, int task, double* __restrict__ Gj, size_t gstride) {
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = (b0 + i < B) ? hw[(b0 + i) * T + lane] : 0.0;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (b0 + i < B) hw[(b0 + i) * T + ((lane + b0 + i) & 31)] = v[i];
+  }
+  __syncwarp();
+  const int BP2 = B <= 8 ? 8 : (B <= 16 ? 16 : 32);  // lanes per row
+  const int rpi = 32 / BP2;                          // rows per store instruction
+  const int b = lane & (BP2 - 1), sub = lane / BP2;
+  {
+    const double* src = hw + min(b, B - 1) * T;  // (lanes beyond the row length read a valid plane and store nothing)
+    double* dst = Gj + b;
+    const int nit = 32 / rpi;  // 8, 16 or 32 store instructions
+    for (int i0 = 0; i0 < nit; i0 += 8) {
+      double v[8];
+      int tk[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int tl = (i0 + i) * rpi + sub;
+        tk[i] = __shfl_sync(0xffffffffu, task, tl);
+        v[i] = src[(tl + b) & 31];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (b < B && tk[i] >= 0) dst[(size_t)tk[i] * gstride] = v[i];
+    }
+  }
+  for (int b1 = BP2; b1 < B; b1 += BP2) {  // B > 32: remaining columns
+    for (int t0 = 0; t0 < 32; t0 += rpi) {
+      const int tl = t0 + sub, bb = b1 + b;
+      const int tk = __shfl_sync(0xffffffffu, task, tl);
+      if (bb < B && tk >= 0) Gj[(size_t)tk * gstride + bb] = hw[bb * T + ((tl + bb) & 31)];
+    }
+  }
+  __syncwarp();
 }
 
 // Pass 1: per task the un-weighted target soft histogram h[B] of its pixels.
@@ -889,52 +979,7 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
   }
   fold_row(h, T, B, (double)n0);  // uniform sums -> sums of the reference's clamped basis
   __syncwarp();
-  // Epilogue: the warp's 32 rows go out as whole 8 B x B lines. Lane l first rotates its row inside the warp's own
-  // columns of the shared array -- value (l, b) to column (l + b) mod 32 of plane b -- so that the lanes which then
-  // write one task's row read B different banks; each store instruction covers 32/B' complete rows (B' = B rounded up
-  // to a power of two) instead of 32 partial sectors of 32 different rows.
-  {
-    double* hw = sm + (threadIdx.x & ~31);  // plane b of this warp: hw[b * T + 0..31]
-    for (int b0 = 0; b0 < B; b0 += 8) {
-      double v[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) v[i] = (b0 + i < B) ? hw[(b0 + i) * T + lane] : 0.0;
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; i++)
-        if (b0 + i < B) hw[(b0 + i) * T + ((lane + b0 + i) & 31)] = v[i];
-    }
-    __syncwarp();
-    const int BP2 = B <= 8 ? 8 : (B <= 16 ? 16 : 32);  // lanes per row
-    const int rpi = 32 / BP2;                          // rows per store instruction
-    const int b = lane & (BP2 - 1), sub = lane / BP2;
-    double* Gj = p.G + (size_t)job * p.g_stride * B;
-    {
-      const double* src = hw + min(b, B - 1) * T;  // (lanes beyond the row length read a valid plane and store nothing)
-      double* dst = Gj + b;
-      const int nit = 32 / rpi;  // 8, 16 or 32 store instructions
-      for (int i0 = 0; i0 < nit; i0 += 8) {
-        double v[8];
-        int tk[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int tl = (i0 + i) * rpi + sub;
-          tk[i] = __shfl_sync(0xffffffffu, task, tl);
-          v[i] = src[(tl + b) & 31];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-          if (b < B && tk[i] >= 0) dst[(size_t)tk[i] * B] = v[i];
-      }
-    }
-    for (int b1 = BP2; b1 < B; b1 += BP2) {  // B > 32: remaining columns
-      for (int t0 = 0; t0 < 32; t0 += rpi) {
-        const int tl = t0 + sub, bb = b1 + b;
-        const int tk = __shfl_sync(0xffffffffu, task, tl);
-        if (bb < B && tk >= 0) Gj[(size_t)tk * B + bb] = hw[bb * T + ((tl + bb) & 31)];
-      }
-    }
-  }
+  store_task_rows<T>(sm + (threadIdx.x & ~31), B, lane, task, p.G + (size_t)job * p.g_stride * B, B);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1285,11 +1330,16 @@ __device__ __forceinline__ double tapd(unsigned v) { return __hiloint2double(0x4
 
 // Pass 2 on W pixels of a group at once; acc[6] are the lane's Jacobian partial sums.
 // wq: the lane's folded class table (fold_table), element t at wq[t * T].
-template <bool PTS, int W, int T>
+// MODE 1 (span tasks): wq points at the warp's staged, folded tables W^ (rows padded to BP = B + 1) followed by V^; the
+// lane's task belongs to reference span kr and every pixel brings its own reference weights (looked up from its
+// intensity byte): c_i = sum_n U'_n(f) (V^[k+n] + sum_m w_ref,v[m] W^[kr+m][k+n]).
+template <bool PTS, int W, int T, int MODE = 0>
 __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const ExactSrc& xs, int rows, int cols,
                                            const Group<PTS>& G, int j0, cudaTextureObject_t tex2,
                                            const uint8_t* __restrict__ im1, double s, int NS, double hfx, double hfy,
-                                           const double* __restrict__ wq, double acc[6]) {
+                                           const double* __restrict__ wq, double acc[6],
+                                           const double* __restrict__ lutw = nullptr, unsigned vv = 0u, bool noref = false,
+                                           int kr = 0) {
   Px r[W];
 #pragma unroll
   for (int j = 0; j < W; j++) front<PTS, false>(g, rows, cols, G.a0[j0 + j], G.a1[j0 + j], G.a2[j0 + j], G.id[j0 + j], r[j]);
@@ -1334,8 +1384,26 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
     const double dw1 = f * fma(f, KC_15, -KC_2);
     const double dw2 = fma(f, fma(f, -KC_15, KC_1), KC_H);
     const double dw3 = KC_H * f * f;
-    const double* q = wq + k * T;
-    double ci = fma(dw3, q[3 * T], fma(dw2, q[2 * T], fma(dw1, q[T], dw0 * q[0])));
+    double ci;
+    if (MODE == 0) {
+      const double* q = wq + k * T;
+      ci = fma(dw3, q[3 * T], fma(dw2, q[2 * T], fma(dw1, q[T], dw0 * q[0])));
+    } else {
+      const int B = NS + 3, BP = B + 1;
+      const double* V = wq + B * BP + k;
+      double c0 = V[0], c1 = V[1], c2 = V[2], c3 = V[3];
+      if (!noref) {
+        const unsigned v = (vv >> (8 * (j0 + j))) & 0xffu;
+        const double* Wr = wq + kr * BP + k;
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const double wr = __ldg(lutw + 4 * v + m);
+          c0 = fma(wr, Wr[m * BP], c0); c1 = fma(wr, Wr[m * BP + 1], c1);
+          c2 = fma(wr, Wr[m * BP + 2], c2); c3 = fma(wr, Wr[m * BP + 3], c3);
+        }
+      }
+      ci = fma(dw3, c3, fma(dw2, c2, fma(dw1, c1, dw0 * c0)));
+    }
     if (ub == 0.0) ci = 0.0;  // the reference's BsplineDer quirk
     if (!r[j].jac) continue;  // (a padding slot may carry z = 0 and non-finite coordinates)
     // d(u,v)/d(xi), types_six_dof_expmap.cpp:438-450, in normalised coordinates xn = x/z, yn = y/z
@@ -1490,6 +1558,231 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
 #pragma unroll
     for (int k = 1; k < 6; k++) vv = lane == k ? acc[k] : vv;
     p.jpart[((size_t)job * p.max_slices + slice) * 6 + lane] = vv;
+  }
+}
+
+// ================================================================================================ span tasks
+// Small cells (the reference's default 16x16 cells of a 640x480 image hold 1200 pixels: fewer than five per reference
+// intensity) are a poor fit for (cell, class) tasks: a task is a handful of pixels, and the per-task and per-slice work
+// (row set-up, fold, row store, class table) outweighs the pixels. There the valid pixels of a cell are regrouped by
+// reference SPAN k_r instead (B - 3 spans plus one for pixels without a reference sample), tasks are full runs of L
+// pixels again, and what the class factorisation saved is paid per pixel: the lane keeps the four joint-histogram rows
+// of its span, 16 accumulations per pixel instead of 4 (pass 1), and pass 2 forms the pixel's table entry from the
+// four reference weights instead of reading a per-class table. The pixel's reference intensity travels with it (one
+// byte per pixel slot, plane `sv`). Everything else -- front end, exact paths, uniform basis and fold -- is shared.
+template <int NG, int T>
+__global__ void __launch_bounds__(T, NID_HIST_MINB * 256 / T)
+k_hist_span(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
+  extern __shared__ double sm[];
+  const int B = p.bins, NS = B - 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int job = job_at(p, NID_BLK_JOB);
+  const int pair = p.job_pair[job];
+  const double* g = gt.g[NID_BLK_JOB];
+  const int slice = NID_BLK_CHUNK * (T >> 5) + warp;
+  if (slice >= p.nslices[pair]) return;  // (no block-wide barrier below)
+  const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
+  const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
+  const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
+  const int span = task >= 0 ? ((p.tasks[(size_t)pair * p.max_tasks + task].y >> 9) & 0x1ff) : NS;
+  const bool noref = span >= NS;
+  double* h = sm + threadIdx.x;  // h[(m * B + b) * T]
+  for (int b = 0; b < 4 * B; b++) h[b * T] = 0.0;
+  const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
+  const double* q0 = p.sd0 + sbase;
+  const unsigned* qi = p.sid + sbase;
+  const unsigned* qv = reinterpret_cast<const unsigned*>(p.sv + sbase);  // four intensity bytes per group and lane
+  const unsigned* fp = p.fp1 + (size_t)pair * p.N;
+  const ExactSrc xs{p.poses + 16 * job, p.Twc0 + 16 * pair, p.cam + 4 * pair};
+  const double s = (double)NS / 255.0;
+  int n0 = 0;
+  double n0m[4] = {0.0, 0.0, 0.0, 0.0};
+  Group<false> G;
+  G.load(q0, nullptr, nullptr, qi, 0);
+  unsigned vv = NID_LD_STREAM(qv);
+  for (int gi = 0; gi < ngroups; gi++) {
+    Group<false> Gn = G;
+    unsigned vn = vv;
+    if (gi + 1 < ngroups) { Gn.load(q0, nullptr, nullptr, qi, (size_t)(gi + 1) * 128); vn = NID_LD_STREAM(qv + (size_t)(gi + 1) * 32); }
+    const size_t go = (size_t)gi * 128;
+    const GroupAddr ga{q0 + go, nullptr, nullptr, qi + go};
+#pragma unroll
+    for (int j0 = 0; j0 < 4; j0 += NID_HIST_W)
+      hist_pixels<false, NID_HIST_W, T, 1>(g, xs, p.rows, p.cols, G, j0, ga, fp, s, NS, h, n0, p.lut_w, vv, noref, n0m);
+    G = Gn;
+    vv = vn;
+  }
+  // uniform sums -> sums of the reference's clamped basis, row by row; then the four rows go out
+  double* Gj = p.G + (size_t)job * p.g_stride * (4 * B);
+#pragma unroll 1
+  for (int m = 0; m < 4; m++) {
+    fold_row(h + m * B * T, T, B, n0m[m]);
+    __syncwarp();
+    store_task_rows<T>(sm + (size_t)m * B * T + (threadIdx.x & ~31), B, lane, task, Gj + m * B, (size_t)4 * B);
+  }
+}
+
+// Assembly for span tasks: one warp per (cell, job) as in k_assemble_warp; a task of span k brings four rows,
+// P_j[k+m][t] += row_m[t], and P_t[t] is the sum of all rows (the four reference weights of a pixel add up to 1).
+__global__ void __launch_bounds__(NID_ASMW_WARPS * 32, NID_ASMW_MINB) k_assemble_span(EvalParams p, int want_jac, int n_jobs) {
+  extern __shared__ double sm[];
+  const int B = p.bins, BB = B * B, NS = B - 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int unit = blockIdx.x * NID_ASMW_WARPS + warp;
+  if (unit >= n_jobs * p.ncell) return;
+  const int c = unit % p.ncell, job = job_at(p, unit / p.ncell);
+  const int pair = p.job_pair[job];
+  const int nc = p.n_c[pair * p.ncell + c];
+  const size_t o = (size_t)job * p.ncell + c;
+  if (nc < NID_MIN_CELL_POINTS) {
+    if (lane == 0) { p.ht[o] = nan(""); p.hj[o] = nan(""); p.err[o] = nan(""); }
+    return;
+  }
+  const int NGR = 32 / B;
+  const int g = lane / B, t = lane - g * B;
+  const bool mine = g < NGR;
+  const int stride = BB + B;
+  double* cp = sm + (size_t)warp * NGR * stride;
+  for (int i = lane; i < NGR * stride; i += 32) cp[i] = 0.0;
+  __syncwarp();
+  double* Pj = cp + (mine ? g : 0) * stride + t;
+  double pt = 0.0;
+  const int t0 = p.cell_task_start[pair * (p.ncell + 1) + c], t1 = p.cell_task_start[pair * (p.ncell + 1) + c + 1];
+  const int2* tk = p.tasks + (size_t)pair * p.max_tasks;
+  const double* G = p.G + (size_t)job * p.g_stride * (4 * B) + t;
+  for (int tb = t0; tb < t1; tb += 2 * NGR) {  // two tasks (eight rows) in flight per sub-group
+    double x[2][4];
+    int sp[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int tt = tb + i * NGR + g;
+      const bool in = mine && tt < t1;
+#pragma unroll
+      for (int m = 0; m < 4; m++) x[i][m] = in ? NID_ASM_LD(G + ((size_t)tt * 4 + m) * B) : 0.0;
+      sp[i] = in ? ((tk[tt].y >> 9) & 0x1ff) : NS;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      pt += (x[i][0] + x[i][1]) + (x[i][2] + x[i][3]);
+      if (sp[i] < NS) {
+        double* q = Pj + sp[i] * B;
+#pragma unroll
+        for (int m = 0; m < 4; m++) q[m * B] += x[i][m];
+      }
+    }
+  }
+  if (mine) cp[g * stride + BB + t] = pt;
+  __syncwarp();
+  for (int i = lane; i < stride; i += 32) {
+    double a = cp[i];
+    for (int k = 1; k < NGR; k++) a += cp[k * stride + i];
+    cp[i] = a;
+  }
+  __syncwarp();
+  double ej = 0.0, et = 0.0;
+  const double dn = (double)nc;
+  double* hist = p.hist ? p.hist + o * (size_t)(BB + B) : nullptr;
+  for (int i = lane; i < stride; i += 32) {
+    const double q = cp[i] / dn;
+    const double lg = (q < kSigma) ? 0.0 : log2(q);
+    if (i < BB) ej -= q * lg; else et -= q * lg;
+    cp[i] = (q < kSigma) ? 0.0 : 1.0 + lg;
+    if (hist) hist[i] = q;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    ej += __shfl_xor_sync(0xffffffffu, ej, off);
+    et += __shfl_xor_sync(0xffffffffu, et, off);
+  }
+  const double Hj = ej, Ht = et;
+  const double Href = p.href[pair * p.ncell + c];
+  if (lane == 0) {
+    p.ht[o] = Ht; p.hj[o] = Hj;
+    p.err[o] = (2 * Hj - Href - Ht) / Hj;
+  }
+  __syncwarp();
+  if (want_jac) {
+    const double s_over = ((double)(B - 3) / 255.0) / ((double)nc * Hj * Hj);
+    const double coefJ = -s_over * (Ht + Href);
+    const double coefT = s_over * Hj;
+    double* wv = p.wv + o * (size_t)(BB + B);
+    for (int i = lane; i < stride; i += 32) wv[i] = cp[i] * (i < BB ? coefJ : coefT);
+  }
+}
+
+// Pass 2 for span tasks: the warp stages the cell's scaled log tables W | V (rows padded to B + 1), folds every row
+// (and V) onto the uniform basis along the target index, and every pixel evaluates its own table entry.
+template <int NG, int T>
+__global__ void __launch_bounds__(T, NID_JAC_MINB * 128 / T)
+k_jac_span(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
+  extern __shared__ double sm[];
+  const int B = p.bins, NS = B - 3, BP = B + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int job = job_at(p, NID_BLK_JOB);
+  const int pair = p.job_pair[job];
+  const double* g = gt.g[NID_BLK_JOB];
+  const int slice = NID_BLK_CHUNK * (T >> 5) + warp;
+  if (slice >= p.nslices[pair]) return;  // (no block-wide barrier below)
+  const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
+  const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
+  const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
+  const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
+  const double* q0 = p.sd0 + sbase;
+  const unsigned* qi = p.sid + sbase;
+  const unsigned* qv = reinterpret_cast<const unsigned*>(p.sv + sbase);
+  Group<false> G;
+  G.load(q0, nullptr, nullptr, qi, 0);
+  unsigned vv = NID_LD_STREAM(qv);
+  const int span = task >= 0 ? ((p.tasks[(size_t)pair * p.max_tasks + task].y >> 9) & 0x1ff) : NS;
+  const bool noref = span >= NS;
+  double* Ww = sm + (size_t)warp * (B * BP + B + 4);  // W^ [B][BP] | V^ [B] (+ slack: the last span reads V^[k..k+3] with k <= NS-1)
+  {
+    const int cell = p.sl_cell[(size_t)pair * p.max_slices + slice];
+    const double* wvg = p.wv + ((size_t)job * p.ncell + cell) * (size_t)(B * B + B);
+    double* Vw = Ww + B * BP;
+    {
+      const int dr = 32 / B, dc = 32 % B;
+      int r = lane / B, cc = lane % B;
+      for (int i = lane; i < B * B; i += 32) {
+        Ww[r * BP + cc] = wvg[i];
+        r += dr; cc += dc;
+        if (cc >= B) { cc -= B; r++; }
+      }
+    }
+    for (int i = lane; i < B; i += 32) Vw[i] = wvg[B * B + i];
+    __syncwarp();
+    for (int r = lane; r <= B; r += 32) fold_table(r < B ? Ww + r * BP : Vw, 1, B);  // rows of W^, then V^
+    __syncwarp();
+  }
+  const cudaTextureObject_t tex2 = p.tex2[pair];
+  const uint8_t* im1 = p.im1 + (size_t)pair * p.N;
+  const ExactSrc xs{p.poses + 16 * job, p.Twc0 + 16 * pair, p.cam + 4 * pair};
+  const double s = (double)NS / 255.0;
+  const double hfx = 0.5 * g[16], hfy = 0.5 * g[17];
+  const int kr = noref ? 0 : span;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int gi = 0; gi < ngroups; gi++) {
+    Group<false> Gn = G;
+    unsigned vn = vv;
+    if (gi + 1 < ngroups) { Gn.load(q0, nullptr, nullptr, qi, (size_t)(gi + 1) * 128); vn = NID_LD_STREAM(qv + (size_t)(gi + 1) * 32); }
+#pragma unroll
+    for (int j0 = 0; j0 < 4; j0 += NID_JAC_W)
+      jac_pixels<false, NID_JAC_W, T, 1>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, Ww, acc, p.lut_w, vv, noref, kr);
+    G = Gn;
+    vv = vn;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    double vx = acc[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) vx += __shfl_xor_sync(0xffffffffu, vx, off);
+    acc[k] = vx;
+  }
+  if (lane < 6) {
+    double vx = acc[0];
+#pragma unroll
+    for (int k = 1; k < 6; k++) vx = lane == k ? acc[k] : vx;
+    p.jpart[((size_t)job * p.max_slices + slice) * 6 + lane] = vx;
   }
 }
 
@@ -1727,7 +2020,8 @@ int launch_layout_and_scatter(nid_ctx* c, int pair0, int n) {
   EvalParams p = make_params(c, 1);
   const int L = c->task_px;
   const dim3 gcell(c->ncell, n);
-  k_layout_totals<<<gcell, NID_LAYOUT_THREADS, 0, c->stream>>>(pair0, c->ncell, L, c->cnt, c->lay_tot);
+  k_layout_totals<<<gcell, NID_LAYOUT_THREADS, 0, c->stream>>>(pair0, c->ncell, L, c->cnt, c->lay_tot, c->span_mode ? c->lut_k : nullptr,
+                                                              c->bins - 3);
   NID_LAUNCH_CHECK(c, "k_layout_totals");
   k_layout_scan<<<n, 256, 0, c->stream>>>(p, pair0, c->lay_tot, c->lay_base, c->cell_task_start, c->cell_slice_start, c->ntasks,
                                          c->nslices, c->sl_off, c->d_flag + 1);
@@ -1866,10 +2160,55 @@ static void launch_jac_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0,
     c->launches++;
   }
 }
+size_t hist_span_smem(const nid_ctx* c, int T) { return sizeof(double) * ((size_t)4 * c->bins * T); }
+size_t jac_span_smem(const nid_ctx* c, int T) {
+  const size_t B = c->bins;
+  return sizeof(double) * (size_t)(T / 32) * (B * (B + 1) + B + 4);
+}
+template <int NG>
+static void launch_hist_span_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs, const int* h_list) {
+  const int T = pick_block(c, ns, n_jobs, NID_HIST_TMAX);
+  const size_t sm = hist_span_smem(c, T);
+  for (int s0 = 0; s0 < n_jobs; s0 += NG) {
+    const int n = std::min(NG, n_jobs - s0);
+    GeoTable<NG> gt;
+    fill_geo(c, gt, job0 + s0, n, true, h_list);
+    EvalParams q = p;
+    q.job0 = job0 + s0;
+    const dim3 grid = NID_GRID(n, (ns + T / 32 - 1) / (T / 32));
+    switch (T) {
+      case 128: k_hist_span<NG, 128><<<grid, 128, sm, c->stream>>>(q, gt); break;
+      case 64: k_hist_span<NG, 64><<<grid, 64, sm, c->stream>>>(q, gt); break;
+      default: k_hist_span<NG, 32><<<grid, 32, sm, c->stream>>>(q, gt); break;
+    }
+    c->launches++;
+  }
+}
+template <int NG>
+static void launch_jac_span_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs, const int* h_list) {
+  const int T = pick_block(c, ns, n_jobs, NID_JAC_TMAX);
+  const size_t sm = jac_span_smem(c, T);
+  for (int s0 = 0; s0 < n_jobs; s0 += NG) {
+    const int n = std::min(NG, n_jobs - s0);
+    GeoTable<NG> gt;
+    fill_geo(c, gt, job0 + s0, n, false, h_list);
+    EvalParams q = p;
+    q.job0 = job0 + s0;
+    const dim3 grid = NID_GRID(n, (ns + T / 32 - 1) / (T / 32));
+    switch (T) {
+      case 64: k_jac_span<NG, 64><<<grid, 64, sm, c->stream>>>(q, gt); break;
+      default: k_jac_span<NG, 32><<<grid, 32, sm, c->stream>>>(q, gt); break;
+    }
+    c->launches++;
+  }
+}
 #define NID_GEO_SMALL 8
 #define NID_GEO_LARGE 96
 static void launch_hist_w(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs, const int* h_list) {
-  if (c->sell_points) {
+  if (c->span_mode) {
+    if (n_jobs <= NID_GEO_SMALL) launch_hist_span_chunks<NID_GEO_SMALL>(c, p, ns, job0, n_jobs, h_list);
+    else launch_hist_span_chunks<NID_GEO_LARGE>(c, p, ns, job0, n_jobs, h_list);
+  } else if (c->sell_points) {
     if (n_jobs <= NID_GEO_SMALL) launch_hist_chunks<true, NID_GEO_SMALL>(c, p, ns, job0, n_jobs, h_list);
     else launch_hist_chunks<true, NID_GEO_LARGE>(c, p, ns, job0, n_jobs, h_list);
   } else {
@@ -1878,7 +2217,10 @@ static void launch_hist_w(nid_ctx* c, const EvalParams& p, int ns, int job0, int
   }
 }
 static void launch_jac_w(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs, const int* h_list) {
-  if (c->sell_points) {
+  if (c->span_mode) {
+    if (n_jobs <= NID_GEO_SMALL) launch_jac_span_chunks<NID_GEO_SMALL>(c, p, ns, job0, n_jobs, h_list);
+    else launch_jac_span_chunks<NID_GEO_LARGE>(c, p, ns, job0, n_jobs, h_list);
+  } else if (c->sell_points) {
     if (n_jobs <= NID_GEO_SMALL) launch_jac_chunks<true, NID_GEO_SMALL>(c, p, ns, job0, n_jobs, h_list);
     else launch_jac_chunks<true, NID_GEO_LARGE>(c, p, ns, job0, n_jobs, h_list);
   } else {
@@ -1899,7 +2241,10 @@ int launch_sorted_pass1(nid_ctx* c, const int* d_list, const int* h_list, int fi
   c->launches--;
   NID_LAUNCH_CHECK(c, "k_hist_sell");
   ktime_mark(c, 1);
-  if (assemble_warp(c)) {
+  if (c->span_mode) {
+    const int units = c->ncell * n;
+    k_assemble_span<<<(units + NID_ASMW_WARPS - 1) / NID_ASMW_WARPS, NID_ASMW_WARPS * 32, assemble_warp_smem(c), c->stream>>>(p, tables, n);
+  } else if (assemble_warp(c)) {
     const int units = c->ncell * n;
     k_assemble_warp<<<(units + NID_ASMW_WARPS - 1) / NID_ASMW_WARPS, NID_ASMW_WARPS * 32, assemble_warp_smem(c), c->stream>>>(p, tables, n);
   } else if (assemble_small(c)) k_assemble_small<<<dim3(c->ncell, n), NID_ASM_SMALL, assemble_smem(c), c->stream>>>(p, tables);
@@ -2027,7 +2372,18 @@ int sorted_init(nid_ctx* c) {
 #undef NID_SMEM_ATTR_PX
   NID_SMEM_ATTR(k_assemble, assemble_smem(c));
   NID_SMEM_ATTR(k_assemble_small, assemble_smem(c));
-  if (c->bins <= 32) { NID_SMEM_ATTR(k_assemble_warp, assemble_warp_smem(c)); }
+  if (c->bins <= 32) { NID_SMEM_ATTR(k_assemble_warp, assemble_warp_smem(c)); NID_SMEM_ATTR(k_assemble_span, assemble_warp_smem(c)); }
+  if (NID_FEW_BINS(c->bins)) {
+#define NID_SMEM_ATTR_SPAN(NG)                                              \
+  NID_SMEM_ATTR((k_hist_span<NG, 128>), hist_span_smem(c, 128));            \
+  NID_SMEM_ATTR((k_hist_span<NG, 64>), hist_span_smem(c, 64));              \
+  NID_SMEM_ATTR((k_hist_span<NG, 32>), hist_span_smem(c, 32));              \
+  NID_SMEM_ATTR((k_jac_span<NG, 64>), jac_span_smem(c, 64));                \
+  NID_SMEM_ATTR((k_jac_span<NG, 32>), jac_span_smem(c, 32));
+    NID_SMEM_ATTR_SPAN(NID_GEO_SMALL)
+    NID_SMEM_ATTR_SPAN(NID_GEO_LARGE)
+#undef NID_SMEM_ATTR_SPAN
+  }
 #undef NID_SMEM_ATTR
   return NID_OK;
 }

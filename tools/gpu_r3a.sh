@@ -1,0 +1,6 @@
+#!/bin/bash
+timeout 1800 python -m pytest tests -m gpu -q -x 2>&1 | tail -12
+for v in base nospan; do
+  if [ "$v" = base ]; then unset NID_B200_LIB; else export NID_B200_LIB=$PWD/build/libvar_$v.so; fi
+  for g in "480 640 16 10" "480 640 12 10" "480 640 8 10"; do echo "== $v: $(timeout 300 python tools/time_config.py $g 96 10 2>&1 | grep 'sorted want_jac=1')"; done
+done
