@@ -900,7 +900,8 @@ __device__ __forceinline__ void store_task_rows(double* hw, int B, int lane, int
 #define NID_JAC_INTTAP 0
 #endif
 #ifndef NID_HIST_TMAX
-#define NID_HIST_TMAX 128  // largest CTA of pass 1 / pass 2 (pick_block shrinks it when few jobs are in flight); measured best
+#define NID_HIST_TMAX 32  // largest CTA of pass 1 / pass 2 (pick_block shrinks it when few jobs are in flight); measured best:
+                          // one-warp CTAs at 18 resident warps (113 registers) 2.28 us per C2 evaluation, 128-thread CTAs at 16 warps 2.49
 #endif
 #ifndef NID_JAC_TMAX
 #define NID_JAC_TMAX 64
@@ -914,8 +915,14 @@ __device__ __forceinline__ void store_task_rows(double* hw, int B, int lane, int
 #ifndef NID_JAC_MINB
 #define NID_JAC_MINB 4  // CTAs of 128 threads per SM (128 registers)
 #endif
+#ifndef NID_HIST_WARPS
+#define NID_HIST_WARPS 18  // resident warps per SM the register budget is set for
+#endif
+#ifndef NID_JAC_WARPS
+#define NID_JAC_WARPS (NID_JAC_MINB * 4)
+#endif
 template <bool PTS, int NG, int T>
-__global__ void __launch_bounds__(T, NID_HIST_MINB * 256 / T)
+__global__ void __launch_bounds__(T, NID_HIST_WARPS * 32 / T)
 k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
   extern __shared__ double sm[];
   const int B = p.bins, NS = B - 3;
@@ -1422,7 +1429,7 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
 
 // grid (jobs of this launch, ceil(max_slices/(T/32))), T = 32..128 threads.
 template <bool PTS, int NG, int T>
-__global__ void __launch_bounds__(T, NID_JAC_MINB * 128 / T)
+__global__ void __launch_bounds__(T, NID_JAC_WARPS * 32 / T)
 k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
   extern __shared__ double sm[];
   const int B = p.bins, NS = B - 3;
@@ -2123,7 +2130,8 @@ static void fill_geo(const nid_ctx* c, GeoTable<NG>& gt, int first, int n, bool 
 
 template <bool PTS, int NG>
 static void launch_hist_chunks(nid_ctx* c, const EvalParams& p, int ns, int job0, int n_jobs, const int* h_list) {
-  const int T = pick_block(c, ns, n_jobs, NID_HIST_TMAX);
+  // (many bins: the rows take the shared memory that one-warp CTAs would need for 18 resident warps: 128-thread CTAs)
+  const int T = pick_block(c, ns, n_jobs, c->bins > 20 ? 128 : NID_HIST_TMAX);
   const size_t sm = hist_sell_smem(c, T);
   for (int s0 = 0; s0 < n_jobs; s0 += NG) {
     const int n = std::min(NG, n_jobs - s0);
@@ -2361,10 +2369,11 @@ int sorted_init(nid_ctx* c) {
   NID_SMEM_ATTR((k_jac_sell<PTS, NG, 128>), jac_sell_smem(c, 128));         \
   NID_SMEM_ATTR((k_jac_sell<PTS, NG, 64>), jac_sell_smem(c, 64));           \
   NID_SMEM_ATTR((k_jac_sell<PTS, NG, 32>), jac_sell_smem(c, 32));                \
-  NID_CARVE((k_hist_sell<PTS, NG, 128>), hist_sell_smem(c, 128), NID_HIST_MINB * 2);   \
-  NID_CARVE((k_hist_sell<PTS, NG, 64>), hist_sell_smem(c, 64), NID_HIST_MINB * 4);     \
-  NID_CARVE((k_jac_sell<PTS, NG, 64>), jac_sell_smem(c, 64), NID_JAC_MINB * 2);        \
-  NID_CARVE((k_jac_sell<PTS, NG, 32>), jac_sell_smem(c, 32), NID_JAC_MINB * 4);
+  NID_CARVE((k_hist_sell<PTS, NG, 128>), hist_sell_smem(c, 128), NID_HIST_WARPS / 4);  \
+  NID_CARVE((k_hist_sell<PTS, NG, 64>), hist_sell_smem(c, 64), NID_HIST_WARPS / 2);    \
+  NID_CARVE((k_hist_sell<PTS, NG, 32>), hist_sell_smem(c, 32), NID_HIST_WARPS);        \
+  NID_CARVE((k_jac_sell<PTS, NG, 64>), jac_sell_smem(c, 64), NID_JAC_WARPS / 2);       \
+  NID_CARVE((k_jac_sell<PTS, NG, 32>), jac_sell_smem(c, 32), NID_JAC_WARPS);
   NID_SMEM_ATTR_PX(true, NID_GEO_SMALL)
   NID_SMEM_ATTR_PX(false, NID_GEO_SMALL)
   NID_SMEM_ATTR_PX(true, NID_GEO_LARGE)
