@@ -647,6 +647,9 @@ struct Group {
 #ifndef NID_BULK_STAGES
 #define NID_BULK_STAGES 3
 #endif
+#ifndef NID_BULK_FENCE
+#define NID_BULK_FENCE 0
+#endif
 struct __align__(16) BulkStage {
   double z[128];    // group g of the slice: lane l owns z[4 l .. 4 l + 3]
   unsigned id[128];
@@ -705,7 +708,11 @@ struct BulkRing {
     for (int j = 0; j < 4; j++) { G.a1[j] = 0.0; G.a2[j] = 0.0; }
     __syncwarp();  // every lane has read the stage
     if (lane == 0 && g + nst < ngroups) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads before the async-proxy refill
+#if NID_BULK_FENCE
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: costly)
+#endif
+      // the stage's reads are complete (their values were consumed before the __syncwarp above could be passed by the
+      // issuing lane's later instructions only in program order; the refill lands hundreds of cycles later)
       issue(g + nst);
     }
   }
@@ -920,6 +927,9 @@ __device__ __forceinline__ void store_task_rows(double* hw, int B, int lane, int
 #endif
 #ifndef NID_JAC_WARPS
 #define NID_JAC_WARPS (NID_JAC_MINB * 4)
+#endif
+#ifndef NID_JAC_NOPF
+#define NID_JAC_NOPF 0
 #endif
 template <bool PTS, int NG, int T>
 __global__ void __launch_bounds__(T, NID_HIST_WARPS * 32 / T)
@@ -1537,6 +1547,20 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
       for (int j0 = 0; j0 < 4; j0 += NID_JAC_W) jac_pixels<PTS, NID_JAC_W, T>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, acc);
     }
   } else {
+#if NID_JAC_NOPF
+    // no register double-buffer: the group is loaded when it is needed (it was pulled into L2 two groups earlier);
+    // twelve registers less per thread
+    for (int gi = 0; gi < ngroups; gi++) {
+      if (gi > 0) G.load(q0, q1, q2, qi, (size_t)gi * 128);
+      if (gi + 2 < ngroups) {
+        const size_t po = (size_t)(gi + 2) * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + po));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(qi + po));
+      }
+#pragma unroll
+      for (int j0 = 0; j0 < 4; j0 += NID_JAC_W) jac_pixels<PTS, NID_JAC_W, T>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, acc);
+    }
+#else
     for (int gi = 0; gi < ngroups; gi++) {
       Group<PTS> Gn = G;
       if (gi + 1 < ngroups) Gn.load(q0, q1, q2, qi, (size_t)(gi + 1) * 128);
@@ -1551,6 +1575,7 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
       for (int j0 = 0; j0 < 4; j0 += NID_JAC_W) jac_pixels<PTS, NID_JAC_W, T>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, acc);
       G = Gn;
     }
+#endif
   }
   // one partial per slice: fixed-order butterfly over the 32 lanes (lanes without a task hold zeros)
 #pragma unroll
