@@ -2270,9 +2270,11 @@ int launch_sorted_pass1(nid_ctx* c, const int* d_list, const int* h_list, int fi
   p.job_list = d_list;
   const int ns = c->max_nslices_prepared;
   ktime_mark(c, 0);
-  launch_hist_w(c, p, ns, first, n, h_list);
-  c->launches--;
-  NID_LAUNCH_CHECK(c, "k_hist_sell");
+  if (ns > 0) {  // (no slices at all: every cell of every prepared pair is inactive; the assembly reports NaN)
+    launch_hist_w(c, p, ns, first, n, h_list);
+    c->launches--;
+    NID_LAUNCH_CHECK(c, "k_hist_sell");
+  }
   ktime_mark(c, 1);
   if (c->span_mode) {
     const int units = c->ncell * n;
@@ -2293,9 +2295,11 @@ int launch_sorted_pass2(nid_ctx* c, const int* d_list, const int* h_list, int fi
   p.job0 = first;
   p.job_list = d_list;
   const int ns = c->max_nslices_prepared;
-  launch_jac_w(c, p, ns, first, n, h_list);
-  c->launches--;
-  NID_LAUNCH_CHECK(c, "k_jac_sell");
+  if (ns > 0) {
+    launch_jac_w(c, p, ns, first, n, h_list);
+    c->launches--;
+    NID_LAUNCH_CHECK(c, "k_jac_sell");
+  }
   ktime_mark(c, 3);
   const int warps = n * c->ncell;
   k_jac_final_sorted<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(p, n);

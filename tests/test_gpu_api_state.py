@@ -290,3 +290,33 @@ def test_span_tasks_and_class_tasks_agree(nid, orc, make_pair, cell, bins, rows,
         np.testing.assert_allclose(a[0][act], b[0][act], rtol=1e-12)
         np.testing.assert_allclose(a[1][act], b[1][act], rtol=1e-12)
         np.testing.assert_allclose(a[2][act], b[2][act], rtol=1e-8, atol=1e-11)
+
+
+def test_every_cell_inactive(nid, orc, make_pair):
+    """Cells of fewer than 300 pixels can never reach the reference's 300-point threshold (computeH.cu:271): everything is
+    NaN, nothing is launched on an empty pixel store, and a solve leaves the pose where it was."""
+    p = make_pair(1000, 120, 160)
+    ctx = nid.Context(120, 160, 8, 10, max_jobs=2)   # 15 x 20 = 300 pixels per cell, minus the ones that leave the image
+    ctx.set_pair(0, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+    pose0 = orc.reference_perturbation(p.T_wc1)
+    M0 = orc.se3_to_mat16(pose0)
+    nc, href = ctx.prepare(0, M0)
+    P = orc.Problem(p.im0, p.depth0, p.im1, p.T_wc0, p.intr, 8, 10)
+    P.set_quirks(0, 1)
+    nco, hrefo = P.prepare(pose0)
+    assert np.array_equal(nc, nco) and np.all(np.isnan(hrefo[nc < 300])) and np.array_equal(np.isnan(href), np.isnan(hrefo))
+    inactive = nc < 300
+    assert 8 <= inactive.sum() < nc.size
+    Ht, Hj, J = ctx.eval(0, M0, True)
+    assert np.all(np.isnan(Ht[inactive])) and np.all(np.isnan(Hj[inactive])) and np.all(np.isnan(J[inactive]))
+    # a geometry in which every single cell is inactive
+    ctx2 = nid.Context(120, 160, 10, 10, max_jobs=2)  # 12 x 16 = 192 pixels per cell
+    ctx2.set_pair(0, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+    nc2, href2 = ctx2.prepare(0, M0)
+    assert np.all(nc2 < 300) and np.all(np.isnan(href2))
+    Ht, Hj, J = ctx2.eval(0, M0, True)
+    assert np.all(np.isnan(Ht)) and np.all(np.isnan(Hj)) and np.all(np.isnan(J))
+    Ht, Hj, _ = ctx2.eval(0, M0, False)
+    assert np.all(np.isnan(Ht))
+    pose, trace, st = ctx2.solve(0, pose0, 3)
+    assert np.array_equal(pose, pose0)
