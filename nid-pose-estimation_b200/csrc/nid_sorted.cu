@@ -36,7 +36,11 @@
 //
 // Memory-system details that were measured to matter: the pixel store is read with evict-first
 // loads and prefetched into L2 two groups ahead, so that L1 stays with the target-image gathers; CTAs are small
-// (128 / 64 threads) at the same number of resident warps; the shared-memory carve-out is requested per kernel.
+// (pass 1: one warp, register budget for 18-20 resident warps; pass 2: two warps at 16 resident warps); the
+// shared-memory carve-out is requested per kernel. Also in this file: the device-side construction of the task and
+// slice tables (k_layout_*), the warp-per-cell assembly for small cells, the optional cp.async.bulk ring of the pixel
+// store and the optional span tasks (both measured slower than what ships, kept as build / run-time options), and
+// kernel 1 on its own (k_warp_sample_jobs).
 #include <cuda_fp16.h>
 #include <math.h>
 
