@@ -63,6 +63,7 @@ int main(int argc, char** argv) {
 
     nid_ctx* ctx = nullptr;
     if (nid_create(&ctx, 0, P.rows, P.cols, cell, bins, 3, 1, 1) != NID_OK) die("nid_create");
+    if (nid_set_option(ctx, "task_px", 16) != NID_OK) die("nid_set_option");  // one pair, one solve: latency-bound (nid_b200.h)
     if (nid_set_pair(ctx, 0, P.depth0.data(), P.im0.data(), P.im1.data(), P.T_wc0.data(), P.intr) != NID_OK) die("nid_set_pair");
     std::vector<int> counter(cell * cell);
     std::vector<double> Href(cell * cell);

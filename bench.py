@@ -509,6 +509,41 @@ def leg_old_gpu(nid, synth, orc, torch):
     return out
 
 
+def leg_single_pair(nid, synth, orc):
+    """Latency of the flow the reference's NID_pose_estimation runs per frame pair (one pair per process,
+    NID_pose_estimation.cpp:253-350): set-up, one evaluation, one optimize(10), each a blocking call, wall clock. Twice:
+    with the library's defaults, and with the 16-pixel tasks its header recommends to latency-bound callers
+    (nid_set_option "task_px"; throughput-bound callers keep 32: 144k against 126k evaluations/s at this geometry)."""
+    p = synth.make_pair(1000, ROWS, COLS)
+    pose0 = orc.reference_perturbation(p.T_wc1)
+    M0 = orc.se3_to_mat16(pose0)
+    out = {"workload": "one 640x480 pair, 4x4 cells, 16 bins, one context (n_pairs=1, max_jobs=1), blocking calls, wall clock per call",
+           "lm": "latency mode: 4 speculative trial poses per round, one CUDA-graph launch per round"}
+    for name, opts in (("default", {}), ("task_px_16", {"task_px": 16})):
+        ctx = nid.Context(ROWS, COLS, 4, 16, n_pairs=1, max_jobs=1)
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+
+        def t(f, n):
+            f()
+            ctx.sync()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                f()
+            ctx.sync()
+            return (time.perf_counter() - t0) / n * 1e3
+        r = {"set_pair_ms": t(lambda: ctx.set_pair(0, p.depth0, p.im0, p.im1, p.T_wc0, p.intr), 10),
+             "prepare_ms": t(lambda: ctx.prepare(0, M0), 10),
+             "eval_cost_ms": t(lambda: ctx.eval(0, M0, False), 50),
+             "eval_cost_jac_ms": t(lambda: ctx.eval(0, M0, True), 50),
+             "solve_ms": t(lambda: ctx.solve(0, pose0), 10)}
+        _, _, st = ctx.solve(0, pose0)
+        r["outer_iters"], r["jac_evals"], r["cost_evals"] = (int(v) for v in st)
+        out[name] = r
+        ctx.close()
+    return out
+
+
 def leg_shim(nid, synth, orc, torch):
     """The reference-API drop-in path: the exact-signature entry points (Calculate3Dpoint, CudaComputeHref,
     g2o::CudaComputeH; csrc/ref_shims.cu) driven like NID_pose_estimation.cpp:253-276 and the LM loop drive them,
@@ -719,7 +754,7 @@ def main():
             c5, c5_pair, c5_all = leg_c5(args, nid, synth, orc, shard, torch, dist, rank, world, local_rank, barrier)
     except Exception as e:  # noqa: BLE001
         c5 = {"error": repr(e)}
-    shim = None
+    shim = single = None
     if rank == 0 and world == 1 and args.old_gpu:
         try:
             old = leg_old_gpu(nid, synth, orc, torch)
@@ -729,6 +764,10 @@ def main():
             shim = leg_shim(nid, synth, orc, torch)
         except Exception as e:  # noqa: BLE001
             shim = {"error": repr(e)}
+        try:
+            single = leg_single_pair(nid, synth, orc)
+        except Exception as e:  # noqa: BLE001
+            single = {"error": repr(e)}
 
     if rank == 0:
         evals = args.steps * n_slots * world
@@ -824,6 +863,8 @@ def main():
             line["old_gpu_path"] = old
         if shim is not None:
             line["reference_api_shim"] = shim
+        if single is not None:
+            line["single_pair_latency"] = single
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -174,7 +174,16 @@ int nid_event_elapsed_ms(nid_ctx* ctx, float* ms);
 /* options: "path" (0 automatic, 1 natural-order kernels, 2 sorted kernels); "keep_hist" (1: keep the
  * normalised histograms of every evaluation for nid_debug_hist);
  * "force_strips" (natural path: CTAs per cell and job; 0 = automatic); "time_kernels" (1: bracket every kernel
- * of nid_eval_staged / nid_eval_jobs with CUDA events and accumulate per-kernel device time; resets) */
+ * of nid_eval_staged / nid_eval_jobs with CUDA events and accumulate per-kernel device time; resets);
+ * "task_px" (sorted path: pixels per task, a multiple of 4 in [8, 256]; default by geometry, 32 for cells of 2048
+ * pixels or more and 16 below; set before nid_prepare*. Latency-bound callers -- one pair, one solve at a time, the
+ * reference's own use -- should set 16: more and shorter slices, 1.68 -> 1.37 ms per 640x480 solve; throughput-bound
+ * callers keep the default. Results for different task lengths agree to rounding, not bit for bit);
+ * "lm_reuse" (1, default: nid_solve_jobs linearises at an accepted trial pose without recomputing its histograms);
+ * "lm_speculate" (0..8, default 4: up to four problems per nid_solve_jobs call run in latency mode, every round
+ * evaluates this many trial poses of the LM schedule at once; 0/1: plain state machine);
+ * "lm_graph" (1, default: a round of the latency mode is one CUDA-graph launch);
+ * "sorted_mode" (1 class tasks, 2 span tasks, 0 automatic) */
 int nid_set_option(nid_ctx* ctx, const char* key, int value);
 
 #ifdef __cplusplus

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <limits>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../host/nid_host_math.hpp"
@@ -266,9 +267,14 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   OKR(dalloc(&c->n_c, P * NC, "n_c")); OKR(dalloc(&c->href, P * NC, "href"));
   OKR(dalloc(&c->cam, P * 4, "cam")); OKR(dalloc(&c->Twc0, P * 16, "Twc0"));
   OKR(dalloc(&c->cnt, P * NC * NID_NCLS, "cnt"));
-  // pixels per task: short tasks when few evaluations are in flight (more threads), longer ones for batches
-  c->task_px = 32;
-  const int min_task_px = 16;
+  // pixels per task, by geometry only (never by the capacity of the context: a shard of a job must compute the same
+  // bits as the whole job). Measured at 640x480, 96 evaluations in flight: 4x4 cells 144k evaluations/s with 32-pixel
+  // tasks, 137k with 24, 126k with 16 (twice the task rows to assemble); 8x8 cells 112k / 110k / 103k; the reference's
+  // default 16x16 cells (1200 pixels, ~5 per reference intensity) 72.5k with 32, 78.7k with 16 or 20, 77k with 12: their
+  // tasks are short anyway and a slice is as long as its longest task. Shorter tasks also cut the latency of a lone
+  // solve (more, shorter slices: 1.68 -> 1.37 ms at 4x4 cells with 16): option "task_px" for latency-bound callers.
+  c->task_px = (long long)c->rb * c->cb < 2048 ? 16 : 32;
+  const int min_task_px = 8;
   c->max_tasks = (int)(N / min_task_px + NC * NID_NCLS + 1);
   c->max_slices = c->max_tasks / 32 + (int)NC + 1;
   // pixel slots per pair: every task is padded to a multiple of 4 and every cell's slices to their longest task
@@ -394,6 +400,9 @@ int nid_destroy(nid_ctx* c) {
   if (c->h_job_pair_ring) cudaFreeHost(c->h_job_pair_ring);
   if (c->h_aux_pose) cudaFreeHost(c->h_aux_pose);
   if (c->h_lm_lists) cudaFreeHost(c->h_lm_lists);
+  destroy_latency_graph(c);
+  if (c->h_lm_stage) cudaFreeHost(c->h_lm_stage);
+  if (c->d_lm_stage) cudaFree(c->d_lm_stage);
   if (c->d_lm_lists) cudaFree(c->d_lm_lists);
   for (int i = 0; i < NID_STAGE_RING; i++) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
   if (c->h_out) cudaFreeHost(c->h_out);
@@ -848,15 +857,35 @@ static int solve_speculative(nid_ctx* c, std::vector<LM>& st, int n, int max_ite
   struct Cand { nidhost::Pose7 pose; double gn[44]; bool valid; };
   std::vector<Cand> cache((size_t)n * K);
   for (auto& q : cache) q.valid = false;
-  if (!c->h_lm_lists) {
-    CU(cudaMallocHost((void**)&c->h_lm_lists, sizeof(int) * 2 * (size_t)c->job_cap), "pinned LM lists");
-    OKR(dalloc(&c->d_lm_lists, 2 * (size_t)c->job_cap, "LM lists"));
+  // one staging block per round: the poses of all n * K slots, then the list of the slots in use (one H2D copy); the
+  // kernels read both from there for the duration of the solve
+  const int nslots = n * K;
+  const size_t stage_bytes = sizeof(double) * 16 * (size_t)c->job_cap + sizeof(int) * (size_t)c->job_cap;
+  if (!c->h_lm_stage) {
+    CU(cudaMallocHost((void**)&c->h_lm_stage, stage_bytes), "pinned LM staging");
+    CU(cudaMalloc((void**)&c->d_lm_stage, stage_bytes), "LM staging");
   }
+  struct Swap {  // restores the context's pose buffers on every way out
+    nid_ctx* c; double* poses; double* h_poses;
+    ~Swap() { c->poses = poses; c->h_poses = h_poses; }
+  } swap{c, c->poses, c->h_poses};
+  c->poses = reinterpret_cast<double*>(c->d_lm_stage);
+  c->h_poses = reinterpret_cast<double*>(c->h_lm_stage);
+  int* const list = reinterpret_cast<int*>(c->h_poses + 16 * (size_t)nslots);
+  int* const d_list = reinterpret_cast<int*>(c->poses + 16 * (size_t)nslots);
+  for (int j = 0; j < n; j++)
+    for (int k = 0; k < K; k++) c->h_job_pair[j * K + k] = st[j].pair;
+  CU(cudaMemcpyAsync(c->job_pair, c->h_job_pair, sizeof(int) * nslots, cudaMemcpyHostToDevice, c->stream), "H2D job_pair");
   CU(cudaStreamSynchronize(c->stream), "sync before LM");
   auto same_pose = [](const nidhost::Pose7& a, const nidhost::Pose7& b) {
     return memcmp(a.t, b.t, sizeof(a.t)) == 0 && memcmp(a.q, b.q, sizeof(a.q)) == 0;
   };
+  const bool tt_on = getenv("NID_LM_TIMES") != nullptr;
+  double tt[4] = {0, 0, 0, 0};
+  int tt_rounds = 0;
+  auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (;;) {
+    const double t0 = now();
     // 1. let every problem consume what the cache already holds
     bool progress = true;
     while (progress) {
@@ -876,7 +905,6 @@ static int solve_speculative(nid_ctx* c, std::vector<LM>& st, int n, int max_ite
     }
     // 2. the next round: per unfinished problem the pose it waits for and the trials that would follow rejections
     int nj = 0;
-    int* list = c->h_lm_lists;
     for (int j = 0; j < n; j++) {
       LM& s = st[j];
       for (int k = 0; k < K; k++) cache[(size_t)j * K + k].valid = false;
@@ -888,8 +916,7 @@ static int solve_speculative(nid_ctx* c, std::vector<LM>& st, int n, int max_ite
         q.pose = sim.est;
         q.valid = true;
         nidhost::pose_to_mat16(sim.est, c->h_poses + 16 * (size_t)slot);
-        c->h_job_pair[slot] = s.pair;
-        list[nj++] = slot;
+        nj++;
         if (sim.phase != 1 || sim.qmax + 1 >= 10) break;  // only trial poses have successors; maxTrials = 10
         // the trial after a rejection of this one (lm_absorb's else branch, then lm_start_trial)
         sim.lambda *= sim.ni;
@@ -900,17 +927,27 @@ static int solve_speculative(nid_ctx* c, std::vector<LM>& st, int n, int max_ite
       }
     }
     if (nj == 0) break;
-    const int nslots = n * K;
-    CU(cudaMemcpyAsync(c->poses, c->h_poses, sizeof(double) * 16 * nslots, cudaMemcpyHostToDevice, c->stream), "H2D poses");
-    CU(cudaMemcpyAsync(c->job_pair, c->h_job_pair, sizeof(int) * nslots, cudaMemcpyHostToDevice, c->stream), "H2D job_pair");
-    CU(cudaMemcpyAsync(c->d_lm_lists, list, sizeof(int) * nj, cudaMemcpyHostToDevice, c->stream), "H2D job list");
-    OKR(launch_sorted_pass1(c, c->d_lm_lists, list, 0, nj, 1));
-    OKR(launch_sorted_pass2(c, c->d_lm_lists, list, 0, nj));
-    OKR(launch_gn_list(c, c->d_lm_lists, 0, nj, delta, 1));
-    CU(cudaMemcpyAsync(c->h_out, c->gn, sizeof(double) * 44 * nslots, cudaMemcpyDeviceToHost, c->stream), "D2H gn");
+    const double t1 = now();
+    // every slot is evaluated every round (one fixed chain: see launch_latency_round); the slots this round has no use
+    // for repeat their problem's first pose and their results are ignored
+    for (int j = 0; j < n; j++) {
+      for (int k = 0; k < K; k++) {
+        const int slot = j * K + k;
+        if (cache[slot].valid) continue;
+        if (k > 0) memcpy(c->h_poses + 16 * (size_t)slot, c->h_poses + 16 * (size_t)(j * K), sizeof(double) * 16);
+        else nidhost::pose_to_mat16(st[j].est, c->h_poses + 16 * (size_t)slot);
+      }
+    }
+    for (int i = 0; i < nslots; i++) list[i] = i;
+    OKR(launch_latency_round(c, nslots, d_list, list, sizeof(double) * 16 * nslots + sizeof(int) * nslots, delta, c->h_out));
+    const double t2 = now();
     CU(cudaStreamSynchronize(c->stream), "sync lm");
-    for (int i = 0; i < nj; i++) memcpy(cache[list[i]].gn, c->h_out + 44 * (size_t)list[i], sizeof(double) * 44);
+    const double t3 = now();
+    for (int i = 0; i < nslots; i++)
+      if (cache[i].valid) memcpy(cache[i].gn, c->h_out + 44 * (size_t)i, sizeof(double) * 44);
+    tt[0] += t1 - t0; tt[1] += t2 - t1; tt[2] += t3 - t2; tt[3] += now() - t3; tt_rounds++;
   }
+  if (tt_on) fprintf(stderr, "lm rounds %d: host %.1f issue %.1f wait %.1f copy %.1f us per round\n", tt_rounds, tt[0] / tt_rounds, tt[1] / tt_rounds, tt[2] / tt_rounds, tt[3] / tt_rounds);
   return NID_OK;
 }
 
@@ -1231,13 +1268,14 @@ int nid_set_option(nid_ctx* c, const char* key, int value) {
   }
   if (!strcmp(key, "keep_hist")) { c->opt_keep_hist = value; return NID_OK; }
   if (!strcmp(key, "lm_reuse")) { c->opt_lm_reuse = value ? 1 : 0; return NID_OK; }
+  if (!strcmp(key, "lm_graph")) { c->opt_lm_graph = value ? 1 : 0; return NID_OK; }
   if (!strcmp(key, "lm_speculate")) {
     if (value < 0 || value > 8) { set_error("lm_speculate must be 0 (off) .. 8 trial poses per round"); return NID_ERR_ARG; }
     c->opt_lm_spec = value;
     return NID_OK;
   }
   if (!strcmp(key, "task_px")) {
-    if (value < 16 || value > NID_TASK_PX_MAX || (value & 3)) { set_error("task_px must be a multiple of 4 in [16, 256]"); return NID_ERR_ARG; }
+    if (value < 8 || value > NID_TASK_PX_MAX || (value & 3)) { set_error("task_px must be a multiple of 4 in [8, 256]"); return NID_ERR_ARG; }
     if (value != c->task_px) {
       c->task_px = value;
       std::fill(c->pair_prepared.begin(), c->pair_prepared.end(), 0);  // the pixel store is laid out per task

@@ -81,6 +81,7 @@ struct EvalParams {
 
 }  // namespace nid
 
+namespace nid { struct LatencyGraph; }
 struct nid_ctx {
   int device = 0;
   int rows = 0, cols = 0, cell = 0, bins = 0, degree = 3;
@@ -194,6 +195,12 @@ struct nid_ctx {
   // LM driver: per half-batch job lists (pinned mirror + device copy), [2 halves][2 lists][max_jobs]
   int* h_lm_lists = nullptr;
   int* d_lm_lists = nullptr;
+  void* h_lm_stage = nullptr;  // latency mode: poses + slot list of a round, pinned / device
+  void* d_lm_stage = nullptr;
+  nid::LatencyGraph* lm_graph = nullptr;  // latency mode: the captured round (nid_sorted.cu)
+  const void* last_hist_func = nullptr;     // the pixel-kernel instantiations the last launch used (graph node lookup)
+  const void* last_jac_func = nullptr;
+  int opt_lm_graph = 1;
   int opt_lm_spec = 4;         // latency mode of nid_solve_jobs (few problems): trial poses evaluated per round and problem
   int opt_lm_reuse = 1;        // a cost+Jacobian job at the pose of the accepted trial reuses that trial's histograms and tables
   double* lm_trace = nullptr;  // set by nid_solve for the duration of one call
@@ -208,6 +215,29 @@ struct nid_ctx {
 namespace nid {
 // the i-th job of a launch
 __host__ __device__ inline int job_at(const EvalParams& p, int i) { return p.job_list ? p.job_list[p.job0 + i] : p.job0 + i; }
+#ifdef __CUDACC__
+// a11: entry `ent` of the Huber-weighted Gauss-Newton block of a job, summed over its active cells in cell order
+// (base_unary_edge.hpp:43-72, robust_kernel_impl.cpp:78-90, sparse_optimizer.cpp:102-116):
+// entry 0 chi2, 1..36 H (row-major), 37..42 b, 43 the number of active cells.
+__device__ __forceinline__ double gn_entry(const EvalParams& p, int job, int ent) {
+  double acc = 0.0;
+  const double* e = p.err + (size_t)job * p.ncell;
+  const double* J = p.der + (size_t)job * p.ncell * 6;
+  for (int c = 0; c < p.ncell; c++) {
+    const double ec = e[c];
+    if (isnan(ec)) continue;
+    const double chi = ec * ec;
+    double rho0, rho1;
+    if (chi <= p.huber_dsqr) { rho0 = chi; rho1 = 1.0; }
+    else { const double sq = sqrt(chi); rho0 = 2 * sq * p.huber_delta - p.huber_dsqr; rho1 = p.huber_delta / sq; }
+    if (ent == 0) acc += rho0;
+    else if (ent <= 36) { const int i = (ent - 1) / 6, j = (ent - 1) % 6; acc += J[6 * c + i] * rho1 * J[6 * c + j]; }
+    else if (ent <= 42) { const int i = ent - 37; acc -= rho1 * J[6 * c + i] * ec; }
+    else acc += 1.0;
+  }
+  return acc;
+}
+#endif
 void set_error(const std::string& s);
 int check_cuda(cudaError_t e, const char* what);
 EvalParams make_params(nid_ctx* c, int n_jobs);
@@ -242,6 +272,9 @@ int launch_eval_sorted(nid_ctx* c, int job0, int n_jobs, int n_jobs_total, int w
 int launch_sorted_pass1(nid_ctx* c, const int* d_list, const int* h_list, int first, int n, int tables);
 int launch_sorted_pass2(nid_ctx* c, const int* d_list, const int* h_list, int first, int n);
 int launch_gn_list(nid_ctx* c, const int* d_list, int first, int n, double delta, int want_jac);
+int launch_sorted_tail_gn(nid_ctx* c, const int* d_list, const int* h_list, int first, int n, double delta, double* gn_out);
+int launch_latency_round(nid_ctx* c, int nslots, const int* d_list, const int* h_list, size_t h2d_bytes, double delta, double* gn_out);
+void destroy_latency_graph(nid_ctx* c);
 int launch_href(nid_ctx* c, int pair0, int n);
 
 // kernel launchers (nid_kernels.cu)

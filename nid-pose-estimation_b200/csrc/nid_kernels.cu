@@ -455,24 +455,8 @@ __global__ void k_gn(EvalParams p, int n_jobs, int want_jac) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_jobs * 44) return;
   const int job = job_at(p, idx / 44), ent = idx % 44;
-  idx = job * 44 + ent;
   if (!want_jac && ent >= 1 && ent <= 42) return;
-  double acc = 0.0;
-  const double* e = p.err + (size_t)job * p.ncell;
-  const double* J = p.der + (size_t)job * p.ncell * 6;
-  for (int c = 0; c < p.ncell; c++) {
-    double ec = e[c];
-    if (isnan(ec)) continue;
-    double chi = ec * ec;
-    double rho0, rho1;
-    if (chi <= p.huber_dsqr) { rho0 = chi; rho1 = 1.0; }
-    else { double sq = sqrt(chi); rho0 = 2 * sq * p.huber_delta - p.huber_dsqr; rho1 = p.huber_delta / sq; }
-    if (ent == 0) acc += rho0;
-    else if (ent <= 36) { int i = (ent - 1) / 6, j = (ent - 1) % 6; acc += J[6 * c + i] * rho1 * J[6 * c + j]; }
-    else if (ent <= 42) { int i = ent - 37; acc -= rho1 * J[6 * c + i] * ec; }
-    else acc += 1.0;
-  }
-  p.gn[idx] = acc;
+  p.gn[job * 44 + ent] = gn_entry(p, job, ent);
 }
 
 // ------------------------------------------------------------------------------------------------

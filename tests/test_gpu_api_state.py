@@ -246,6 +246,50 @@ def test_lm_reuse_of_the_accepted_trial_is_bit_identical(nid, orc, make_pair, ce
     assert np.max(np.abs(out1[2] - poseo)) < 1e-7
 
 
+def test_latency_mode_graph_survives_changes_of_the_context(nid, orc, make_pair):
+    """The latency mode replays one captured CUDA graph per round (nid_sorted.cu, launch_latency_round). Everything the
+    graph captured by value may change between solves -- another pair in the slot, another prepare pose (other slice
+    counts), another task length, another Huber delta, another number of problems -- and every solve must equal the
+    same solve without the graph, bit for bit."""
+    pairs = [make_pair(1000 + i, 120, 160) for i in range(3)]
+    ctx = nid.Context(120, 160, 2, 12, n_pairs=3, max_jobs=3)
+    pose0 = []
+    for i, p in enumerate(pairs):
+        ctx.set_pair(i, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+        pose0.append(orc.reference_perturbation(p.T_wc1))
+        ctx.prepare(i, orc.se3_to_mat16(pose0[i]))
+    pose0 = np.stack(pose0)
+
+    def both(f):
+        ctx.set_option("lm_graph", 1)
+        a = f()
+        a2 = f()  # replay of the cached graph
+        ctx.set_option("lm_graph", 0)
+        b = f()
+        for x, y, z in zip(a, a2, b):
+            assert np.array_equal(x, y) and np.array_equal(x, z)
+        return a
+
+    both(lambda: ctx.solve(0, pose0[0]))
+    both(lambda: ctx.solve(1, pose0[1], 10, 0.5))                      # another pair, another delta
+    both(lambda: ctx.solve_jobs(pose0, np.arange(3, dtype=np.int32)))  # three problems: other slot count
+    q = make_pair(1010, 120, 160, invalid_depth_frac=0.3)              # fewer valid pixels: other slice counts
+    ctx.set_pair(0, q.depth0, q.im0, q.im1, q.T_wc0, q.intr)
+    q0 = orc.reference_perturbation(q.T_wc1)
+    ctx.prepare(0, orc.se3_to_mat16(q0))
+    pose, trace, st = both(lambda: ctx.solve(0, q0))
+    ctx.set_option("task_px", 32)
+    for i in range(3):
+        ctx.prepare(i, orc.se3_to_mat16(pose0[i] if i else q0))
+    pose32, trace32, st32 = both(lambda: ctx.solve(0, q0))
+    assert np.array_equal(st, st32) and np.max(np.abs(pose - pose32)) < 1e-9  # (another task length: another summation order)
+    P = orc.Problem(q.im0, q.depth0, q.im1, q.T_wc0, q.intr, 2, 12, threads=4)
+    P.set_quirks(0, 1)
+    P.prepare(q0)
+    poseo, its, traceo, counts = P.optimize(q0, 10)
+    assert st[0] == its and np.max(np.abs(pose - poseo)) < 1e-7
+
+
 @pytest.mark.parametrize("cell,bins,rows,cols", [(8, 10, 240, 320), (16, 10, 480, 640), (4, 16, 120, 160), (5, 20, 200, 250)])
 def test_span_tasks_and_class_tasks_agree(nid, orc, make_pair, cell, bins, rows, cols):
     """Small cells take tasks per reference span (16 accumulations per pixel, long tasks) instead of tasks per reference

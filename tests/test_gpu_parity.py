@@ -382,7 +382,7 @@ def test_integer_aligned_warp(nid, orc, make_pair, synth, path):
     assert _jrel(J, Jo) < 1e-8
 
 
-@pytest.mark.parametrize("task_px", [16, 32, 128, 256])
+@pytest.mark.parametrize("task_px", [8, 16, 32, 128, 256])
 def test_task_length_does_not_change_results(nid, orc, make_pair, task_px):
     p = make_pair(1000, 240, 320)
     P, ctx, pose0 = _setup(nid, orc, p, 4, 16, path=SORTED)

@@ -15,6 +15,9 @@ for path in (1, 2):
     try:
         ctx = nid.Context(rows, cols, cell, bins, n_pairs=pairs, max_jobs=pairs)
         ctx.set_option("path", path)
+        for kv in filter(None, os.environ.get("NID_OPTS", "").split(",")):
+            k, v = kv.split("=")
+            ctx.set_option(k, int(v))
     except Exception as e:
         print("path", path, "unavailable:", e)
         continue
