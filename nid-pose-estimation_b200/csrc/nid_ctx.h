@@ -201,6 +201,7 @@ struct nid_ctx {
   const void* last_hist_func = nullptr;     // the pixel-kernel instantiations the last launch used (graph node lookup)
   const void* last_jac_func = nullptr;
   int opt_lm_graph = 1;
+  int opt_asm_wide = 1;  // 1024-thread assembly when there are fewer (cell, job) units than SMs
   int opt_lm_spec = 4;         // latency mode of nid_solve_jobs (few problems): trial poses evaluated per round and problem
   int opt_lm_reuse = 1;        // a cost+Jacobian job at the pose of the accepted trial reuses that trial's histograms and tables
   double* lm_trace = nullptr;  // set by nid_solve for the duration of one call

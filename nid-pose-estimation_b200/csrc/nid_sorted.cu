@@ -1052,7 +1052,7 @@ __device__ __forceinline__ void assemble_body(const EvalParams& p, int want_jac)
   unsigned long long tr_[12];
   if (threadIdx.x == 0) tr_[0] = gtimer();
 #endif
-  __shared__ double scratch[NT / 32];
+  __shared__ double scratch[8];
   __shared__ int s_cts[NID_NCLS + 1];
   __shared__ int s_bnd[NT / 3 + 2];
   __shared__ int s_span[NID_SORTED_MAX_BINS];  // first class of every span (+ end)
@@ -1215,8 +1215,9 @@ __device__ __forceinline__ void assemble_body(const EvalParams& p, int want_jac)
   // ---- P_j: item (kk, r, t) sums the classes of span r-kk (in class order: the summation order is part of the result)
   {
     const unsigned mdiv = (1048576u + (unsigned)B - 1u) / (unsigned)B;  // idx / B == (idx * mdiv) >> 20 for idx < 2^20 / B
-    for (int kk = 0; kk < 4; kk++)
-      for (int idx = threadIdx.x; idx < BB; idx += blockDim.x) {
+    for (int item = threadIdx.x; item < 4 * BB; item += blockDim.x) {
+      const int kk = item / BB, idx = item - kk * BB;
+      {
         const int r = (int)(((unsigned)idx * mdiv) >> 20), tt = idx - r * B;
         const int k = r - kk;
         double a = 0.0;
@@ -1237,41 +1238,60 @@ __device__ __forceinline__ void assemble_body(const EvalParams& p, int want_jac)
         }
         part[kk * BB + idx] = a;
       }
+    }
   }
-  // ---- P_t: thread (g, tt) sums classes g, g+ng, ... ; groups are then added in order
-  {
-    const int ng = NT / B;
+  // Every sum below has ONE order whatever the CTA size (the 128-, 256- and 1024-thread variants of this kernel -- the
+  // last one for a handful of evaluations in flight -- produce the same bits):
+  // ---- P_t: ngt = max(1, 128 / B) groups; group g sums classes g, g + ngt, ... in order, the groups are then added in order
+  const int ngt = max(1, 128 / B);
+  if ((int)threadIdx.x < ngt * B) {
     const int g = threadIdx.x / B, tt = threadIdx.x % B;
     double a = 0.0;
-    if (g < ng)
-      for (int v = g; v < NID_NCLS; v += ng) a += hvs[v * B + tt];
+    for (int v = g; v < NID_NCLS; v += ngt) a += hvs[v * B + tt];
     red[threadIdx.x] = a;
   }
   __syncthreads();
   ASM_T(3);
-  double ej = 0.0, et = 0.0;
   for (int idx = threadIdx.x; idx < BB; idx += blockDim.x) {
     const double a = ((part[idx] + part[BB + idx]) + part[2 * BB + idx]) + part[3 * BB + idx];
     const double q = a / (double)nc;
     Pall[idx] = q;
     const double lg = (q < kSigma) ? 0.0 : log2(q);
-    ej -= q * lg;
-    part[idx] = (q < kSigma) ? 0.0 : 1.0 + lg;  // this thread's own slot: 1 + log2 P_j for the tables below
+    part[BB + idx] = -(q * lg);                 // entropy term of this entry (slots idx of the four planes are this thread's)
+    part[idx] = (q < kSigma) ? 0.0 : 1.0 + lg;  // 1 + log2 P_j for the tables below
   }
   if ((int)threadIdx.x >= NT - B) {  // the last B threads (idle in the loop above for B <= 22)
     const int tt = threadIdx.x - (NT - B);
-    const int ng = NT / B;
     double a = 0.0;
-    for (int g = 0; g < ng; g++) a += red[g * B + tt];
+    for (int g = 0; g < ngt; g++) a += red[g * B + tt];
     const double q = a / (double)nc;
     Pall[BB + tt] = q;
     const double lg = (q < kSigma) ? 0.0 : log2(q);
-    et -= q * lg;
-    red[tt] = (q < kSigma) ? 0.0 : 1.0 + lg;  // (column tt of red belongs to this thread)
+    red[B + tt] = -(q * lg);                    // entropy term of bin tt (column tt of red belongs to this thread)
+    red[tt] = (q < kSigma) ? 0.0 : 1.0 + lg;
   }
+  __syncthreads();
   ASM_T(4);
-  const double Hj = block_sum(ej, scratch);
-  const double Ht = block_sum(et, scratch);
+  // ---- H_j: 128 partial sums (partial j takes the terms j, j + 128, ... in order), an xor tree inside each of the four
+  // warps, the four warp sums in order. H_t: the same with one warp's worth of partials.
+  {
+    double ej = 0.0, et = 0.0;
+    if (threadIdx.x < 128) {
+      for (int idx = threadIdx.x; idx < BB; idx += 128) ej += part[BB + idx];
+      if (threadIdx.x < 32)
+        for (int tt = threadIdx.x; tt < B; tt += 32) et += red[B + tt];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        ej += __shfl_xor_sync(0xffffffffu, ej, off);
+        et += __shfl_xor_sync(0xffffffffu, et, off);
+      }
+      if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = ej;
+      if (threadIdx.x == 0) scratch[4] = et;
+    }
+  }
+  __syncthreads();
+  const double Hj = ((scratch[0] + scratch[1]) + scratch[2]) + scratch[3];
+  const double Ht = scratch[4];
   ASM_T(5);
   const double Href = p.href[pair * p.ncell + c];
   if (threadIdx.x == 0) {
@@ -1301,6 +1321,11 @@ __global__ void __launch_bounds__(NID_ASM_THREADS, NID_ASM_MINB) k_assemble(Eval
 }
 __global__ void __launch_bounds__(NID_ASM_SMALL, 2 * NID_ASM_MINB) k_assemble_small(EvalParams p, int want_jac) {
   assemble_body<NID_ASM_SMALL>(p, want_jac);
+}
+// a handful of evaluations in flight (a lone LM solve): fewer CTAs than SMs, so every cell gets a whole SM's worth of threads
+#define NID_ASM_WIDE 1024
+__global__ void __launch_bounds__(NID_ASM_WIDE, 1) k_assemble_wide(EvalParams p, int want_jac) {
+  assemble_body<NID_ASM_WIDE>(p, want_jac);
 }
 
 // Assembly for small cells (the reference's default 16x16 cells hold ~1200 pixels, i.e. ~130 task rows and at most a
@@ -2232,8 +2257,8 @@ static bool assemble_warp(const nid_ctx* c) { return NID_ASM_WARP && assemble_sm
 static size_t assemble_warp_smem(const nid_ctx* c) {
   return sizeof(double) * (size_t)NID_ASMW_WARPS * (32 / c->bins) * ((size_t)c->bins * c->bins + c->bins);
 }
-size_t assemble_smem(const nid_ctx* c) {
-  return sizeof(double) * ((size_t)5 * c->bins * c->bins + c->bins + NID_ASM_THREADS + (size_t)NID_NCLS * c->bins + (NID_FEW_BINS(c->bins) ? 1024 : 0));
+size_t assemble_smem(const nid_ctx* c, int threads) {
+  return sizeof(double) * ((size_t)5 * c->bins * c->bins + c->bins + threads + (size_t)NID_NCLS * c->bins + (NID_FEW_BINS(c->bins) ? 1024 : 0));
 }
 
 // Host side of the geometry table: job (first + i) -> gt.g[i] from the staged poses (pinned mirror), the pair's
@@ -2392,8 +2417,10 @@ int launch_sorted_pass1(nid_ctx* c, const int* d_list, const int* h_list, int fi
   } else if (assemble_warp(c)) {
     const int units = c->ncell * n;
     k_assemble_warp<<<(units + NID_ASMW_WARPS - 1) / NID_ASMW_WARPS, NID_ASMW_WARPS * 32, assemble_warp_smem(c), c->stream>>>(p, tables, n);
-  } else if (assemble_small(c)) k_assemble_small<<<dim3(c->ncell, n), NID_ASM_SMALL, assemble_smem(c), c->stream>>>(p, tables);
-  else k_assemble<<<dim3(c->ncell, n), NID_ASM_THREADS, assemble_smem(c), c->stream>>>(p, tables);
+  } else if (c->opt_asm_wide && c->ncell * n <= c->sm_count) {
+    k_assemble_wide<<<dim3(c->ncell, n), NID_ASM_WIDE, assemble_smem(c, NID_ASM_WIDE), c->stream>>>(p, tables);
+  } else if (assemble_small(c)) k_assemble_small<<<dim3(c->ncell, n), NID_ASM_SMALL, assemble_smem(c, NID_ASM_THREADS), c->stream>>>(p, tables);
+  else k_assemble<<<dim3(c->ncell, n), NID_ASM_THREADS, assemble_smem(c, NID_ASM_THREADS), c->stream>>>(p, tables);
   NID_LAUNCH_CHECK(c, "k_assemble");
   ktime_mark(c, 2);
   return NID_OK;
@@ -2652,8 +2679,9 @@ int sorted_init(nid_ctx* c) {
   NID_SMEM_ATTR_PX(true, NID_GEO_LARGE)
   NID_SMEM_ATTR_PX(false, NID_GEO_LARGE)
 #undef NID_SMEM_ATTR_PX
-  NID_SMEM_ATTR(k_assemble, assemble_smem(c));
-  NID_SMEM_ATTR(k_assemble_small, assemble_smem(c));
+  NID_SMEM_ATTR(k_assemble, assemble_smem(c, NID_ASM_THREADS));
+  NID_SMEM_ATTR(k_assemble_small, assemble_smem(c, NID_ASM_THREADS));
+  NID_SMEM_ATTR(k_assemble_wide, assemble_smem(c, NID_ASM_WIDE));
   if (c->bins <= 32) { NID_SMEM_ATTR(k_assemble_warp, assemble_warp_smem(c)); NID_SMEM_ATTR(k_assemble_span, assemble_warp_smem(c)); }
   if (NID_FEW_BINS(c->bins)) {
 #define NID_SMEM_ATTR_SPAN(NG)                                              \
