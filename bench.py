@@ -337,8 +337,11 @@ def leg_c4(args, nid, synth, orc, shard, torch, dist, rank, world, local_rank, b
     pose0 = np.stack(pose0)
     init = np.stack([orc.se3_to_mat16(q) for q in pose0])
     n = len(pairs)
-    chunk = min(n, 128)          # problems per nid_solve_jobs call
-    block = min(n, 256)          # pairs per set-up submission
+    # pairs per set-up submission. Smaller blocks for many ranks (128 pairs per rank at N=8) were measured and do not pay:
+    # one block of 128 31.6 ms, two of 64 32.8 ms, four of 32 38.3 ms -- solves of fewer problems per call fill the device
+    # less, and the concurrent upload competes with them
+    block = min(n, 256)
+    chunk = min(block, 128)      # problems per nid_solve_jobs call
     # two contexts ping-pong: while one solves its block of pairs, the other one's block is uploaded and prepared
     # (set-up runs on its own host thread and its own stream; the ctypes calls release the GIL)
     ctxs = [nid.Context(ROWS, COLS, CELL, BINS, n_pairs=block, max_jobs=chunk, device=local_rank) for _ in range(2 if n > block else 1)]
@@ -386,7 +389,7 @@ def leg_c4(args, nid, synth, orc, shard, torch, dist, rank, world, local_rank, b
     assert np.all(np.isfinite(table)), "c4: non-finite rows in the gathered table"
     res = {"value": n_total / el, "unit": "pairs/s", "pairs": n_total, "pairs_per_rank": int(n), "seconds": el,
            "first_block_setup_seconds": setup_s, "scaling": "strong", "sharding": "block (shard.py)",
-           "overlap": "two contexts ping-pong: the set-up of the next block of 256 pairs overlaps the solves of the current one",
+           "overlap": f"two contexts ping-pong: the set-up of the next block of {block} pairs overlaps the solves of the current one",
            "gather": "NCCL all_gather of {pose7, outer_iters, jac_evals, cost_evals} per pair" if world > 1 else "single rank",
            "mean_outer_iters": float(table[:, 7].mean()), "mean_jac_evals": float(table[:, 8].mean()),
            "mean_cost_evals": float(table[:, 9].mean()), "host_generation_seconds_untimed": gen_s,
