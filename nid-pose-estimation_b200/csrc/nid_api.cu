@@ -67,6 +67,7 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.ht = c->ht; p.hj = c->hj; p.err = c->err; p.der = c->der; p.gn = c->gn;
   p.sd0 = c->sd0; p.sd1 = c->sd1; p.sd2 = c->sd2; p.sid = c->sid;
   p.sv = c->sv; p.span_mode = c->span_mode ? 1 : 0;
+  p.stage_bulk = (c->opt_stage_bulk < 0 ? (long long)c->rb * c->cb < 2048 : c->opt_stage_bulk) ? 1 : 0;
   p.sl_off = c->sl_off; p.sl_task = c->sl_task; p.sl_cell = c->sl_cell; p.nslices = c->nslices;
   p.sell_cap = c->sell_cap; p.max_slices = c->max_slices; p.Twc0 = c->Twc0;
   p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start; p.cell_slice_start = c->cell_slice_start;
@@ -134,7 +135,10 @@ int ensure_job_buffers(nid_ctx* c) {
       c->g_rows = rows_per_task;
     }
     if (!c->jpart_s) OKR(dalloc(&c->jpart_s, J * (size_t)c->max_slices * 6, "jpart_s"));  // one partial per slice
-    if (!c->wv) OKR(dalloc(&c->wv, J * NC * hs, "wv"));
+    if (!c->wv) {
+      OKR(dalloc(&c->wv, J * NC * (size_t)nid::wv_stride(c->bins), "wv"));
+      CU(cudaMemset(c->wv, 0, sizeof(double) * J * NC * (size_t)nid::wv_stride(c->bins)), "memset wv");  // (the padding is copied, never used)
+    }
   } else if (!c->part) {
     c->part_slots = J + 2 * (size_t)c->sm_count + 64;
     OKR(dalloc(&c->part, c->part_slots * NC * hs, "part"));
@@ -1270,6 +1274,7 @@ int nid_set_option(nid_ctx* c, const char* key, int value) {
   if (!strcmp(key, "lm_reuse")) { c->opt_lm_reuse = value ? 1 : 0; return NID_OK; }
   if (!strcmp(key, "lm_graph")) { c->opt_lm_graph = value ? 1 : 0; return NID_OK; }
   if (!strcmp(key, "asm_wide")) { c->opt_asm_wide = value ? 1 : 0; return NID_OK; }
+  if (!strcmp(key, "stage_bulk")) { c->opt_stage_bulk = value < 0 ? -1 : (value ? 1 : 0); return NID_OK; }
   if (!strcmp(key, "lm_speculate")) {
     if (value < 0 || value > 8) { set_error("lm_speculate must be 0 (off) .. 8 trial poses per round"); return NID_ERR_ARG; }
     c->opt_lm_spec = value;

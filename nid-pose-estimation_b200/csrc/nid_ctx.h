@@ -57,6 +57,7 @@ struct EvalParams {
   const unsigned* sid;  // [n_pairs][sell_cap] (row << 16) | col, 0xFFFFFFFF = padding
   uint8_t* sv;          // span tasks only: [n_pairs][sell_cap] reference intensity of the pixel in that slot
   int span_mode;        // tasks are (cell, reference span) runs instead of (cell, reference intensity) runs
+  int stage_bulk;       // pass 2 stages the cell's log tables by a bulk copy (small cells: short slices)
   const int* sl_off;    // [n_pairs][max_slices+1] first pixel slot of every slice (multiples of 128)
   const int* sl_task;   // [n_pairs][max_slices*32] task of every lane, -1 = none
   const int* sl_cell;   // [n_pairs][max_slices] cell of every slice
@@ -201,6 +202,7 @@ struct nid_ctx {
   const void* last_hist_func = nullptr;     // the pixel-kernel instantiations the last launch used (graph node lookup)
   const void* last_jac_func = nullptr;
   int opt_lm_graph = 1;
+  int opt_stage_bulk = -1;  // pass 2 table staging by cp.async.bulk: -1 by geometry (cells under 2048 pixels), 0 never, 1 always
   int opt_asm_wide = 1;  // 1024-thread assembly when there are fewer (cell, job) units than SMs
   int opt_lm_spec = 4;         // latency mode of nid_solve_jobs (few problems): trial poses evaluated per round and problem
   int opt_lm_reuse = 1;        // a cost+Jacobian job at the pose of the accepted trial reuses that trial's histograms and tables
@@ -215,6 +217,15 @@ struct nid_ctx {
 
 namespace nid {
 // the i-th job of a launch
+// up to this many bins pass 2 stages the cell's log tables per warp and k_assemble the reference weight table in shared memory;
+// beyond, the staging areas would cost a resident CTA per SM and the tables are read through L1
+#define NID_FEW_BINS(bins) ((bins) <= 20)
+// Layout of the scaled log tables W | V of one (job, cell), written by the assembly and read by pass 2: B rows of W at a
+// stride of wv_row(B) doubles -- B + 1 where pass 2 stages the block in shared memory (its lanes then read four rows
+// each without bank conflicts, and the block is staged by ONE bulk copy, byte for byte) -- then the B entries of V;
+// the block is padded to an even number of doubles (bulk copies move 16-byte units).
+__host__ __device__ inline int wv_row(int B) { return NID_FEW_BINS(B) ? B + 1 : B; }
+__host__ __device__ inline int wv_stride(int B) { return (B * wv_row(B) + B + 1) & ~1; }
 __host__ __device__ inline int job_at(const EvalParams& p, int i) { return p.job_list ? p.job_list[p.job0 + i] : p.job0 + i; }
 #ifdef __CUDACC__
 // a11: entry `ent` of the Huber-weighted Gauss-Newton block of a job, summed over its active cells in cell order

@@ -25,7 +25,14 @@ for (rows, cols, cell, bins, mode) in ((120, 160, 2, 16, 0), (120, 160, 4, 10, 0
     ctx.eval_jobs(poses, jp, True)
     ctx.eval(0, M0, False)
     ctx.solve_jobs(np.stack([pose0] * 12), jp, 3)   # lock-step, two half-batches, job lists
-    ctx.solve(0, pose0, 2)                          # latency mode (speculative trial poses)
+    ctx.solve(0, pose0, 2)                          # latency mode (speculative trial poses, one graph launch per round)
+    ctx.solve(0, pose0, 2)                          # replay of the cached graph (parameter update of the pixel-kernel nodes)
+    ctx.set_option("lm_graph", 0)
+    ctx.solve(0, pose0, 2)                          # the same round as plain launches (k_tail_gn writes to pinned memory)
+    ctx.set_option("asm_wide", 0)
+    ctx.eval_jobs(poses, jp, True)                  # 128/256-thread assembly instead of the 1024-thread one
+    ctx.set_option("asm_wide", 1)
+    ctx.set_option("lm_graph", 1)
     ctx.warp_sample_jobs(poses, jp)                 # mixed fp64 / u16 depth planes -> fp64 variant
     ctx.warp_sample_jobs(poses[:4], np.array([1, 2, 1, 2], dtype=np.int32))  # u16 variant
     ctx.hard_eval_jobs(poses, jp)
