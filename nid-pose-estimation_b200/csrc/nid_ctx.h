@@ -60,6 +60,7 @@ struct EvalParams {
   int stage_bulk;       // pass 2 stages the cell's log tables by a bulk copy (small cells: short slices)
   const int* sl_off;    // [n_pairs][max_slices+1] first pixel slot of every slice (multiples of 128)
   const int* sl_task;   // [n_pairs][max_slices*32] task of every lane, -1 = none
+  const int* sl_desc;   // [n_pairs][max_slices*32] that task's descriptor (tasks[].y: count | cls<<9 | cell<<18), 0 = none
   const int* sl_cell;   // [n_pairs][max_slices] cell of every slice
   const int* nslices;   // [n_pairs]
   size_t sell_cap;      // pixel slots per pair
@@ -123,6 +124,7 @@ struct nid_ctx {
   bool span_mode = false;      // small cells: tasks by reference span (nid_sorted.cu, "span tasks"); fixed per geometry
   int opt_sorted_mode = 0;     // 0 automatic, 1 class tasks, 2 span tasks
   size_t sell_cap = 0;
+  int* sl_desc = nullptr;
   int *sl_off = nullptr, *sl_task = nullptr, *sl_cell = nullptr, *nslices = nullptr, *task_pos = nullptr;
   int max_slices = 0;
   std::vector<int> h_nslices;

@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(NID_LAYOUT_THREADS) k_layout_write(EvalParams 
   int2* tk = tasks + (size_t)pair * p.max_tasks + tb;
   int* tp = task_pos + (size_t)pair * p.max_tasks + tb;
   int* st = sl_task + ((size_t)pair * p.max_slices + sb) * 32;
+  int* sd = const_cast<int*>(p.sl_desc) + ((size_t)pair * p.max_slices + sb) * 32;
   for (int t = threadIdx.x; t < s.T; t += blockDim.x) {
     int lo = 0, hi = NID_NCLS;  // class of task t: the last v with ts[v] <= t
     while (hi - lo > 1) {
@@ -370,8 +371,9 @@ __global__ void __launch_bounds__(NID_LAYOUT_THREADS) k_layout_write(EvalParams 
     tk[t] = make_int2(i * L, len | (v << 9) | (c << 18));
     tp[t] = pb + off + 4 * ln;
     st[rank] = tb + t;
+    sd[rank] = len | (v << 9) | (c << 18);
   }
-  for (int q = s.T + threadIdx.x; q < s.S * 32; q += blockDim.x) st[q] = -1;  // empty lanes of the cell's last slice
+  for (int q = s.T + threadIdx.x; q < s.S * 32; q += blockDim.x) { st[q] = -1; sd[q] = 0; }  // empty lanes of the cell's last slice
   for (int sl = threadIdx.x; sl < s.S; sl += blockDim.x) {
     sl_off[(size_t)pair * (p.max_slices + 1) + sb + sl] = pb + (sl < s.SF ? sl * 32 * L : s.tail_off[sl - s.SF]);
     sl_cell[(size_t)pair * p.max_slices + sb + sl] = c;
@@ -421,6 +423,7 @@ __global__ void k_pack_fp(int rows, int cols, int pair0, const uint8_t* __restri
 template <int NG>
 struct GeoTable {
   double g[NG][NID_GEO_STRIDE];
+  int job[NG], pair[NG];  // the launch's i-th job and its pair (the pixel kernels start without two dependent global loads)
 };
 
 // The reference's exact sequence for one pixel: CudaPoints3d.cu:20-28 then computeH.cu:152-158, from the
@@ -947,7 +950,7 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
   if (slice >= p.nslices[pair]) return;  // (no block-wide barrier below)
   const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
-  const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
+  const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];  // (for the epilogue; requested early)
   double* h = sm + threadIdx.x;  // h[b * T]
   for (int b = 0; b < B; b++) h[b * T] = 0.0;
   const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
@@ -1589,15 +1592,17 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   extern __shared__ __align__(16) double sm[];
   const int B = p.bins, NS = B - 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int job = job_at(p, NID_BLK_JOB);
-  const int pair = p.job_pair[job];
+  const int job = gt.job[NID_BLK_JOB], pair = gt.pair[NID_BLK_JOB];
   const double* g = gt.g[NID_BLK_JOB];
   // shared: the lanes' class tables W^v [B][T] | per-warp log tables W|V (prologue only)
   const int slice = NID_BLK_CHUNK * (T >> 5) + warp;
   if (slice >= p.nslices[pair]) return;  // (no block-wide barrier below)
   const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
-  const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];
+  // (the lane's task descriptor from the slice's own table: no sl_task -> tasks chain of dependent loads in front of the
+  // class table; 0 = no task)
+  const int desc = p.sl_desc[((size_t)pair * p.max_slices + slice) * 32 + lane];
+  const int task = desc != 0 ? 0 : -1;
   double* wq = sm + threadIdx.x;  // wq[t * T]
   // the first group of pixels is requested before the prologue, so that it arrives while the class table is built
   const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
@@ -1648,7 +1653,6 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
       }
       __syncwarp();
     }
-    const int desc = task >= 0 ? p.tasks[(size_t)pair * p.max_tasks + task].y : 0;
     const int cls = (desc >> 9) & 0x1ff;
     double wr[4] = {0.0, 0.0, 0.0, 0.0};
     int kr = 0;
@@ -2306,6 +2310,7 @@ static void fill_geo(const nid_ctx* c, GeoTable<NG>& gt, int first, int n, bool 
     const double* T0 = c->h_Twc0.data() + 16 * (size_t)pair;
     const double* cam = c->h_cam.data() + 4 * (size_t)pair;
     double* g = gt.g[i];
+    gt.job[i] = job; gt.pair[i] = pair;
     for (int col = 0; col < 4; col++)
       for (int r = 0; r < 3; r++) {
         double m;
