@@ -423,7 +423,10 @@ __global__ void k_pack_fp(int rows, int cols, int pair0, const uint8_t* __restri
 template <int NG>
 struct GeoTable {
   double g[NG][NID_GEO_STRIDE];
-  int job[NG], pair[NG];  // the launch's i-th job and its pair (the pixel kernels start without two dependent global loads)
+  // the launch's i-th job, its pair, the pair's slice count and packed target texture: the pixel kernels start without
+  // a chain of dependent global loads (job list -> job_pair -> nslices / texture handle)
+  unsigned long long tex[NG];
+  int job[NG], pair[NG], nsl[NG];
 };
 
 // The reference's exact sequence for one pixel: CudaPoints3d.cu:20-28 then computeH.cu:152-158, from the
@@ -943,6 +946,7 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
   extern __shared__ __align__(16) double sm[];
   const int B = p.bins, NS = B - 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // (the job / pair / slice-count entries of the parameter table, which pass 2 uses, cost this kernel 24 bytes of spills)
   const int job = job_at(p, NID_BLK_JOB);
   const int pair = p.job_pair[job];
   const double* g = gt.g[NID_BLK_JOB];
@@ -1596,7 +1600,7 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   const double* g = gt.g[NID_BLK_JOB];
   // shared: the lanes' class tables W^v [B][T] | per-warp log tables W|V (prologue only)
   const int slice = NID_BLK_CHUNK * (T >> 5) + warp;
-  if (slice >= p.nslices[pair]) return;  // (no block-wide barrier below)
+  if (slice >= gt.nsl[NID_BLK_JOB]) return;  // (no block-wide barrier below)
   const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
   // (the lane's task descriptor from the slice's own table: no sl_task -> tasks chain of dependent loads in front of the
@@ -1694,7 +1698,7 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
     }
     if (task >= 0) fold_table(wq, T, B);
   }
-  const cudaTextureObject_t tex2 = p.tex2[pair];
+  const cudaTextureObject_t tex2 = (cudaTextureObject_t)gt.tex[NID_BLK_JOB];
   const uint8_t* im1 = p.im1 + (size_t)pair * p.N;
   const ExactSrc xs{p.poses + 16 * job, p.Twc0 + 16 * pair, p.cam + 4 * pair};
   const double s = (double)NS / 255.0;
@@ -2311,6 +2315,8 @@ static void fill_geo(const nid_ctx* c, GeoTable<NG>& gt, int first, int n, bool 
     const double* cam = c->h_cam.data() + 4 * (size_t)pair;
     double* g = gt.g[i];
     gt.job[i] = job; gt.pair[i] = pair;
+    gt.nsl[i] = c->h_nslices[pair];
+    gt.tex[i] = c->h_tex2.empty() ? 0ull : (unsigned long long)c->h_tex2[pair];
     for (int col = 0; col < 4; col++)
       for (int r = 0; r < 3; r++) {
         double m;
