@@ -67,7 +67,7 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.ht = c->ht; p.hj = c->hj; p.err = c->err; p.der = c->der; p.gn = c->gn;
   p.sd0 = c->sd0; p.sd1 = c->sd1; p.sd2 = c->sd2; p.sid = c->sid;
   p.sv = c->sv; p.span_mode = c->span_mode ? 1 : 0;
-  p.stage_bulk = (c->opt_stage_bulk < 0 ? (long long)c->rb * c->cb < 2048 : c->opt_stage_bulk) ? 1 : 0;
+  p.stage_bulk = (c->opt_stage_bulk < 0 ? (long long)c->rb * c->cb < NID_SMALL_CELL_PX : c->opt_stage_bulk) ? 1 : 0;
   p.sl_off = c->sl_off; p.sl_task = c->sl_task; p.sl_desc = c->sl_desc; p.sl_cell = c->sl_cell; p.nslices = c->nslices;
   p.sell_cap = c->sell_cap; p.max_slices = c->max_slices; p.Twc0 = c->Twc0;
   p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start; p.cell_slice_start = c->cell_slice_start;
@@ -277,7 +277,7 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   // default 16x16 cells (1200 pixels, ~5 per reference intensity) 72.5k with 32, 78.7k with 16 or 20, 77k with 12: their
   // tasks are short anyway and a slice is as long as its longest task. Shorter tasks also cut the latency of a lone
   // solve (more, shorter slices: 1.68 -> 1.37 ms at 4x4 cells with 16): option "task_px" for latency-bound callers.
-  c->task_px = (long long)c->rb * c->cb < 2048 ? 16 : 32;
+  c->task_px = (long long)c->rb * c->cb < NID_SMALL_CELL_PX ? 16 : 32;
   const int min_task_px = 8;
   c->max_tasks = (int)(N / min_task_px + NC * NID_NCLS + 1);
   c->max_slices = c->max_tasks / 32 + (int)NC + 1;
