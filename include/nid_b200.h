@@ -175,7 +175,7 @@ int nid_event_elapsed_ms(nid_ctx* ctx, float* ms);
  * normalised histograms of every evaluation for nid_debug_hist);
  * "force_strips" (natural path: CTAs per cell and job; 0 = automatic); "time_kernels" (1: bracket every kernel
  * of nid_eval_staged / nid_eval_jobs with CUDA events and accumulate per-kernel device time; resets);
- * "task_px" (sorted path: pixels per task, a multiple of 4 in [8, 256]; default by geometry, 32 for cells of 2048
+ * "task_px" (sorted path: pixels per task, a multiple of 4 in [8, 256]; default by geometry, 32 for cells of 2560
  * pixels or more and 16 below; set before nid_prepare*. Latency-bound callers -- one pair, one solve at a time, the
  * reference's own use -- should set 16: more and shorter slices, 1.68 -> 1.37 ms per 640x480 solve; throughput-bound
  * callers keep the default. Results for different task lengths agree to rounding, not bit for bit);

@@ -274,7 +274,8 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   // pixels per task, by geometry only (never by the capacity of the context: a shard of a job must compute the same
   // bits as the whole job). Measured at 640x480, 96 evaluations in flight: 4x4 cells 144k evaluations/s with 32-pixel
   // tasks, 137k with 24, 126k with 16 (twice the task rows to assemble); 8x8 cells 112k / 110k / 103k; the reference's
-  // default 16x16 cells (1200 pixels, ~5 per reference intensity) 72.5k with 32, 78.7k with 16 or 20, 77k with 12: their
+  // default 16x16 cells (1200 pixels, ~5 per reference intensity) 72.5k with 32, 78.7k with 16 or 20, 77k with 12 (before
+  // the other small-cell choices of NID_SMALL_CELL_PX): their
   // tasks are short anyway and a slice is as long as its longest task. Shorter tasks also cut the latency of a lone
   // solve (more, shorter slices: 1.68 -> 1.37 ms at 4x4 cells with 16): option "task_px" for latency-bound callers.
   c->task_px = (long long)c->rb * c->cb < NID_SMALL_CELL_PX ? 16 : 32;

@@ -222,8 +222,12 @@ namespace nid {
 // up to this many bins pass 2 stages the cell's log tables per warp and k_assemble the reference weight table in shared memory;
 // beyond, the staging areas would cost a resident CTA per SM and the tables are read through L1
 #define NID_FEW_BINS(bins) ((bins) <= 20)
-// cells of fewer pixels than this are "small": 16-pixel tasks, bulk-copy staging and one-warp CTAs in pass 2
-#define NID_SMALL_CELL_PX 2048
+// cells of fewer pixels than this are "small": 16-pixel tasks, bulk-copy staging and one-warp CTAs in pass 2.
+// Measured at 640x480 (evaluations/s as small / as large): 16x16 cells of 1200 pixels 90.6k / 72.5k, 12x12 cells of 2120
+// pixels 107.8k / 102.1k, 8x8 cells of 4800 pixels 109.7k / 119.1k.
+#ifndef NID_SMALL_CELL_PX
+#define NID_SMALL_CELL_PX 2560
+#endif
 // Layout of the scaled log tables W | V of one (job, cell), written by the assembly and read by pass 2: B rows of W at a
 // stride of wv_row(B) doubles -- B + 1 where pass 2 stages the block in shared memory (its lanes then read four rows
 // each without bank conflicts, and the block is staged by ONE bulk copy, byte for byte) -- then the B entries of V;

@@ -937,6 +937,14 @@ __device__ __forceinline__ void store_task_rows(double* hw, int B, int lane, int
 #ifndef NID_JAC_WARPS
 #define NID_JAC_WARPS (NID_JAC_MINB * 4)
 #endif
+// the small-cell instantiations (BULK: short slices, prologue-heavy) trade registers for resident warps (__maxnreg__): measured
+// at 16x16 cells, us per evaluation by register budget (resident warps): 128 (16) 5.48, 120 (17) 5.28, 112 (18) 5.50,
+// 104 (19) 5.52, 96 (21) 5.08, 88 (23) 5.56, 80 (25) 5.75; at 12x12 cells 4.70 with 112, 4.42 with 96. At 4x4 cells the
+// full 128 registers are best (3.43 against 3.68 with 96).
+#ifndef NID_JAC_REGS_SMALL
+#define NID_JAC_REGS_SMALL 96
+#endif
+#define NID_JAC_WARPS_SMALL (2048 / NID_JAC_REGS_SMALL)  // resident warps the register file holds at that budget
 #ifndef NID_JAC_NOPF
 #define NID_JAC_NOPF 0
 #endif
@@ -1347,7 +1355,7 @@ __global__ void __launch_bounds__(NID_ASM_WIDE, 1) k_assemble_wide(EvalParams p,
 // Fixed per geometry (cells under NID_ASM_SMALL_PX pixels and at most 32 bins), so results never depend on the batch.
 #define NID_ASMW_WARPS 8
 #ifndef NID_ASMW_BATCH
-#define NID_ASMW_BATCH 8  // task rows a lane keeps in flight (16 and 24 cost resident warps: measured slower)
+#define NID_ASMW_BATCH 4  // task rows a lane keeps in flight (16x16 cells: 1.68 us per evaluation with 4, 1.70 with 6, 1.81 with 8, 2.08 with 12)
 #endif
 #ifndef NID_ASMW_MINB
 #define NID_ASMW_MINB 4
@@ -1591,7 +1599,7 @@ __device__ __forceinline__ void jac_pixels(const double* __restrict__ g, const E
 
 // grid (jobs of this launch, ceil(max_slices/(T/32))), T = 32..128 threads.
 template <bool PTS, int NG, int T, bool BULK>
-__global__ void __launch_bounds__(T, NID_JAC_WARPS * 32 / T)
+__global__ void __launch_bounds__(T) __maxnreg__(BULK ? NID_JAC_REGS_SMALL : 65536 / (NID_JAC_WARPS * 32))
 k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTable<NG> gt) {
   extern __shared__ __align__(16) double sm[];
   const int B = p.bins, NS = B - 3;
@@ -2732,8 +2740,8 @@ int sorted_init(nid_ctx* c) {
   NID_CARVE((k_hist_sell<PTS, NG, 32>), hist_sell_smem(c, 32), NID_HIST_WARPS);        \
   NID_CARVE((k_jac_sell<PTS, NG, 64, false>), jac_sell_smem(c, 64), NID_JAC_WARPS / 2);  \
   NID_CARVE((k_jac_sell<PTS, NG, 32, false>), jac_sell_smem(c, 32), NID_JAC_WARPS);      \
-  NID_CARVE((k_jac_sell<PTS, NG, 64, true>), jac_sell_smem(c, 64), NID_JAC_WARPS / 2);   \
-  NID_CARVE((k_jac_sell<PTS, NG, 32, true>), jac_sell_smem(c, 32), NID_JAC_WARPS);
+  NID_CARVE((k_jac_sell<PTS, NG, 64, true>), jac_sell_smem(c, 64), NID_JAC_WARPS_SMALL / 2);   \
+  NID_CARVE((k_jac_sell<PTS, NG, 32, true>), jac_sell_smem(c, 32), NID_JAC_WARPS_SMALL);
   NID_SMEM_ATTR_PX(true, NID_GEO_SMALL)
   NID_SMEM_ATTR_PX(false, NID_GEO_SMALL)
   NID_SMEM_ATTR_PX(true, NID_GEO_LARGE)
