@@ -246,6 +246,32 @@ def test_lm_reuse_of_the_accepted_trial_is_bit_identical(nid, orc, make_pair, ce
     assert np.max(np.abs(out1[2] - poseo)) < 1e-7
 
 
+@pytest.mark.parametrize("cell,bins,rows,cols", [(8, 10, 240, 320), (2, 16, 120, 160), (2, 40, 120, 160), (1, 9, 96, 128)])
+def test_launch_shape_options_do_not_change_any_bit(nid, orc, make_pair, cell, bins, rows, cols):
+    """How the work is launched is chosen by geometry and by the number of evaluations in flight -- bulk-copy or linear
+    staging of the log tables in pass 2, the 1024-thread assembly for a handful of jobs, one job or twelve per launch --
+    and none of it may change a result: every combination must reproduce the default bit for bit."""
+    p = make_pair(1003, rows, cols, invalid_depth_frac=0.04)
+    pose0 = orc.reference_perturbation(p.T_wc1)
+    poses = np.stack([orc.se3_to_mat16(orc.se3_mul(orc.se3_exp(1e-3 * (k + 1) * np.array([1, -1, 0.5, 2, -2, 1.0])), pose0)) for k in range(12)])
+    ctx = nid.Context(rows, cols, cell, bins, n_pairs=1, max_jobs=12)
+    ctx.set_pair(0, p.depth0, p.im0, p.im1, p.T_wc0, p.intr)
+    ctx.prepare(0, orc.se3_to_mat16(pose0))
+    ref = ctx.eval_jobs(poses, np.zeros(12, np.int32), True)
+    assert np.isfinite(ref[2][~np.isnan(ref[0])]).all()
+    for bulk in (0, 1):
+        for wide in (0, 1):
+            ctx.set_option("stage_bulk", bulk)
+            ctx.set_option("asm_wide", wide)
+            got = ctx.eval_jobs(poses, np.zeros(12, np.int32), True)
+            for a, b in zip(ref, got):
+                assert np.array_equal(a, b, equal_nan=True), (bulk, wide)
+            one = ctx.eval(0, poses[5], True)  # one job in flight: other CTA sizes, the wide assembly when allowed
+            for a, b in zip(ref, one):
+                assert np.array_equal(a[5], b, equal_nan=True), (bulk, wide)
+    ctx.close()
+
+
 def test_latency_mode_graph_survives_changes_of_the_context(nid, orc, make_pair):
     """The latency mode replays one captured CUDA graph per round (nid_sorted.cu, launch_latency_round). Everything the
     graph captured by value may change between solves -- another pair in the slot, another prepare pose (other slice
