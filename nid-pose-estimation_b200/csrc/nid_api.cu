@@ -1275,7 +1275,7 @@ int nid_set_option(nid_ctx* c, const char* key, int value) {
   if (!strcmp(key, "keep_hist")) { c->opt_keep_hist = value; return NID_OK; }
   if (!strcmp(key, "lm_reuse")) { c->opt_lm_reuse = value ? 1 : 0; return NID_OK; }
   if (!strcmp(key, "lm_graph")) { c->opt_lm_graph = value ? 1 : 0; return NID_OK; }
-  if (!strcmp(key, "asm_wide")) { c->opt_asm_wide = value ? 1 : 0; return NID_OK; }
+  if (!strcmp(key, "asm_wide")) { c->opt_asm_wide = value < 0 ? 0 : std::min(value, 2); return NID_OK; }
   if (!strcmp(key, "stage_bulk")) { c->opt_stage_bulk = value < 0 ? -1 : (value ? 1 : 0); return NID_OK; }
   if (!strcmp(key, "lm_speculate")) {
     if (value < 0 || value > 8) { set_error("lm_speculate must be 0 (off) .. 8 trial poses per round"); return NID_ERR_ARG; }

@@ -2482,7 +2482,12 @@ int launch_sorted_pass1(nid_ctx* c, const int* d_list, const int* h_list, int fi
   } else if (assemble_warp(c)) {
     const int units = c->ncell * n;
     k_assemble_warp<<<(units + NID_ASMW_WARPS - 1) / NID_ASMW_WARPS, NID_ASMW_WARPS * 32, assemble_warp_smem(c), c->stream>>>(p, tables, n);
-  } else if (c->opt_asm_wide && c->ncell * n <= c->sm_count) {
+  } else if (c->opt_asm_wide && (c->ncell * n <= c->sm_count || c->opt_asm_wide == 2 ||
+                                 (!assemble_small(c) && assemble_smem(c, NID_ASM_THREADS) > (size_t)100 * 1024))) {
+    // the 1024-thread variant (same bits): for a handful of evaluations in flight (fewer units than SMs), and whenever the
+    // shared memory of a CTA leaves room for one or two CTAs per SM only (more than ~30 bins) -- 1024 threads then fill the
+    // SM where 256 leave it mostly empty (C3, 32 bins: 5.57 -> 4.00 us per evaluation; 40 bins at 640x480: 4.59 -> 2.55;
+    // but 28 bins: 1.97 -> 2.09, 24 bins: 1.44 -> 1.88, 16 bins: 0.87 -> 1.51, so not there)
     k_assemble_wide<<<dim3(c->ncell, n), NID_ASM_WIDE, assemble_smem(c, NID_ASM_WIDE), c->stream>>>(p, tables);
   } else if (assemble_small(c)) k_assemble_small<<<dim3(c->ncell, n), NID_ASM_SMALL, assemble_smem(c, NID_ASM_THREADS), c->stream>>>(p, tables);
   else k_assemble<<<dim3(c->ncell, n), NID_ASM_THREADS, assemble_smem(c, NID_ASM_THREADS), c->stream>>>(p, tables);
