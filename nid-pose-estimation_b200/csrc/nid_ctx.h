@@ -236,26 +236,57 @@ __host__ __device__ inline int wv_row(int B) { return NID_FEW_BINS(B) ? B + 1 : 
 __host__ __device__ inline int wv_stride(int B) { return (B * wv_row(B) + B + 1) & ~1; }
 __host__ __device__ inline int job_at(const EvalParams& p, int i) { return p.job_list ? p.job_list[p.job0 + i] : p.job0 + i; }
 #ifdef __CUDACC__
-// a11: entry `ent` of the Huber-weighted Gauss-Newton block of a job, summed over its active cells in cell order
+// a11: the Huber-weighted Gauss-Newton block of a job, summed over its active cells in cell order
 // (base_unary_edge.hpp:43-72, robust_kernel_impl.cpp:78-90, sparse_optimizer.cpp:102-116):
 // entry 0 chi2, 1..36 H (row-major), 37..42 b, 43 the number of active cells.
-__device__ __forceinline__ double gn_entry(const EvalParams& p, int job, int ent) {
-  double acc = 0.0;
-  const double* e = p.err + (size_t)job * p.ncell;
-  const double* J = p.der + (size_t)job * p.ncell * 6;
-  for (int c = 0; c < p.ncell; c++) {
+// huber_weights: rho(e^2) and rho'(e^2) of one cell (robust_kernel_impl.cpp:78-90 with its `float dsqr`).
+// gn_accumulate adds the cells [0, n) of the staged arrays (error, the two weights, six Jacobian entries per cell) to
+// entry `ent`, in cell order.
+__device__ __forceinline__ void huber_weights(double ec, double dsqr, double delta, double& rho0, double& rho1) {
+  const double chi = ec * ec;
+  if (chi <= dsqr) { rho0 = chi; rho1 = 1.0; }
+  else { const double sq = sqrt(chi); rho0 = 2 * sq * delta - dsqr; rho1 = delta / sq; }
+}
+__device__ __forceinline__ void gn_accumulate(double& acc, const double* e, const double* r0, const double* r1, const double* J, int n, int ent) {
+  const int i = ent <= 36 ? (ent - 1) / 6 : ent - 37, j = ent <= 36 ? (ent - 1) % 6 : 0;
+  for (int c = 0; c < n; c++) {
     const double ec = e[c];
     if (isnan(ec)) continue;
-    const double chi = ec * ec;
-    double rho0, rho1;
-    if (chi <= p.huber_dsqr) { rho0 = chi; rho1 = 1.0; }
-    else { const double sq = sqrt(chi); rho0 = 2 * sq * p.huber_delta - p.huber_dsqr; rho1 = p.huber_delta / sq; }
-    if (ent == 0) acc += rho0;
-    else if (ent <= 36) { const int i = (ent - 1) / 6, j = (ent - 1) % 6; acc += J[6 * c + i] * rho1 * J[6 * c + j]; }
-    else if (ent <= 42) { const int i = ent - 37; acc -= rho1 * J[6 * c + i] * ec; }
+    if (ent == 0) acc += r0[c];
+    else if (ent <= 36) acc += J[6 * c + i] * r1[c] * J[6 * c + j];
+    else if (ent <= 42) acc -= r1[c] * J[6 * c + i] * ec;
     else acc += 1.0;
   }
-  return acc;
+}
+// The block of one job by one CTA (any size >= 64): the job's errors and Jacobians are staged in shared memory 256 cells
+// at a time by all threads (coalesced, independent loads) and every thread computes the Huber weights of its cells -- an
+// fp64 square root and a division each, which the thread-per-entry loop used to run 256 times in a row (the reference's
+// default geometry has 256 cells: measured 49-68 us per launch, a third of a latency-mode round) -- then threads 0..43 walk
+// the staged cells in order: the sum is the sequential one.
+// out: 44 doubles per job (device or pinned host memory). want_jac == 0: chi2 and the active count only.
+#define NID_GN_CHUNK 256
+__device__ __forceinline__ void gn_block(const EvalParams& p, int job, int want_jac, double* __restrict__ out) {
+  __shared__ double s_e[NID_GN_CHUNK], s_r0[NID_GN_CHUNK], s_r1[NID_GN_CHUNK];
+  __shared__ double s_J[6 * NID_GN_CHUNK];
+  const double* e = p.err + (size_t)job * p.ncell;
+  const double* J = p.der + (size_t)job * p.ncell * 6;
+  const int ent = threadIdx.x;
+  const bool mine = ent < 44 && (want_jac || ent == 0 || ent == 43);
+  double acc = 0.0;
+  for (int c0 = 0; c0 < p.ncell; c0 += NID_GN_CHUNK) {
+    const int n = min(NID_GN_CHUNK, p.ncell - c0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double ec = e[c0 + i];
+      double rho0 = 0.0, rho1 = 0.0;
+      if (!isnan(ec)) huber_weights(ec, p.huber_dsqr, p.huber_delta, rho0, rho1);
+      s_e[i] = ec; s_r0[i] = rho0; s_r1[i] = rho1;
+    }
+    if (want_jac) for (int i = threadIdx.x; i < 6 * n; i += blockDim.x) s_J[i] = J[6 * c0 + i];
+    __syncthreads();
+    if (mine) gn_accumulate(acc, s_e, s_r0, s_r1, s_J, n, ent);
+    __syncthreads();
+  }
+  if (mine) out[job * 44 + ent] = acc;
 }
 #endif
 void set_error(const std::string& s);

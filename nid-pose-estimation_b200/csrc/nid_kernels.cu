@@ -451,12 +451,8 @@ __global__ void k_jac_final(EvalParams p, int n_jobs) {
 // a11: Huber-weighted Gauss-Newton block over the active cells of a job, in cell order
 // (base_unary_edge.hpp:43-72, robust_kernel_impl.cpp:78-90, sparse_optimizer.cpp:102-116).
 // One thread per (job, entry): entry 0 chi2, 1..36 H, 37..42 b, 43 active count.
-__global__ void k_gn(EvalParams p, int n_jobs, int want_jac) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_jobs * 44) return;
-  const int job = job_at(p, idx / 44), ent = idx % 44;
-  if (!want_jac && ent >= 1 && ent <= 42) return;
-  p.gn[job * 44 + ent] = gn_entry(p, job, ent);
+__global__ void __launch_bounds__(128) k_gn(EvalParams p, int want_jac) {
+  gn_block(p, job_at(p, blockIdx.x), want_jac, p.gn);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -723,11 +719,11 @@ int launch_eval_mixed(nid_ctx* c, int base, int nj, int nt, double delta) {
     }
   }
   if (nj > 0) {
-    k_gn<<<(nj * 44 + 127) / 128, 128, 0, c->stream>>>(p, nj, 1);
+    k_gn<<<nj, 128, 0, c->stream>>>(p, 1);
     NID_LAUNCH_CHECK(c, "k_gn");
   }
   if (nt > 0) {
-    k_gn<<<(nt * 44 + 127) / 128, 128, 0, c->stream>>>(q, nt, 0);
+    k_gn<<<nt, 128, 0, c->stream>>>(q, 0);
     NID_LAUNCH_CHECK(c, "k_gn(chi2)");
   }
   return NID_OK;
@@ -739,7 +735,7 @@ int launch_gn_list(nid_ctx* c, const int* d_list, int first, int n, double delta
   p.huber_dsqr = (double)(float)(delta * delta);  // `float dsqr`, robust_kernel_impl.h:84
   p.job0 = first;
   p.job_list = d_list;
-  k_gn<<<(n * 44 + 127) / 128, 128, 0, c->stream>>>(p, n, want_jac);
+  k_gn<<<n, 128, 0, c->stream>>>(p, want_jac);
   NID_LAUNCH_CHECK(c, want_jac ? "k_gn" : "k_gn(chi2)");
   return NID_OK;
 }
@@ -748,8 +744,7 @@ int launch_gn(nid_ctx* c, int n_jobs, double delta) {
   EvalParams p = make_params(c, n_jobs);
   p.huber_delta = delta;
   p.huber_dsqr = (double)(float)(delta * delta);  // `float dsqr`, robust_kernel_impl.h:84
-  int total = n_jobs * 44;
-  k_gn<<<(total + 127) / 128, 128, 0, c->stream>>>(p, n_jobs, 1);
+  k_gn<<<n_jobs, 128, 0, c->stream>>>(p, 1);
   NID_LAUNCH_CHECK(c, "k_gn");
   return NID_OK;
 }
@@ -758,8 +753,7 @@ int launch_chi2(nid_ctx* c, int n_jobs, double delta) {
   EvalParams p = make_params(c, n_jobs);
   p.huber_delta = delta;
   p.huber_dsqr = (double)(float)(delta * delta);
-  int total = n_jobs * 44;
-  k_gn<<<(total + 127) / 128, 128, 0, c->stream>>>(p, n_jobs, 0);
+  k_gn<<<n_jobs, 128, 0, c->stream>>>(p, 0);
   NID_LAUNCH_CHECK(c, "k_gn(chi2)");
   return NID_OK;
 }

@@ -1362,10 +1362,16 @@ __global__ void __launch_bounds__(NID_ASM_WIDE, 1) k_assemble_wide(EvalParams p,
 #ifndef NID_ASMW_MINB
 #define NID_ASMW_MINB 4
 #endif
+#ifndef NID_ASMW_BATCH_LAT
+#define NID_ASMW_BATCH_LAT 16
+#endif
 // Lanes are (g, t) = (lane / B, lane % B): NG = 32 / B sub-groups each stream every NG-th task row of the cell into
 // their own copy of P_j / P_t (rows are B doubles, so one load instruction fetches NG whole rows); the copies are
 // added in sub-group order at the end. Task order within a sub-group and sub-group order are fixed: deterministic.
-__global__ void __launch_bounds__(NID_ASMW_WARPS * 32, NID_ASMW_MINB) k_assemble_warp(EvalParams p, int want_jac, int n_jobs) {
+// BATCH: task rows a lane keeps in flight -- NID_ASMW_BATCH when the device is full (more resident warps matter more),
+// NID_ASMW_BATCH_LAT for a handful of evaluations (a lone solve: fewer dependent round trips per warp); same bits.
+template <int BATCH>
+__global__ void __launch_bounds__(NID_ASMW_WARPS * 32, BATCH > 8 ? 1 : NID_ASMW_MINB) k_assemble_warp(EvalParams p, int want_jac, int n_jobs) {
   extern __shared__ __align__(16) double sm[];  // per warp: NG copies of P_j as [B][B] (+ one row of P_t each)
   const int B = p.bins, BB = B * B;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1395,18 +1401,18 @@ __global__ void __launch_bounds__(NID_ASMW_WARPS * 32, NID_ASMW_MINB) k_assemble
   const int t0 = p.cell_task_start[pair * (p.ncell + 1) + c], t1 = p.cell_task_start[pair * (p.ncell + 1) + c + 1];
   const int2* tk = p.tasks + (size_t)pair * p.max_tasks;
   const double* G = p.G + (size_t)job * p.g_stride * B + t;
-  for (int tb = t0; tb < t1; tb += NID_ASMW_BATCH * NG) {
-    double x[NID_ASMW_BATCH];
-    int cls[NID_ASMW_BATCH];
+  for (int tb = t0; tb < t1; tb += BATCH * NG) {
+    double x[BATCH];
+    int cls[BATCH];
 #pragma unroll
-    for (int i = 0; i < NID_ASMW_BATCH; i++) {
+    for (int i = 0; i < BATCH; i++) {
       const int tt = tb + i * NG + g;
       const bool in = mine && tt < t1;
       x[i] = in ? NID_ASM_LD(G + (size_t)tt * B) : 0.0;
       cls[i] = in ? ((tk[tt].y >> 9) & 0x1ff) : 256;
     }
 #pragma unroll
-    for (int i = 0; i < NID_ASMW_BATCH; i++) {
+    for (int i = 0; i < BATCH; i++) {
       pt += x[i];
       if (cls[i] < 256) {  // (class 256: valid points without a reference sample count in P_t only)
         const int k = __ldg(p.lut_k + cls[i]);
@@ -2021,8 +2027,13 @@ __global__ void __launch_bounds__(256) k_jac_final_sorted(EvalParams p, int n_jo
   jac_tail_cell(p, job, p.job_pair[job], c, lane);
 }
 
+// the Gauss-Newton blocks of the launch's jobs written where the host reads them (see k_tail_gn)
+__global__ void __launch_bounds__(128) k_gn_out(EvalParams p, double* __restrict__ gn_out) {
+  gn_block(p, job_at(p, blockIdx.x), 1, gn_out);
+}
+
 // Latency mode of the LM driver: the Jacobian tail and the Gauss-Newton block of a job in ONE launch (one CTA per job:
-// its warps finish the cells, then 44 threads sum the block exactly as k_gn does), written where the host reads it
+// its warps finish the cells, then the block is summed exactly as k_gn does (gn_block)), written where the host reads it
 // (gn_out may be pinned host memory: no copy is queued behind the kernel).
 __global__ void __launch_bounds__(256) k_tail_gn(EvalParams p, double* __restrict__ gn_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -2030,7 +2041,7 @@ __global__ void __launch_bounds__(256) k_tail_gn(EvalParams p, double* __restric
   const int pair = p.job_pair[job];
   for (int c = warp; c < p.ncell; c += blockDim.x >> 5) jac_tail_cell(p, job, pair, c, lane);
   __syncthreads();  // (the der values this CTA wrote are visible to all of its threads)
-  if (threadIdx.x < 44) gn_out[job * 44 + threadIdx.x] = gn_entry(p, job, threadIdx.x);
+  gn_block(p, job, 1, gn_out);
 }
 
 // Kernel-1 target texture: three stacked planes of 16-bit floats, rows [0,R) I, [R,2R) Gx/2, [2R,3R) Gy/2 with the
@@ -2481,7 +2492,10 @@ int launch_sorted_pass1(nid_ctx* c, const int* d_list, const int* h_list, int fi
     k_assemble_span<<<(units + NID_ASMW_WARPS - 1) / NID_ASMW_WARPS, NID_ASMW_WARPS * 32, assemble_warp_smem(c), c->stream>>>(p, tables, n);
   } else if (assemble_warp(c)) {
     const int units = c->ncell * n;
-    k_assemble_warp<<<(units + NID_ASMW_WARPS - 1) / NID_ASMW_WARPS, NID_ASMW_WARPS * 32, assemble_warp_smem(c), c->stream>>>(p, tables, n);
+    if (units <= 2 * c->sm_count * NID_ASMW_WARPS)
+      k_assemble_warp<NID_ASMW_BATCH_LAT><<<(units + NID_ASMW_WARPS - 1) / NID_ASMW_WARPS, NID_ASMW_WARPS * 32, assemble_warp_smem(c), c->stream>>>(p, tables, n);
+    else
+      k_assemble_warp<NID_ASMW_BATCH><<<(units + NID_ASMW_WARPS - 1) / NID_ASMW_WARPS, NID_ASMW_WARPS * 32, assemble_warp_smem(c), c->stream>>>(p, tables, n);
   } else if (c->opt_asm_wide && (c->ncell * n <= c->sm_count || c->opt_asm_wide == 2 ||
                                  (!assemble_small(c) && assemble_smem(c, NID_ASM_THREADS) > (size_t)100 * 1024))) {
     // the 1024-thread variant (same bits): for a handful of evaluations in flight (fewer units than SMs), and whenever the
@@ -2527,8 +2541,18 @@ int launch_sorted_tail_gn(nid_ctx* c, const int* d_list, const int* h_list, int 
     c->launches--;
     NID_LAUNCH_CHECK(c, "k_jac_sell");
   }
-  k_tail_gn<<<n, 256, 0, c->stream>>>(p, gn_out);
-  NID_LAUNCH_CHECK(c, "k_tail_gn");
+  if (c->ncell <= 32) {
+    k_tail_gn<<<n, 256, 0, c->stream>>>(p, gn_out);
+    NID_LAUNCH_CHECK(c, "k_tail_gn");
+  } else {
+    // many cells (the reference's default geometry has 256): one CTA per job would walk them eight at a time (measured
+    // ~120 us of a 240 us round); a warp per (job, cell) for the tails, then the block sums
+    const int warps = n * c->ncell;
+    k_jac_final_sorted<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(p, n);
+    NID_LAUNCH_CHECK(c, "k_jac_final_sorted");
+    k_gn_out<<<n, 128, 0, c->stream>>>(p, gn_out);
+    NID_LAUNCH_CHECK(c, "k_gn_out");
+  }
   return NID_OK;
 }
 
@@ -2757,7 +2781,11 @@ int sorted_init(nid_ctx* c) {
   NID_SMEM_ATTR(k_assemble, assemble_smem(c, NID_ASM_THREADS));
   NID_SMEM_ATTR(k_assemble_small, assemble_smem(c, NID_ASM_THREADS));
   NID_SMEM_ATTR(k_assemble_wide, assemble_smem(c, NID_ASM_WIDE));
-  if (c->bins <= 32) { NID_SMEM_ATTR(k_assemble_warp, assemble_warp_smem(c)); NID_SMEM_ATTR(k_assemble_span, assemble_warp_smem(c)); }
+  if (c->bins <= 32) {
+    NID_SMEM_ATTR(k_assemble_warp<NID_ASMW_BATCH>, assemble_warp_smem(c));
+    NID_SMEM_ATTR(k_assemble_warp<NID_ASMW_BATCH_LAT>, assemble_warp_smem(c));
+    NID_SMEM_ATTR(k_assemble_span, assemble_warp_smem(c));
+  }
   if (NID_FEW_BINS(c->bins)) {
 #define NID_SMEM_ATTR_SPAN(NG)                                              \
   NID_SMEM_ATTR((k_hist_span<NG, 128>), hist_span_smem(c, 128));            \
