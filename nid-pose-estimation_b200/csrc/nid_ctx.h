@@ -247,43 +247,54 @@ __device__ __forceinline__ void huber_weights(double ec, double dsqr, double del
   if (chi <= dsqr) { rho0 = chi; rho1 = 1.0; }
   else { const double sq = sqrt(chi); rho0 = 2 * sq * delta - dsqr; rho1 = delta / sq; }
 }
-__device__ __forceinline__ void gn_accumulate(double& acc, const double* e, const double* r0, const double* r1, const double* J, int n, int ent) {
-  const int i = ent <= 36 ? (ent - 1) / 6 : ent - 37, j = ent <= 36 ? (ent - 1) % 6 : 0;
-  for (int c = 0; c < n; c++) {
-    const double ec = e[c];
-    if (isnan(ec)) continue;
-    if (ent == 0) acc += r0[c];
-    else if (ent <= 36) acc += J[6 * c + i] * r1[c] * J[6 * c + j];
-    else if (ent <= 42) acc -= r1[c] * J[6 * c + i] * ec;
-    else acc += 1.0;
+// (staged arrays: inactive cells -- NaN error -- hold zeros everywhere, so the loops need no branch: adding +0.0 changes nothing)
+__device__ __forceinline__ void gn_accumulate(double& acc, const double* e, const double* r0, const double* r1, const double* act,
+                                              const double* J, int n, int ent) {
+  if (ent == 0) {
+    for (int c = 0; c < n; c++) acc += r0[c];
+  } else if (ent <= 36) {
+    const int i = (ent - 1) / 6, j = (ent - 1) % 6;
+    for (int c = 0; c < n; c++) acc += J[6 * c + i] * r1[c] * J[6 * c + j];
+  } else if (ent <= 42) {
+    const int i = ent - 37;
+    for (int c = 0; c < n; c++) acc -= r1[c] * J[6 * c + i] * e[c];
+  } else {
+    for (int c = 0; c < n; c++) acc += act[c];
   }
 }
-// The block of one job by one CTA (any size >= 64): the job's errors and Jacobians are staged in shared memory 256 cells
-// at a time by all threads (coalesced, independent loads) and every thread computes the Huber weights of its cells -- an
-// fp64 square root and a division each, which the thread-per-entry loop used to run 256 times in a row (the reference's
-// default geometry has 256 cells: measured 49-68 us per launch, a third of a latency-mode round) -- then threads 0..43 walk
-// the staged cells in order: the sum is the sequential one.
+// The block of one job by one CTA of at least 128 threads: the job's errors and Jacobians are staged in shared memory 256
+// cells at a time by all threads (coalesced, independent loads) and every thread computes the Huber weights of its cells
+// -- an fp64 square root and a division each -- then 44 threads walk the staged cells in order, one entry each: the sum is
+// the sequential one. The entries are dealt to the warps by kind (H: threads 0..35, b: 64..69, chi2: 96, count: 97) so
+// that no warp diverges inside its loop. Before: one thread per entry looping over global memory with the weights inline,
+// 256 times in a row at the reference's default geometry (256 cells): 49-68 us per launch, a third of a latency-mode round.
 // out: 44 doubles per job (device or pinned host memory). want_jac == 0: chi2 and the active count only.
 #define NID_GN_CHUNK 256
 __device__ __forceinline__ void gn_block(const EvalParams& p, int job, int want_jac, double* __restrict__ out) {
-  __shared__ double s_e[NID_GN_CHUNK], s_r0[NID_GN_CHUNK], s_r1[NID_GN_CHUNK];
+  __shared__ double s_e[NID_GN_CHUNK], s_r0[NID_GN_CHUNK], s_r1[NID_GN_CHUNK], s_act[NID_GN_CHUNK];
   __shared__ double s_J[6 * NID_GN_CHUNK];
   const double* e = p.err + (size_t)job * p.ncell;
   const double* J = p.der + (size_t)job * p.ncell * 6;
-  const int ent = threadIdx.x;
-  const bool mine = ent < 44 && (want_jac || ent == 0 || ent == 43);
+  const int t = threadIdx.x;
+  const int ent = t < 36 ? t + 1 : (t >= 64 && t < 70) ? t - 64 + 37 : t == 96 ? 0 : t == 97 ? 43 : -1;
+  const bool mine = ent >= 0 && (want_jac || ent == 0 || ent == 43);
   double acc = 0.0;
   for (int c0 = 0; c0 < p.ncell; c0 += NID_GN_CHUNK) {
     const int n = min(NID_GN_CHUNK, p.ncell - c0);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const double ec = e[c0 + i];
+      const bool active = !isnan(ec);
       double rho0 = 0.0, rho1 = 0.0;
-      if (!isnan(ec)) huber_weights(ec, p.huber_dsqr, p.huber_delta, rho0, rho1);
-      s_e[i] = ec; s_r0[i] = rho0; s_r1[i] = rho1;
+      if (active) huber_weights(ec, p.huber_dsqr, p.huber_delta, rho0, rho1);
+      s_e[i] = active ? ec : 0.0; s_r0[i] = rho0; s_r1[i] = rho1; s_act[i] = active ? 1.0 : 0.0;
     }
-    if (want_jac) for (int i = threadIdx.x; i < 6 * n; i += blockDim.x) s_J[i] = J[6 * c0 + i];
+    if (want_jac)
+      for (int i = threadIdx.x; i < 6 * n; i += blockDim.x) {
+        const double v = J[6 * c0 + i];
+        s_J[i] = isnan(e[c0 + i / 6]) ? 0.0 : v;  // (inactive cells carry NaN Jacobians)
+      }
     __syncthreads();
-    if (mine) gn_accumulate(acc, s_e, s_r0, s_r1, s_J, n, ent);
+    if (mine) gn_accumulate(acc, s_e, s_r0, s_r1, s_act, s_J, n, ent);
     __syncthreads();
   }
   if (mine) out[job * 44 + ent] = acc;
