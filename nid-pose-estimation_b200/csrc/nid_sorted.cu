@@ -912,6 +912,9 @@ __device__ __forceinline__ void store_task_rows(double* hw, int B, int lane, int
 #ifndef NID_HIST_W
 #define NID_HIST_W 4
 #endif
+#ifndef NID_HIST_HALF_LAST
+#define NID_HIST_HALF_LAST 0  // measured: the two-pixel tail step costs pass 1 more than the skipped half step saves (3.69 against 3.60 us at 16x16 cells, 2.45 against 2.31 at 4x4)
+#endif
 #ifndef NID_JAC_W
 #define NID_JAC_W 2
 #endif
@@ -965,6 +968,10 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
   const int* so = p.sl_off + (size_t)pair * (p.max_slices + 1) + slice;
   const int off0 = so[0], ngroups = (so[1] - off0) >> 7;
   const int task = p.sl_task[((size_t)pair * p.max_slices + slice) * 32 + lane];  // (for the epilogue; requested early)
+#if NID_HIST_HALF_LAST
+  // (see k_jac_sell: the second half of the slice's last group is empty when its longest task ends in the first half)
+  const bool half_last = (((__shfl_sync(0xffffffffu, p.sl_desc[((size_t)pair * p.max_slices + slice) * 32 + lane], 0) & 0x1ff) - 1) & 3) < 2;
+#endif
   double* h = sm + threadIdx.x;  // h[b * T]
   for (int b = 0; b < B; b++) h[b * T] = 0.0;
   const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
@@ -1009,8 +1016,14 @@ k_hist_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTab
 #endif
       const size_t go = (size_t)gi * 128;
       const GroupAddr ga{q0 + go, PTS ? q1 + go : nullptr, PTS ? q2 + go : nullptr, qi + go};
+#if NID_HIST_HALF_LAST
+      if (half_last && gi + 1 == ngroups) hist_pixels<PTS, 2, T>(g, xs, p.rows, p.cols, G, 0, ga, fp, s, NS, h, n0);
+      else
+#endif
+      {
 #pragma unroll
-      for (int j0 = 0; j0 < 4; j0 += NID_HIST_W) hist_pixels<PTS, NID_HIST_W, T>(g, xs, p.rows, p.cols, G, j0, ga, fp, s, NS, h, n0);
+        for (int j0 = 0; j0 < 4; j0 += NID_HIST_W) hist_pixels<PTS, NID_HIST_W, T>(g, xs, p.rows, p.cols, G, j0, ga, fp, s, NS, h, n0);
+      }
       G = Gn;
     }
   }
@@ -1623,6 +1636,10 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
   // class table; 0 = no task)
   const int desc = p.sl_desc[((size_t)pair * p.max_slices + slice) * 32 + lane];
   const int task = desc != 0 ? 0 : -1;
+  // the slice is as long as its first lane's task (tasks are dealt longest first): when that task ends in the first half
+  // of its last group of four, no lane has a pixel in the second half and the last step of the slice is skipped
+  // (small cells: slices are 2.6 groups long on average, half of them end that way)
+  const bool half_last = (((__shfl_sync(0xffffffffu, desc, 0) & 0x1ff) - 1) & 3) < 2;
   double* wq = sm + threadIdx.x;  // wq[t * T]
   // the first group of pixels is requested before the prologue, so that it arrives while the class table is built
   const size_t sbase = (size_t)pair * p.sell_cap + off0 + lane * 4;
@@ -1752,7 +1769,10 @@ k_jac_sell(const __grid_constant__ EvalParams p, const __grid_constant__ GeoTabl
       }
 #endif
 #pragma unroll
-      for (int j0 = 0; j0 < 4; j0 += NID_JAC_W) jac_pixels<PTS, NID_JAC_W, T>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, acc);
+      for (int j0 = 0; j0 < 4; j0 += NID_JAC_W) {
+        if (BULK && j0 >= 2 && half_last && gi + 1 == ngroups) break;  // (small cells only: 5.07 -> 4.98 us; at 4x4 cells 3.43 -> 3.48)
+        jac_pixels<PTS, NID_JAC_W, T>(g, xs, p.rows, p.cols, G, j0, tex2, im1, s, NS, hfx, hfy, wq, acc);
+      }
       G = Gn;
     }
 #endif
