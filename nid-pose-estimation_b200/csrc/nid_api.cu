@@ -68,7 +68,7 @@ EvalParams make_params(nid_ctx* c, int n_jobs) {
   p.sd0 = c->sd0; p.sd1 = c->sd1; p.sd2 = c->sd2; p.sid = c->sid;
   p.sv = c->sv; p.span_mode = c->span_mode ? 1 : 0;
   p.stage_bulk = (c->opt_stage_bulk < 0 ? (long long)c->rb * c->cb < NID_SMALL_CELL_PX : c->opt_stage_bulk) ? 1 : 0;
-  p.sl_off = c->sl_off; p.sl_task = c->sl_task; p.sl_desc = c->sl_desc; p.sl_cell = c->sl_cell; p.nslices = c->nslices;
+  p.sl_off = c->sl_off; p.sl_task = c->sl_task; p.sl_desc = c->sl_desc; p.task_cls = c->task_cls; p.sl_cell = c->sl_cell; p.nslices = c->nslices;
   p.sell_cap = c->sell_cap; p.max_slices = c->max_slices; p.Twc0 = c->Twc0;
   p.tasks = c->tasks; p.ntasks = c->ntasks; p.cell_task_start = c->cell_task_start; p.cell_slice_start = c->cell_slice_start;
   p.cls_task_start = c->cls_task_start; p.span_start = c->span_start; p.wv = c->wv;
@@ -288,6 +288,7 @@ int nid_create(nid_ctx** out, int device, int rows, int cols, int cell, int bins
   OKR(dalloc(&c->sl_off, P * ((size_t)c->max_slices + 1), "sl_off"));
   OKR(dalloc(&c->sl_task, P * (size_t)c->max_slices * 32, "sl_task"));
   OKR(dalloc(&c->sl_desc, P * (size_t)c->max_slices * 32, "sl_desc"));
+  OKR(dalloc(&c->task_cls, P * (size_t)c->max_tasks, "task_cls"));
   OKR(dalloc(&c->sl_cell, P * (size_t)c->max_slices, "sl_cell"));
   OKR(dalloc(&c->task_pos, P * (size_t)c->max_tasks, "task_pos"));
   OKR(dalloc(&c->nslices, P, "nslices"));
@@ -393,7 +394,7 @@ int nid_destroy(nid_ctx* c) {
   void* ptrs[] = {c->pwx, c->pwy, c->pwz, c->im0, c->im1, c->inb0, c->n_c, c->href, c->cam, c->Twc0, c->cnt, c->d_depth,
                   c->d_img64, c->d_flag, c->d_pix, c->d_pix4, c->d_pix4_jobs, c->chunk_cnt, c->d_bsv, c->d_bsi, c->lut_w, c->lut_k, c->poses,
                   c->job_pair, c->aux_pose, c->part, c->jpart, c->hist, c->ht, c->hj, c->err, c->der, c->gn, c->hard,
-                  c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sv, c->sl_off, c->sl_task, c->sl_desc, c->sl_cell, c->nslices, c->task_pos,
+                  c->depth, c->sd0, c->sd1, c->sd2, c->sid, c->sv, c->sl_off, c->sl_task, c->sl_desc, c->task_cls, c->sl_cell, c->nslices, c->task_pos,
                   c->lay_tot, c->lay_base, c->prep_poses, c->depth16, c->depth_factor, c->d_tex2, c->d_pack, c->tasks, c->ntasks, c->cell_task_start, c->cell_slice_start, c->G, c->jpart_s, c->fp1, c->cls_task_start, c->span_start, c->wv};
   for (auto t : c->h_k1tex) if (t) cudaDestroyTextureObject(t);
   for (auto arr : c->k1_arrays) if (arr) cudaFreeArray(arr);

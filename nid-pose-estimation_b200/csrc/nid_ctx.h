@@ -61,6 +61,7 @@ struct EvalParams {
   const int* sl_off;    // [n_pairs][max_slices+1] first pixel slot of every slice (multiples of 128)
   const int* sl_task;   // [n_pairs][max_slices*32] task of every lane, -1 = none
   const int* sl_desc;   // [n_pairs][max_slices*32] that task's descriptor (tasks[].y: count | cls<<9 | cell<<18), 0 = none
+  const unsigned short* task_cls;  // [n_pairs][max_tasks] class of every task (the warp assembly reads two bytes per row)
   const int* sl_cell;   // [n_pairs][max_slices] cell of every slice
   const int* nslices;   // [n_pairs]
   size_t sell_cap;      // pixel slots per pair
@@ -125,6 +126,7 @@ struct nid_ctx {
   int opt_sorted_mode = 0;     // 0 automatic, 1 class tasks, 2 span tasks
   size_t sell_cap = 0;
   int* sl_desc = nullptr;
+  unsigned short* task_cls = nullptr;
   int *sl_off = nullptr, *sl_task = nullptr, *sl_cell = nullptr, *nslices = nullptr, *task_pos = nullptr;
   int max_slices = 0;
   std::vector<int> h_nslices;

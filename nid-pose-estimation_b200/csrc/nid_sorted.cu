@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(NID_LAYOUT_THREADS) k_layout_write(EvalParams 
   int* tp = task_pos + (size_t)pair * p.max_tasks + tb;
   int* st = sl_task + ((size_t)pair * p.max_slices + sb) * 32;
   int* sd = const_cast<int*>(p.sl_desc) + ((size_t)pair * p.max_slices + sb) * 32;
+  unsigned short* tc = const_cast<unsigned short*>(p.task_cls) + (size_t)pair * p.max_tasks + tb;
   for (int t = threadIdx.x; t < s.T; t += blockDim.x) {
     int lo = 0, hi = NID_NCLS;  // class of task t: the last v with ts[v] <= t
     while (hi - lo > 1) {
@@ -372,6 +373,7 @@ __global__ void __launch_bounds__(NID_LAYOUT_THREADS) k_layout_write(EvalParams 
     tp[t] = pb + off + 4 * ln;
     st[rank] = tb + t;
     sd[rank] = len | (v << 9) | (c << 18);
+    tc[t] = (unsigned short)v;
   }
   for (int q = s.T + threadIdx.x; q < s.S * 32; q += blockDim.x) { st[q] = -1; sd[q] = 0; }  // empty lanes of the cell's last slice
   for (int sl = threadIdx.x; sl < s.S; sl += blockDim.x) {
@@ -1412,17 +1414,18 @@ __global__ void __launch_bounds__(NID_ASMW_WARPS * 32, BATCH > 8 ? 1 : NID_ASMW_
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   int cur = -1;
   const int t0 = p.cell_task_start[pair * (p.ncell + 1) + c], t1 = p.cell_task_start[pair * (p.ncell + 1) + c + 1];
-  const int2* tk = p.tasks + (size_t)pair * p.max_tasks;
-  const double* G = p.G + (size_t)job * p.g_stride * B + t;
-  for (int tb = t0; tb < t1; tb += BATCH * NG) {
+  // the lane's rows are t0 + g, t0 + g + NG, ...: one pointer per array, stepped by constant strides
+  const unsigned short* tcp = p.task_cls + (size_t)pair * p.max_tasks + t0 + g;
+  const double* gp = p.G + ((size_t)job * p.g_stride + t0 + g) * B + t;
+  const int rstep = NG * B;
+  for (int tb = t0; tb < t1; tb += BATCH * NG, tcp += BATCH * NG, gp += BATCH * rstep) {
     double x[BATCH];
     int cls[BATCH];
 #pragma unroll
     for (int i = 0; i < BATCH; i++) {
-      const int tt = tb + i * NG + g;
-      const bool in = mine && tt < t1;
-      x[i] = in ? NID_ASM_LD(G + (size_t)tt * B) : 0.0;
-      cls[i] = in ? ((tk[tt].y >> 9) & 0x1ff) : 256;
+      const bool in = mine && tb + i * NG + g < t1;
+      x[i] = in ? NID_ASM_LD(gp + i * rstep) : 0.0;
+      cls[i] = in ? (int)__ldg(tcp + i * NG) : 256;
     }
 #pragma unroll
     for (int i = 0; i < BATCH; i++) {
