@@ -2041,13 +2041,48 @@ __device__ __forceinline__ void jac_tail_cell(const EvalParams& p, int job, int 
   }
 }
 
-// one warp per (job, cell)
+// The same for geometries of many cells with few slices each (64 cells or more; chosen by geometry, so one context always
+// sums the same way): component k of der[6] of one (job, cell) by one thread, in slice order. A cell has 5 slices at the
+// reference's default geometry: a warp per cell with a butterfly per component is mostly idle lanes and shuffles there
+// (0.19 -> 0.10 us per evaluation at 16x16 cells); with one cell of 300 slices it is the other way round (0.13 -> 0.34).
+__device__ __forceinline__ void jac_tail_entry(const EvalParams& p, int job, int pair, int c, int k) {
+  double* der = p.der + ((size_t)job * p.ncell + c) * 6;
+  if (p.n_c[pair * p.ncell + c] < NID_MIN_CELL_POINTS) { der[k] = nan(""); return; }
+  const int s0 = p.cell_slice_start[pair * (p.ncell + 1) + c];
+  const int s1 = p.cell_slice_start[pair * (p.ncell + 1) + c + 1];
+  const double* jp = p.jpart + ((size_t)job * p.max_slices + s0) * 6 + k;
+  double acc = 0.0;
+  int t = s0;
+  for (; t + 8 <= s1; t += 8, jp += 48) {  // eight independent loads, then the ordered additions
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = jp[6 * u];
+#pragma unroll
+    for (int u = 0; u < 8; u++) acc += v[u];
+  }
+  for (; t < s1; t++, jp += 6) acc += jp[0];
+  der[k] = acc;
+}
+
+#define NID_TAIL_PER_THREAD(ncell) ((ncell) >= 64)
+// one warp per (job, cell), or one thread per (job, cell, component)
 __global__ void __launch_bounds__(256) k_jac_final_sorted(EvalParams p, int n_jobs) {
-  const int lane = threadIdx.x & 31;
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (wid >= n_jobs * p.ncell) return;
-  const int job = job_at(p, wid / p.ncell), c = wid % p.ncell;
-  jac_tail_cell(p, job, p.job_pair[job], c, lane);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (NID_TAIL_PER_THREAD(p.ncell)) {
+    if (idx >= n_jobs * p.ncell * 6) return;
+    const int k = idx % 6, c = (idx / 6) % p.ncell;
+    const int job = job_at(p, idx / (6 * p.ncell));
+    jac_tail_entry(p, job, p.job_pair[job], c, k);
+  } else {
+    const int wid = idx >> 5;
+    if (wid >= n_jobs * p.ncell) return;
+    const int job = job_at(p, wid / p.ncell), c = wid % p.ncell;
+    jac_tail_cell(p, job, p.job_pair[job], c, threadIdx.x & 31);
+  }
+}
+static int jac_final_blocks(const nid_ctx* c, int n) {
+  const long long threads = NID_TAIL_PER_THREAD(c->ncell) ? (long long)n * c->ncell * 6 : (long long)n * c->ncell * 32;
+  return (int)((threads + 255) / 256);
 }
 
 // the Gauss-Newton blocks of the launch's jobs written where the host reads them (see k_tail_gn)
@@ -2059,10 +2094,9 @@ __global__ void __launch_bounds__(128) k_gn_out(EvalParams p, double* __restrict
 // its warps finish the cells, then the block is summed exactly as k_gn does (gn_block)), written where the host reads it
 // (gn_out may be pinned host memory: no copy is queued behind the kernel).
 __global__ void __launch_bounds__(256) k_tail_gn(EvalParams p, double* __restrict__ gn_out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int job = job_at(p, blockIdx.x);
   const int pair = p.job_pair[job];
-  for (int c = warp; c < p.ncell; c += blockDim.x >> 5) jac_tail_cell(p, job, pair, c, lane);
+  for (int c = threadIdx.x >> 5; c < p.ncell; c += blockDim.x >> 5) jac_tail_cell(p, job, pair, c, threadIdx.x & 31);  // (at most 32 cells here)
   __syncthreads();  // (the der values this CTA wrote are visible to all of its threads)
   gn_block(p, job, 1, gn_out);
 }
@@ -2545,8 +2579,7 @@ int launch_sorted_pass2(nid_ctx* c, const int* d_list, const int* h_list, int fi
     NID_LAUNCH_CHECK(c, "k_jac_sell");
   }
   ktime_mark(c, 3);
-  const int warps = n * c->ncell;
-  k_jac_final_sorted<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(p, n);
+  k_jac_final_sorted<<<jac_final_blocks(c, n), 256, 0, c->stream>>>(p, n);
   NID_LAUNCH_CHECK(c, "k_jac_final_sorted");
   ktime_mark(c, 4);
   return NID_OK;
@@ -2570,8 +2603,7 @@ int launch_sorted_tail_gn(nid_ctx* c, const int* d_list, const int* h_list, int 
   } else {
     // many cells (the reference's default geometry has 256): one CTA per job would walk them eight at a time (measured
     // ~120 us of a 240 us round); a warp per (job, cell) for the tails, then the block sums
-    const int warps = n * c->ncell;
-    k_jac_final_sorted<<<(warps * 32 + 255) / 256, 256, 0, c->stream>>>(p, n);
+    k_jac_final_sorted<<<jac_final_blocks(c, n), 256, 0, c->stream>>>(p, n);
     NID_LAUNCH_CHECK(c, "k_jac_final_sorted");
     k_gn_out<<<n, 128, 0, c->stream>>>(p, gn_out);
     NID_LAUNCH_CHECK(c, "k_gn_out");
