@@ -48,3 +48,15 @@ def test_no_cpu_fallback(nid):
         pytest.skip("GPU present")
     with pytest.raises(nid.NidError, match="no CUDA device"):
         nid.Context(120, 160, 4, 16)
+
+
+def test_every_run_time_option_is_documented_in_the_header():
+    """nid_set_option's keys are part of the interface: every key the library accepts is described in include/nid_b200.h."""
+    import re
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(ROOT, "nid-pose-estimation_b200", "csrc", "nid_api.cu")).read()
+    keys = set(re.findall(r'strcmp\(key, "([a-z_0-9]+)"\)', src))
+    assert {"path", "task_px", "lm_speculate", "lm_graph"} <= keys
+    hdr = open(os.path.join(ROOT, "include", "nid_b200.h")).read()
+    missing = [k for k in sorted(keys) if f'"{k}"' not in hdr]
+    assert not missing, missing
